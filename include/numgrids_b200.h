@@ -1,0 +1,166 @@
+/* numgrids_b200.h -- C ABI of libnumgrids_b200.so (sm_100a CUDA kernels for the numgrids hot path).
+ *
+ * The reference (maroba/numgrids, pure Python) has no FFI; its seam for this path is the
+ * GridDiff protocol "subclasses set self.operator to a callable NDArray -> NDArray"
+ * (reference numgrids/diff.py:26-28, :48-61) reached through Axis.create_diff_operator
+ * (numgrids/axes.py:124-140), plus the four CurvilinearGrid methods
+ * (numgrids/curvilinear.py:153-317).  Each entry point below replaces the arithmetic behind one
+ * of those callables; the reference lines it replaces are cited per function.  INTEGRATION.md
+ * shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - all arrays are float64, C-contiguous, shape == grid shape (1 <= ndim <= NG_MAX_DIM);
+ *   - "d_" pointers are device pointers, "h_" pointers are host pointers;
+ *   - every function returns 0 on success, else an NG_E* code; ng_last_error() gives the text
+ *     (thread-local);
+ *   - plans are immutable after creation (ng_curv_set_coef excepted, before first use), own only
+ *     their device tables/workspace and never allocate user-visible arrays;
+ *   - device calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream); the *_host calls stage H2D/D2H themselves and return after the result is in h_out;
+ *   - all coefficient tables (FD weights from numpy.linalg.solve, Chebyshev matrix entries,
+ *     FFT multipliers, scale-factor tables) are computed by the host layer exactly as the
+ *     reference computes them and passed in; the library never recomputes them.
+ *   - no CPU fallback: without a usable CUDA device every compute call fails with NG_ECUDA.
+ */
+#ifndef NUMGRIDS_B200_H
+#define NUMGRIDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NG_MAX_DIM 4
+#define NG_MAX_TAPS 16
+#define NG_ABI_VERSION 1
+
+enum ng_status {
+    NG_OK = 0,
+    NG_EINVAL = 1,       /* bad argument */
+    NG_ECUDA = 2,        /* CUDA runtime error / no device */
+    NG_ENOMEM = 3,
+    NG_EUNSUPPORTED = 4
+};
+
+typedef struct ng_plan ng_plan; /* opaque */
+
+/* A broadcastable coefficient array: element (i0..i3) lives at ptr[sum_a i_a*stride[a]];
+ * stride 0 = constant along that axis.  ptr == NULL means "absent". */
+typedef struct ng_coef {
+    const double* ptr;
+    int64_t stride[NG_MAX_DIM];
+} ng_coef;
+
+/* Elementwise work fused around one per-axis apply D.  Evaluation order (each step IEEE
+ * round-to-nearest, never contracted), steps with absent operands skipped:
+ *     x   = pre * in                      (before the derivative; `coeff * v[i]`, curvilinear.py:212-213)
+ *     d   = D(x)
+ *     d   = minuend - d                   (curl: D_j(..) - D_k(..), curvilinear.py:296-298, :312-314)
+ *     d   = post * d                      ((1.0/h_i)*D f, (J/h_i**2)*D f, 1/(h_j h_k)*(..))
+ *     d   = addend + d   |  0.0 + d       (result = result + D_i(..), curvilinear.py:213, :242)
+ *     d   = d / divisor                   (result / J, curvilinear.py:214, :243)
+ *     d   = isfinite(d) ? d : 0.0         (np.where(np.isfinite(..)), curvilinear.py:175, :215, :244)
+ * minuend/addend are full-shape device arrays and may alias `out` (never `in`). */
+typedef struct ng_fuse {
+    ng_coef pre;
+    const double* minuend;
+    ng_coef post;
+    const double* addend;
+    int32_t add_zero;
+    ng_coef divisor;
+    int32_t finite;
+} ng_fuse;
+
+int ng_abi_version(void);
+const char* ng_last_error(void);
+/* number of visible CUDA devices (0 without a driver/GPU; never fails) */
+int ng_device_count(void);
+/* number of kernels this library launched since load (for bench.py's gpu_launches) */
+int64_t ng_launch_count(void);
+
+/* ---- finite differences: FiniteDifferenceDiff / LogDiff ------------------------------------
+ * Replaces findiff.FinDiff(axis, h, order, acc)(f) behind numgrids/diff.py:88 and :259-262.
+ * Three schemes (central on [nb, n-nb), forward on [0, nb), backward on [n-nb, n), nb = n_center/2),
+ * each out = (sum_k w[k]*in[i+off[k]], accumulated in stored order from 0.0) * inv_h_pow.
+ * h_x_div (length shape[axis]) or NULL: LogDiff's `/ meshed_coords[axis]` (diff.py:261-262). */
+int ng_fd_plan_create(int ndim, const int64_t* shape, int axis,
+                      int n_center, const double* w_center, const int32_t* off_center,
+                      int n_side, const double* w_fwd, const int32_t* off_fwd,
+                      const double* w_bwd, const int32_t* off_bwd,
+                      double inv_h_pow, const double* h_x_div, ng_plan** out);
+
+/* ---- Chebyshev: ChebyshevDiff ---------------------------------------------------------------
+ * Replaces `self._diff_matrix * f.reshape(-1)` (numgrids/diff.py:194-197): out_i = sum_j M[i][j] in_j
+ * along `axis`, accumulated sequentially from 0.0 with separately rounded multiply and add,
+ * j ascending (descending_k = 0) or descending (1) -- the order scipy's matvec uses on the
+ * reference's Kronecker matrix.  h_M is the n x n row-major 1-D matrix. */
+int ng_cheb_plan_create(int ndim, const int64_t* shape, int axis,
+                        const double* h_M, int descending_k, ng_plan** out);
+
+/* ---- periodic spectral derivative: FFTDiff --------------------------------------------------
+ * Replaces real(ifft(W * fft(f, axis), axis)) (numgrids/diff.py:133-143).  h_W_re_im holds the n
+ * complex multipliers of diff.py:117-125 interleaved (re, im).  Power-of-two n uses the in-shared-
+ * memory FFT kernel; other n use h_D (n x n row-major real matrix F^-1 diag(W) F, the matrix of
+ * diff.py:145-157) applied as a dense contraction (NULL h_D with non-power-of-two n -> NG_EINVAL). */
+int ng_fft_plan_create(int ndim, const int64_t* shape, int axis,
+                       const double* h_W_re_im, const double* h_D, ng_plan** out);
+
+/* ---- apply ------------------------------------------------------------------------------------
+ * GridDiff.__call__ (numgrids/diff.py:48-61).  d_out must not alias d_in. */
+int ng_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream);
+int ng_apply_fused(const ng_plan* plan, const double* d_in, double* d_out,
+                   const ng_fuse* fuse, void* stream);
+/* Same from host buffers (pinned or pageable): H2D, kernel, D2H, synchronous. */
+int ng_apply_host(ng_plan* plan, const double* h_in, double* h_out);
+/* Slab variant for a finite-difference plan whose `axis` is sharded across ranks: d_lo_halo /
+ * d_hi_halo hold the nb neighbour planes [rows][nb] (rows = product of the other extents) or are
+ * NULL on the global boundary, where the one-sided schemes are used. */
+int ng_fd_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
+                     const double* d_lo_halo, const double* d_hi_halo, void* stream);
+/* Pack the first / last `nb` planes along the plan's axis into contiguous [rows][nb] buffers. */
+int ng_fd_pack_halo(const ng_plan* plan, const double* d_in, double* d_lo_planes,
+                    double* d_hi_planes, void* stream);
+int ng_plan_halo_width(const ng_plan* plan);
+
+/* ---- fused Cartesian Laplacian ----------------------------------------------------------------
+ * The reference idiom Diff(g,2,0)(f) + Diff(g,2,1)(f) + ... on equidistant axes (reference
+ * tests/test_diff.py:29-39, docs/guide/differentiation.md) in ONE pass: per-axis sums as in
+ * ng_fd_plan_create, combined as ((d0 + d1) + d2)...; axis_plans are ndim FD plans (one per axis,
+ * same shape).  Slab variant: last axis sharded, halos as in ng_fd_apply_slab. */
+int ng_fdlap_plan_create(int ndim, const int64_t* shape, ng_plan* const* axis_plans, ng_plan** out);
+int ng_fdlap_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream);
+int ng_fdlap_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
+                        const double* d_lo_halo, const double* d_hi_halo, void* stream);
+int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out);
+
+/* ---- curvilinear composites: CurvilinearGrid.gradient/divergence/laplacian/curl ---------------
+ * numgrids/curvilinear.py:153-317.  axis_plans[i] is the first-derivative plan of axis i
+ * (curvilinear.py:142-149).  Coefficients are evaluated on the host exactly as the reference does
+ * (J/h_i**2, J/h_i, 1.0/h_i, h_i, 1.0/(h_j*h_k), J) and registered with ng_curv_set_coef in
+ * broadcast-compact form (`count` doubles at h_values, element strides per axis, 0 = broadcast). */
+enum ng_coef_kind {
+    NG_COEF_J = 0,        /* index ignored */
+    NG_COEF_LAP = 1,      /* J / h_i**2        index i */
+    NG_COEF_DIV = 2,      /* J / h_i           index i */
+    NG_COEF_GRAD = 3,     /* 1.0 / h_i         index i */
+    NG_COEF_H = 4,        /* h_i               index i */
+    NG_COEF_CURL = 5      /* 1.0 / (h_j * h_k) index = output component (0 for 2-D) */
+};
+int ng_curv_plan_create(int ndim, const int64_t* shape, ng_plan* const* axis_plans, ng_plan** out);
+int ng_curv_set_coef(ng_plan* plan, int kind, int index, const double* h_values, int64_t count,
+                     const int64_t* stride);
+int ng_curv_laplacian(ng_plan* plan, const double* d_f, double* d_out, void* stream);
+int ng_curv_gradient(ng_plan* plan, const double* d_f, double* const* d_out, void* stream);
+int ng_curv_divergence(ng_plan* plan, const double* const* d_v, double* d_out, void* stream);
+int ng_curv_curl(ng_plan* plan, const double* const* d_v, double* const* d_out, void* stream);
+
+/* ---- lifetime ---------------------------------------------------------------------------------*/
+int ng_plan_destroy(ng_plan* plan);
+/* bytes of device memory owned by the plan (tables + workspace + host-call staging) */
+int64_t ng_plan_device_bytes(const ng_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUMGRIDS_B200_H */

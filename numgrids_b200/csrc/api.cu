@@ -1,0 +1,378 @@
+// api.cu -- the C ABI of libnumgrids_b200.so (declared in include/numgrids_b200.h): plan creation,
+// table upload, dispatch and host-buffer staging.  All validation that maps to Python exceptions
+// in the reference stays in the Python layer; this file rejects only what would make a kernel
+// read out of bounds.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+std::atomic<long long> g_ng_launches{0};
+static thread_local char t_err[512] = "";
+
+void ng_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+int ng_fdlap_upload_params(ng_plan* p);
+
+namespace {
+
+int set_shape(ng_plan* p, int ndim, const int64_t* shape, int axis) {
+    NG_REQUIRE(ndim >= 1 && ndim <= NG_MAX_DIM, "ndim must be in 1..%d, got %d", NG_MAX_DIM, ndim);
+    NG_REQUIRE(shape != nullptr, "shape is NULL");
+    NG_REQUIRE(axis >= 0 && axis < ndim, "axis %d out of range for ndim %d", axis, ndim);
+    p->ndim = ndim;
+    p->axis = axis;
+    p->size = 1;
+    for (int a = 0; a < NG_MAX_DIM; ++a) p->shape[a] = 1;
+    for (int a = 0; a < ndim; ++a) {
+        NG_REQUIRE(shape[a] >= 1, "shape[%d] = %lld must be positive", a, (long long)shape[a]);
+        p->shape[a] = shape[a];
+        p->size *= shape[a];
+    }
+    p->outer = 1;
+    p->inner = 1;
+    for (int a = 0; a < axis; ++a) p->outer *= shape[a];
+    for (int a = axis + 1; a < ndim; ++a) p->inner *= shape[a];
+    p->n = shape[axis];
+    return NG_OK;
+}
+
+int upload(ng_plan* p, double** d_dst, const double* h_src, i64 count) {
+    NG_CUDA_OK(cudaMalloc((void**)d_dst, sizeof(double) * (size_t)(count > 0 ? count : 1)));
+    p->device_bytes += sizeof(double) * count;
+    if (count > 0)
+        NG_CUDA_OK(cudaMemcpy(*d_dst, h_src, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice));
+    return NG_OK;
+}
+
+int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        ng_set_error("no usable CUDA device (%s); numgrids_b200 has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        return NG_ECUDA;
+    }
+    return NG_OK;
+}
+
+int ensure_stage(ng_plan* p, int nbuf_in) {
+    const i64 need = p->size * nbuf_in;
+    if (p->stage_elems >= need && p->d_stage_in && p->d_stage_out) return NG_OK;
+    if (p->d_stage_in) cudaFree(p->d_stage_in);
+    if (p->d_stage_out) cudaFree(p->d_stage_out);
+    p->d_stage_in = p->d_stage_out = nullptr;
+    NG_CUDA_OK(cudaMalloc((void**)&p->d_stage_in, sizeof(double) * (size_t)need));
+    NG_CUDA_OK(cudaMalloc((void**)&p->d_stage_out, sizeof(double) * (size_t)p->size));
+    p->device_bytes += sizeof(double) * (need + p->size - (p->stage_elems > 0 ? p->stage_elems + p->size : 0));
+    p->stage_elems = need;
+    return NG_OK;
+}
+
+FuseDev no_fuse(const ng_plan* p) {
+    FuseDev F;
+    memset(&F, 0, sizeof(F));
+    for (int a = 0; a < NG_MAX_DIM; ++a) F.shape[a] = p->shape[a];
+    F.vec_axis = 0;
+    for (int a = 0; a < NG_MAX_DIM; ++a) if (p->shape[a] > 1) F.vec_axis = a;
+    return F;
+}
+
+}  // namespace
+
+void ng_fuse_to_dev(const ng_plan* p, const ng_fuse* f, FuseDev* out) {
+    *out = no_fuse(p);
+    if (!f) return;
+    auto cp = [](CoefDev& d, const ng_coef& s) {
+        d.ptr = s.ptr;
+        for (int a = 0; a < NG_MAX_DIM; ++a) d.s[a] = s.ptr ? s.stride[a] : 0;
+    };
+    cp(out->pre, f->pre);
+    cp(out->post, f->post);
+    cp(out->div, f->divisor);
+    out->minuend = f->minuend;
+    out->addend = f->addend;
+    out->add_zero = f->add_zero;
+    out->finite = f->finite;
+    out->any = (f->pre.ptr || f->post.ptr || f->divisor.ptr || f->minuend || f->addend ||
+                f->add_zero || f->finite) ? 1 : 0;
+}
+
+int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                 cudaStream_t st) {
+    switch (p->kind) {
+        case PK_FD: return ng_fd_launch(p, in, out, F, nullptr, nullptr, st);
+        case PK_CHEB: return ng_dense_launch(p, in, out, F, st);
+        case PK_FFT: return ng_fft_launch(p, in, out, F, st);
+        default:
+            ng_set_error("plan kind %d cannot be applied with ng_apply", p->kind);
+            return NG_EINVAL;
+    }
+}
+
+extern "C" {
+
+int ng_abi_version(void) { return NG_ABI_VERSION; }
+const char* ng_last_error(void) { return t_err; }
+int64_t ng_launch_count(void) { return g_ng_launches.load(); }
+
+int ng_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ng_fd_plan_create(int ndim, const int64_t* shape, int axis, int n_center,
+                      const double* w_center, const int32_t* off_center, int n_side,
+                      const double* w_fwd, const int32_t* off_fwd, const double* w_bwd,
+                      const int32_t* off_bwd, double inv_h_pow, const double* h_x_div,
+                      ng_plan** out) {
+    NG_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    NG_REQUIRE(n_center >= 1 && n_center <= NG_MAX_TAPS && n_side >= 1 && n_side <= NG_MAX_TAPS,
+               "tap counts (%d central, %d one-sided) must be in 1..%d", n_center, n_side, NG_MAX_TAPS);
+    NG_REQUIRE(w_center && off_center && w_fwd && off_fwd && w_bwd && off_bwd, "NULL tap table");
+    ng_plan* p = new (std::nothrow) ng_plan();
+    if (!p) { ng_set_error("out of host memory"); return NG_ENOMEM; }
+    int rc = set_shape(p, ndim, shape, axis);
+    if (rc) { delete p; return rc; }
+    p->kind = PK_FD;
+    FdTables& T = p->fd;
+    memset(&T, 0, sizeof(T));
+    T.n_center = n_center;
+    T.n_side = n_side;
+    T.nb = n_center / 2;
+    T.inv_h_pow = inv_h_pow;
+    const i64 n = p->n;
+    bool ok = n >= 2 * (i64)T.nb;
+    for (int k = 0; k < n_center; ++k) {
+        T.wc[k] = w_center[k]; T.oc[k] = off_center[k];
+        if (off_center[k] < -T.nb || off_center[k] > T.nb) ok = false;
+    }
+    for (int k = 0; k < n_side; ++k) {
+        T.wf[k] = w_fwd[k]; T.of[k] = off_fwd[k];
+        T.wb[k] = w_bwd[k]; T.ob[k] = off_bwd[k];
+        // forward scheme is used at i in [0, nb), backward at [n-nb, n): all taps must stay inside
+        if (off_fwd[k] < 0 || (T.nb - 1) + off_fwd[k] >= n) ok = false;
+        if (off_bwd[k] > 0 || (n - T.nb) + off_bwd[k] < 0) ok = false;
+    }
+    if (!ok) {
+        ng_set_error("axis of %lld points is too short for a %d/%d-tap finite-difference stencil",
+                     (long long)n, n_center, n_side);
+        delete p;
+        return NG_EINVAL;
+    }
+    if (h_x_div) {
+        rc = require_device();
+        if (!rc) rc = upload(p, &p->d_xdiv, h_x_div, n);
+        if (rc) { ng_plan_destroy(p); return rc; }
+    }
+    *out = p;
+    return NG_OK;
+}
+
+int ng_cheb_plan_create(int ndim, const int64_t* shape, int axis, const double* h_M,
+                        int descending_k, ng_plan** out) {
+    NG_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    NG_REQUIRE(h_M != nullptr, "matrix is NULL");
+    ng_plan* p = new (std::nothrow) ng_plan();
+    if (!p) { ng_set_error("out of host memory"); return NG_ENOMEM; }
+    int rc = set_shape(p, ndim, shape, axis);
+    if (!rc) rc = require_device();
+    if (rc) { delete p; return rc; }
+    p->kind = PK_CHEB;
+    p->descending = descending_k ? 1 : 0;
+    const i64 n = p->n;
+    std::vector<double> Mt((size_t)(n * n));
+    for (i64 i = 0; i < n; ++i)
+        for (i64 k = 0; k < n; ++k) Mt[(size_t)(k * n + i)] = h_M[i * n + k];
+    rc = upload(p, &p->d_M, h_M, n * n);
+    if (!rc) rc = upload(p, &p->d_Mt, Mt.data(), n * n);
+    if (rc) { ng_plan_destroy(p); return rc; }
+    *out = p;
+    return NG_OK;
+}
+
+int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h_W_re_im,
+                       const double* h_D, ng_plan** out) {
+    NG_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    NG_REQUIRE(h_W_re_im != nullptr, "multiplier table is NULL");
+    ng_plan* p = new (std::nothrow) ng_plan();
+    if (!p) { ng_set_error("out of host memory"); return NG_ENOMEM; }
+    int rc = set_shape(p, ndim, shape, axis);
+    if (!rc) rc = require_device();
+    if (rc) { delete p; return rc; }
+    p->kind = PK_FFT;
+    const i64 n = p->n;
+    const bool pow2 = n >= 2 && (n & (n - 1)) == 0 && n <= 8192;
+    static const bool force_dense = getenv("NG_FFT_DENSE") && atoi(getenv("NG_FFT_DENSE"));
+    if (pow2 && !(force_dense && h_D)) {
+        p->fft_pow2 = 1;
+        int l = 0;
+        while ((1LL << l) < n) ++l;
+        p->log2n = l;
+        std::vector<double> Wbr((size_t)(2 * n)), tw((size_t)n);   // tw: n/2 complex
+        for (i64 k = 0; k < n; ++k) {
+            i64 r = 0;
+            for (int b = 0; b < l; ++b) if (k & (1LL << b)) r |= 1LL << (l - 1 - b);
+            // position r of the DIF output holds bin k
+            Wbr[(size_t)(2 * r)] = h_W_re_im[2 * k] / (double)n;
+            Wbr[(size_t)(2 * r + 1)] = h_W_re_im[2 * k + 1] / (double)n;
+        }
+        // twiddles exp(-2 pi i j / n), j < n/2, evaluated in long double and rounded once
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (i64 j = 0; j < n / 2; ++j) {
+            const long double a = two_pi * (long double)j / (long double)n;
+            tw[(size_t)(2 * j)] = (double)cosl(a);
+            tw[(size_t)(2 * j + 1)] = (double)(-sinl(a));
+        }
+        rc = upload(p, &p->d_W, Wbr.data(), 2 * n);
+        if (!rc) rc = upload(p, &p->d_tw, tw.data(), n);
+    } else {
+        if (!h_D) {
+            ng_set_error("n = %lld is not a power of two <= 8192: the dense spectral matrix is required",
+                         (long long)n);
+            delete p;
+            return NG_EINVAL;
+        }
+        p->use_fma = 1;
+        std::vector<double> Mt((size_t)(n * n));
+        for (i64 i = 0; i < n; ++i)
+            for (i64 k = 0; k < n; ++k) Mt[(size_t)(k * n + i)] = h_D[i * n + k];
+        rc = upload(p, &p->d_M, h_D, n * n);
+        if (!rc) rc = upload(p, &p->d_Mt, Mt.data(), n * n);
+    }
+    if (rc) { ng_plan_destroy(p); return rc; }
+    *out = p;
+    return NG_OK;
+}
+
+int ng_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream) {
+    return ng_apply_fused(plan, d_in, d_out, nullptr, stream);
+}
+
+int ng_apply_fused(const ng_plan* plan, const double* d_in, double* d_out, const ng_fuse* fuse,
+                   void* stream) {
+    NG_REQUIRE(plan && d_in && d_out, "ng_apply: NULL plan or buffer");
+    NG_REQUIRE(d_in != d_out, "ng_apply: output must not alias input");
+    FuseDev F;
+    ng_fuse_to_dev(plan, fuse, &F);
+    return ng_apply_any(plan, d_in, d_out, F, (cudaStream_t)stream);
+}
+
+int ng_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
+    NG_REQUIRE(plan && h_in && h_out, "ng_apply_host: NULL plan or buffer");
+    int rc = require_device();
+    if (rc) return rc;
+    rc = ensure_stage(plan, 1);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * (size_t)plan->size;
+    NG_CUDA_OK(cudaMemcpyAsync(plan->d_stage_in, h_in, bytes, cudaMemcpyHostToDevice, 0));
+    FuseDev F = no_fuse(plan);
+    rc = ng_apply_any(plan, plan->d_stage_in, plan->d_stage_out, F, 0);
+    if (rc) return rc;
+    NG_CUDA_OK(cudaMemcpyAsync(h_out, plan->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
+    NG_CUDA_OK(cudaStreamSynchronize(0));
+    return NG_OK;
+}
+
+int ng_plan_halo_width(const ng_plan* plan) {
+    if (!plan) return 0;
+    if (plan->kind == PK_FD) return plan->fd.nb;
+    if (plan->kind == PK_FDLAP) return plan->lap[plan->ndim - 1].nb;
+    return 0;
+}
+
+int ng_fd_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
+                     const double* d_lo_halo, const double* d_hi_halo, void* stream) {
+    NG_REQUIRE(plan && plan->kind == PK_FD, "ng_fd_apply_slab: finite-difference plan required");
+    NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fd_apply_slab: bad buffers");
+    FuseDev F = no_fuse(plan);
+    return ng_fd_launch(plan, d_in, d_out, F, d_lo_halo, d_hi_halo, (cudaStream_t)stream);
+}
+
+int ng_fdlap_plan_create(int ndim, const int64_t* shape, ng_plan* const* axis_plans,
+                         ng_plan** out) {
+    NG_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    NG_REQUIRE(axis_plans != nullptr, "axis_plans is NULL");
+    ng_plan* p = new (std::nothrow) ng_plan();
+    if (!p) { ng_set_error("out of host memory"); return NG_ENOMEM; }
+    int rc = set_shape(p, ndim, shape, ndim - 1 >= 0 ? ndim - 1 : 0);
+    if (!rc) rc = require_device();
+    if (rc) { delete p; return rc; }
+    p->kind = PK_FDLAP;
+    for (int a = 0; a < ndim; ++a) {
+        const ng_plan* q = axis_plans[a];
+        bool ok = q && q->kind == PK_FD && q->ndim == ndim && q->axis == a && !q->d_xdiv;
+        for (int b = 0; ok && b < ndim; ++b) ok = q->shape[b] == p->shape[b];
+        if (!ok) {
+            ng_set_error("axis_plans[%d] must be an equidistant FD plan of the same shape along axis %d", a, a);
+            delete p;
+            return NG_EINVAL;
+        }
+        p->lap[a] = q->fd;
+    }
+    rc = ng_fdlap_upload_params(p);
+    if (rc) { ng_plan_destroy(p); return rc; }
+    *out = p;
+    return NG_OK;
+}
+
+int ng_fdlap_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream) {
+    return ng_fdlap_apply_slab(plan, d_in, d_out, nullptr, nullptr, stream);
+}
+
+int ng_fdlap_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
+                        const double* d_lo_halo, const double* d_hi_halo, void* stream) {
+    NG_REQUIRE(plan && plan->kind == PK_FDLAP, "ng_fdlap_apply: Laplacian plan required");
+    NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fdlap_apply: bad buffers");
+    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, (cudaStream_t)stream);
+}
+
+int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
+    NG_REQUIRE(plan && plan->kind == PK_FDLAP && h_in && h_out, "ng_fdlap_apply_host: bad arguments");
+    int rc = require_device();
+    if (rc) return rc;
+    rc = ensure_stage(plan, 1);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * (size_t)plan->size;
+    NG_CUDA_OK(cudaMemcpyAsync(plan->d_stage_in, h_in, bytes, cudaMemcpyHostToDevice, 0));
+    rc = ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, 0);
+    if (rc) return rc;
+    NG_CUDA_OK(cudaMemcpyAsync(h_out, plan->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
+    NG_CUDA_OK(cudaStreamSynchronize(0));
+    return NG_OK;
+}
+
+int64_t ng_plan_device_bytes(const ng_plan* plan) { return plan ? plan->device_bytes : 0; }
+
+int ng_plan_destroy(ng_plan* p) {
+    if (!p) return NG_OK;
+    auto fr = [](double* q) { if (q) cudaFree(q); };
+    fr(p->d_xdiv); fr(p->d_M); fr(p->d_Mt); fr(p->d_W); fr(p->d_tw); fr(p->d_work);
+    fr(p->d_stage_in); fr(p->d_stage_out);
+    fr(p->cJ.d_ptr);
+    for (int a = 0; a < NG_MAX_DIM; ++a) {
+        fr(p->cLap[a].d_ptr); fr(p->cDiv[a].d_ptr); fr(p->cGrad[a].d_ptr);
+        fr(p->cH[a].d_ptr); fr(p->cCurl[a].d_ptr);
+    }
+    delete p;
+    return NG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// common.cuh -- plan object, error plumbing and the fused-epilogue device helpers shared by all
+// translation units of libnumgrids_b200.so.  sm_100a only; compiled with -fmad=false so that
+// every `a*b+c` in the bit-exact paths stays a separately rounded DMUL + DADD (the reference's
+// NumPy/SciPy arithmetic); the FFT path opts in to FMA with explicit fma().
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/numgrids_b200.h"
+
+typedef long long i64;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void ng_set_error(const char* fmt, ...);
+extern std::atomic<long long> g_ng_launches;
+
+#define NG_CUDA_OK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ng_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                        \
+            return NG_ECUDA;                                                               \
+        }                                                                                  \
+    } while (0)
+
+#define NG_LAUNCH_CHECK()                                                              \
+    do {                                                                               \
+        g_ng_launches.fetch_add(1, std::memory_order_relaxed);                         \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess) {                                                       \
+            ng_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                         __FILE__, __LINE__);                                          \
+            return NG_ECUDA;                                                           \
+        }                                                                              \
+    } while (0)
+
+#define NG_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            ng_set_error(__VA_ARGS__);   \
+            return NG_EINVAL;            \
+        }                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// tables passed to kernels by value
+// ---------------------------------------------------------------------------------------------
+struct FdTables {
+    int n_center, n_side, nb;
+    int oc[NG_MAX_TAPS], of[NG_MAX_TAPS], ob[NG_MAX_TAPS];
+    double wc[NG_MAX_TAPS], wf[NG_MAX_TAPS], wb[NG_MAX_TAPS];
+    double inv_h_pow;
+};
+
+struct CoefDev {
+    const double* ptr;
+    i64 s[NG_MAX_DIM];
+};
+
+struct FuseDev {
+    CoefDev pre, post, div;
+    const double* minuend;
+    const double* addend;
+    int add_zero;
+    int finite;
+    int any;              // 0 = plain apply
+    int vec_axis;         // innermost grid axis with extent > 1 (the axis a double2 pair runs along)
+    i64 shape[NG_MAX_DIM];
+};
+
+enum PlanKind { PK_FD = 1, PK_CHEB = 2, PK_FFT = 3, PK_FDLAP = 4, PK_CURV = 5 };
+
+struct CoefHost {           // device-resident compact coefficient table owned by a curv plan
+    double* d_ptr = nullptr;
+    i64 count = 0;
+    i64 stride[NG_MAX_DIM] = {0, 0, 0, 0};
+};
+
+struct ng_plan {
+    int kind = 0;
+    int ndim = 0;
+    int axis = 0;
+    i64 shape[NG_MAX_DIM] = {1, 1, 1, 1};
+    i64 size = 1;
+    i64 outer = 1, n = 1, inner = 1;   // [outer][n][inner] view around `axis`
+    i64 device_bytes = 0;
+
+    // PK_FD
+    FdTables fd;
+    double* d_xdiv = nullptr;
+
+    // PK_CHEB (and the dense fallback of PK_FFT)
+    double* d_M = nullptr;    // [n][n] row-major
+    double* d_Mt = nullptr;   // transposed copy (k-major) for broadcast-friendly panel loads
+    int descending = 0;
+    int use_fma = 0;
+
+    // PK_FFT
+    int fft_pow2 = 0;
+    int log2n = 0;
+    double* d_W = nullptr;    // [n][2]
+    double* d_tw = nullptr;   // [n][2] forward twiddles exp(-2 pi i k / n)
+
+    // PK_FDLAP
+    FdTables lap[NG_MAX_DIM];
+
+    // PK_CURV
+    ng_plan* axis_plans[NG_MAX_DIM] = {nullptr, nullptr, nullptr, nullptr};
+    CoefHost cJ, cLap[NG_MAX_DIM], cDiv[NG_MAX_DIM], cGrad[NG_MAX_DIM], cH[NG_MAX_DIM],
+        cCurl[NG_MAX_DIM];
+    double* d_work = nullptr;
+
+    // host-call staging (ng_apply_host / ng_fdlap_apply_host)
+    double* d_stage_in = nullptr;
+    double* d_stage_out = nullptr;
+    i64 stage_elems = 0;
+};
+
+// per-kind entry points implemented in the other translation units
+int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                 const double* lo, const double* hi, cudaStream_t st);
+int ng_dense_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                    cudaStream_t st);
+int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                  cudaStream_t st);
+int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
+                    const double* hi, cudaStream_t st);
+int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                 cudaStream_t st);
+void ng_fuse_to_dev(const ng_plan* p, const ng_fuse* f, FuseDev* out);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+struct Idx4 {
+    i64 i[NG_MAX_DIM];
+};
+
+__device__ __forceinline__ Idx4 unravel4(i64 lin, const i64* shape) {
+    Idx4 r;
+    if (lin < 0x7fffffffLL) {   // 32-bit fast path (all config sizes)
+        unsigned t = (unsigned)lin;
+        unsigned s3 = (unsigned)shape[3], s2 = (unsigned)shape[2], s1 = (unsigned)shape[1];
+        unsigned q = t / s3; r.i[3] = t - q * s3; t = q;
+        q = t / s2; r.i[2] = t - q * s2; t = q;
+        q = t / s1; r.i[1] = t - q * s1; r.i[0] = q;
+    } else {
+        i64 t = lin;
+        r.i[3] = t % shape[3]; t /= shape[3];
+        r.i[2] = t % shape[2]; t /= shape[2];
+        r.i[1] = t % shape[1]; r.i[0] = t / shape[1];
+    }
+    return r;
+}
+
+__device__ __forceinline__ i64 coef_off(const CoefDev& c, const Idx4& ix) {
+    return ix.i[0] * c.s[0] + ix.i[1] * c.s[1] + ix.i[2] * c.s[2] + ix.i[3] * c.s[3];
+}
+
+// The elementwise tail of ng_fuse (see numgrids_b200.h for the order); `lin` is the linear index
+// of the output element, `ix` its multi-index.
+__device__ __forceinline__ double fuse_tail(const FuseDev& F, double d, i64 lin, const Idx4& ix) {
+    if (F.minuend) d = __dsub_rn(F.minuend[lin], d);
+    if (F.post.ptr) d = __dmul_rn(F.post.ptr[coef_off(F.post, ix)], d);
+    if (F.addend) d = __dadd_rn(F.addend[lin], d);
+    else if (F.add_zero) d = __dadd_rn(0.0, d);
+    if (F.div.ptr) d = __ddiv_rn(d, F.div.ptr[coef_off(F.div, ix)]);
+    if (F.finite) d = isfinite(d) ? d : 0.0;
+    return d;
+}

@@ -1,0 +1,237 @@
+// fdlap3d.cu -- 3-D production kernel of the fused Cartesian FD Laplacian (see fdlap.cu).
+//
+// Shape (nx, ny, nz), z contiguous; acc=4 second-derivative tables (central offsets -2..2,
+// one-sided 6 taps) -- the reference default `Diff(g, 2, a)` (numgrids/api.py:31, acc=4).
+//
+// Mapping (HBM-bound, 16 B/point; co-limited by the FP64 pipe: 33 non-contractable DMUL/DADD per
+// point because parity forbids FMA):
+//   * a warp covers 64 contiguous z (one double2 = 128-bit LDG/STG per lane) x R rows of y;
+//     a CTA stacks WY warps along y; grid = (z tiles, y tiles, x chunks);
+//   * the CTA marches along x keeping the 5-plane x window of its own points in registers, so
+//     every input point is fetched from HBM once (plus 4 planes of overlap per x chunk);
+//   * y neighbours: R own rows + 4 halo rows (L1/L2 hits: they are the own rows of the
+//     neighbouring warps); z neighbours: the adjacent lanes' double2 by warp shuffle, tile-edge
+//     lanes load the 16 B next to the tile (or the slab halo);
+//   * the first/last 2 indices of each axis use the one-sided schemes, recomputed by the owning
+//     threads from direct loads in warp-uniform branches (rare).
+// Arithmetic is the reference's, bit for bit: per axis acc = 0.0; acc = acc + w_k*f_k in stored
+// tap order; d_a = acc * inv_h2_a; out = (d_x + d_y) + d_z.
+#include "common.cuh"
+
+namespace {
+
+struct Lap3W {
+    double wc[3][5], wf[3][6], wb[3][6], ih[3];
+};
+
+__device__ __forceinline__ double2 ld2(const double* p) {
+    return *reinterpret_cast<const double2*>(p);
+}
+__device__ __forceinline__ double2 shfl_up2(double2 v) {
+    return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ double2 shfl_dn2(double2 v) {
+    return make_double2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ double mad_rn(double acc, double w, double f) {
+    return __dadd_rn(acc, __dmul_rn(w, f));
+}
+// 5-tap central sum on two lanes of a double2 column
+__device__ __forceinline__ double2 central5(const double* w, double2 a, double2 b, double2 c,
+                                            double2 d, double2 e, double ih) {
+    double sx = 0.0, sy = 0.0;
+    sx = mad_rn(sx, w[0], a.x); sy = mad_rn(sy, w[0], a.y);
+    sx = mad_rn(sx, w[1], b.x); sy = mad_rn(sy, w[1], b.y);
+    sx = mad_rn(sx, w[2], c.x); sy = mad_rn(sy, w[2], c.y);
+    sx = mad_rn(sx, w[3], d.x); sy = mad_rn(sy, w[3], d.y);
+    sx = mad_rn(sx, w[4], e.x); sy = mad_rn(sy, w[4], e.y);
+    return make_double2(__dmul_rn(sx, ih), __dmul_rn(sy, ih));
+}
+// 6-tap one-sided sum along a strided direction: taps at p[k*step], k = 0..5 (step may be negative)
+__device__ __forceinline__ double2 onesided6(const double* w, const double* p, i64 step, double ih) {
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double2 v = ld2(p + k * step);
+        sx = mad_rn(sx, w[k], v.x);
+        sy = mad_rn(sy, w[k], v.y);
+    }
+    return make_double2(__dmul_rn(sx, ih), __dmul_rn(sy, ih));
+}
+// one-sided along the contiguous axis for a single output: taps p[k*dir]
+__device__ __forceinline__ double onesided6_z(const double* w, const double* p, int dir, double ih) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s = mad_rn(s, w[k], p[k * dir]);
+    return __dmul_rn(s, ih);
+}
+
+template <int R, int WY>
+__global__ void __launch_bounds__(32 * WY)
+fdlap3d_march_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
+                     int xchunk, Lap3W W, const double* __restrict__ lo,
+                     const double* __restrict__ hi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int z0 = blockIdx.x * 64;
+    const int z = z0 + 2 * lane;
+    const int y0 = (blockIdx.y * WY + warp) * R;
+    const int xs = blockIdx.z * xchunk;
+    const int xe = min(nx, xs + xchunk);
+    if (y0 >= ny) return;                       // warp-uniform
+    const bool zok = z < nz;                    // nz is even: the pair is valid or not as a whole
+    const i64 sy = nz, sx = (i64)ny * nz;
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    // which lane holds the last pair of the pencil (z = nz-2) in this tile, if any
+    const bool tile_has_zlo = (z0 == 0);
+    const bool tile_has_zhi = (z0 + 64 >= nz);
+    const bool fix_zlo = tile_has_zlo && lo == nullptr;
+    const bool fix_zhi = tile_has_zhi && hi == nullptr;
+
+    // register window: w[j][r] = plane (x-2+j), row y0+r, this lane's pair
+    double2 w[5][R];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int xp = xs - 2 + j;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool ok = zok && xp >= 0 && xp < nx && (y0 + r) < ny;
+            w[j + 1][r] = ok ? ld2(in + xp * sx + (i64)(y0 + r) * sy + z) : zero2;
+        }
+    }
+
+    for (int x = xs; x < xe; ++x) {
+        // ---- shift window, fetch plane x+2
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < R; ++r) w[j][r] = w[j + 1][r];
+        {
+            const int xp = x + 2;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool ok = zok && xp < nx && (y0 + r) < ny;
+                w[4][r] = ok ? ld2(in + xp * sx + (i64)(y0 + r) * sy + z) : zero2;
+            }
+        }
+        const double* plane = in + x * sx;
+        // ---- y column of the centre plane: rows y0-2 .. y0+R+1
+        double2 col[R + 4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) col[r + 2] = w[2][r];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ya = y0 - 2 + h, yb = y0 + R + h;
+            col[h] = (zok && ya >= 0) ? ld2(plane + (i64)ya * sy + z) : zero2;
+            col[R + 2 + h] = (zok && yb < ny) ? ld2(plane + (i64)yb * sy + z) : zero2;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int y = y0 + r;
+            if (y >= ny) break;                 // warp-uniform
+            const double* row = plane + (i64)y * sy;
+            const double2 c = w[2][r];
+            // ---- z neighbours: adjacent lanes, tile-edge lanes from memory / slab halo
+            double2 L = shfl_up2(c), Rn = shfl_dn2(c);
+            if (lane == 0) {
+                if (z0 > 0) L = ld2(row + z0 - 2);
+                else if (lo) L = ld2(lo + ((i64)x * ny + y) * 2);
+                else L = zero2;
+            }
+            if (lane == 31) {
+                if (z0 + 64 < nz) Rn = ld2(row + z0 + 64);
+                else if (z0 + 64 == nz && hi) Rn = ld2(hi + ((i64)x * ny + y) * 2);
+                else Rn = zero2;
+            }
+            if (tile_has_zhi && hi && z == nz - 2 && lane != 31)      // partial last tile in slab mode
+                Rn = ld2(hi + ((i64)x * ny + y) * 2);
+            // ---- central sums
+            double2 dx = central5(W.wc[0], w[0][r], w[1][r], c, w[3][r], w[4][r], W.ih[0]);
+            double2 dy = central5(W.wc[1], col[r], col[r + 1], c, col[r + 3], col[r + 4], W.ih[1]);
+            double2 dz;
+            {
+                double s0 = 0.0, s1 = 0.0;
+                const double* wz = W.wc[2];
+                s0 = mad_rn(s0, wz[0], L.x);  s1 = mad_rn(s1, wz[0], L.y);
+                s0 = mad_rn(s0, wz[1], L.y);  s1 = mad_rn(s1, wz[1], c.x);
+                s0 = mad_rn(s0, wz[2], c.x);  s1 = mad_rn(s1, wz[2], c.y);
+                s0 = mad_rn(s0, wz[3], c.y);  s1 = mad_rn(s1, wz[3], Rn.x);
+                s0 = mad_rn(s0, wz[4], Rn.x); s1 = mad_rn(s1, wz[4], Rn.y);
+                dz = make_double2(__dmul_rn(s0, W.ih[2]), __dmul_rn(s1, W.ih[2]));
+            }
+            // ---- one-sided fix-ups (uniform per warp / per step)
+            if (zok) {
+                if (x < 2) dx = onesided6(W.wf[0], row + z, sx, W.ih[0]);
+                else if (x >= nx - 2) dx = onesided6(W.wb[0], row + z, -sx, W.ih[0]);
+                if (y < 2) dy = onesided6(W.wf[1], row + z, sy, W.ih[1]);
+                else if (y >= ny - 2) dy = onesided6(W.wb[1], row + z, -sy, W.ih[1]);
+                if (fix_zlo && z == 0) {
+                    dz.x = onesided6_z(W.wf[2], row, 1, W.ih[2]);
+                    dz.y = onesided6_z(W.wf[2], row + 1, 1, W.ih[2]);
+                }
+                if (fix_zhi && z == nz - 2) {
+                    dz.x = onesided6_z(W.wb[2], row + nz - 2, -1, W.ih[2]);
+                    dz.y = onesided6_z(W.wb[2], row + nz - 1, -1, W.ih[2]);
+                }
+                double2 o;
+                o.x = __dadd_rn(__dadd_rn(dx.x, dy.x), dz.x);
+                o.y = __dadd_rn(__dadd_rn(dx.y, dy.y), dz.y);
+                *reinterpret_cast<double2*>(out + x * sx + (i64)y * sy + z) = o;
+            }
+        }
+    }
+}
+
+bool tables_match(const FdTables& T) {
+    if (T.n_center != 5 || T.n_side != 6 || T.nb != 2) return false;
+    for (int k = 0; k < 5; ++k) if (T.oc[k] != k - 2) return false;
+    for (int k = 0; k < 6; ++k) if (T.of[k] != k || T.ob[k] != -k) return false;
+    return true;
+}
+
+}  // namespace
+
+// tuning knobs (read once from the environment; defaults chosen on B200)
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const double* lo,
+                          const double* hi, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (p->ndim != 3) return NG_OK;
+    const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
+    if (nz % 2 || nx < 6 || ny < 6 || nz < 8 || nx * ny * nz >= (1LL << 40)) return NG_OK;
+    if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)lo | (uintptr_t)hi) & 15) != 0) return NG_OK;
+    for (int a = 0; a < 3; ++a) if (!tables_match(p->lap[a])) return NG_OK;
+    static const int force_generic = env_int("NG_FDLAP_GENERIC", 0);
+    if (force_generic) return NG_OK;
+
+    Lap3W W;
+    for (int a = 0; a < 3; ++a) {
+        for (int k = 0; k < 5; ++k) W.wc[a][k] = p->lap[a].wc[k];
+        for (int k = 0; k < 6; ++k) { W.wf[a][k] = p->lap[a].wf[k]; W.wb[a][k] = p->lap[a].wb[k]; }
+        W.ih[a] = p->lap[a].inv_h_pow;
+    }
+    static const int cfg_R = env_int("NG_FDLAP_R", 4);
+    static const int cfg_xchunk = env_int("NG_FDLAP_XCHUNK", 128);
+    int xchunk = cfg_xchunk < 1 ? 1 : cfg_xchunk;
+    if (xchunk > nx) xchunk = (int)nx;
+    const unsigned gx = (unsigned)((nz + 63) / 64);
+    const unsigned gz = (unsigned)((nx + xchunk - 1) / xchunk);
+#define NG_LAP_GO(RR, WW)                                                                      \
+    do {                                                                                       \
+        dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                         \
+        fdlap3d_march_kernel<RR, WW><<<grid, 32 * WW, 0, st>>>(in, out, (int)nx, (int)ny,      \
+                                                               (int)nz, xchunk, W, lo, hi);    \
+    } while (0)
+    if (cfg_R == 1) NG_LAP_GO(1, 8);
+    else if (cfg_R == 2) NG_LAP_GO(2, 8);
+    else if (cfg_R == 8) NG_LAP_GO(8, 4);
+    else NG_LAP_GO(4, 8);
+#undef NG_LAP_GO
+    NG_LAUNCH_CHECK();
+    *handled = true;
+    return NG_OK;
+}

@@ -1,0 +1,249 @@
+"""Per-axis differentiation operators -- same classes as the reference's numgrids/diff.py, with the
+arithmetic running in libnumgrids_b200.so (hand-written sm_100a kernels) instead of
+findiff / numpy.fft / scipy.sparse.
+
+Protocol kept from the reference (numgrids/diff.py:26-28, :48-61): a ``GridDiff`` carries
+``axis, order, grid, axis_index``, sets ``self.operator`` to a callable array -> array, and may
+provide ``as_matrix()``.  The callable here is a :class:`DeviceOperator` bound to a lazily created
+C plan; ``as_matrix()`` is assembled lazily on the host from the same 1-D tables (the reference
+builds an ``n x grid.size`` Kronecker matrix eagerly in ``__init__``, numgrids/diff.py:128, :189).
+
+There is no CPU fallback: calling an operator without a CUDA device raises NumgridsB200Error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse
+
+from . import _device, _lib, _tables
+from .axes import EquidistantAxis, LogAxis
+
+
+class DeviceOperator:
+    """Callable ``f -> D f`` backed by an ``ng_plan`` (created on first use)."""
+
+    def __init__(self, shape, plan_factory, flexible_shape=False):
+        self.shape = tuple(int(s) for s in shape)
+        self._factory = plan_factory
+        self._plan = None
+        self._flex = flexible_shape
+
+    # -- plan ----------------------------------------------------------
+    @property
+    def plan(self) -> _lib.Plan:
+        if self._plan is None:
+            self._plan = self._factory()
+        return self._plan
+
+    # -- device-pointer level (used by composites and the slab layer) ---
+    def apply_ptr(self, d_in: int, d_out: int, stream: int | None = None, fuse=None) -> None:
+        lib = _lib.load()
+        st = _device.current_stream_ptr() if stream is None else stream
+        if fuse is None:
+            _lib.check(lib.ng_apply(self.plan.handle, d_in, d_out, st), "ng_apply")
+        else:
+            _lib.check(lib.ng_apply_fused(self.plan.handle, d_in, d_out, C.byref(fuse), st),
+                       "ng_apply_fused")
+
+    # -- user level ----------------------------------------------------
+    def __call__(self, f):
+        if _device.is_device_array(f):
+            x = _device.as_device_tensor(f, self.shape)
+            out = _device.empty_like_device(x)
+            self.apply_ptr(x.data_ptr(), out.data_ptr())
+            return out
+        a = _device.as_host_array(f, self.shape)
+        _lib.require_gpu()
+        out = np.empty_like(a)
+        _lib.check(_lib.load().ng_apply_host(self.plan.handle, a.ctypes.data, out.ctypes.data),
+                   "ng_apply_host")
+        if _device.is_torch_tensor(f):
+            return _device.torch().from_numpy(out)
+        return out
+
+
+def _shape_arg(grid):
+    return _lib.as_i64(list(grid.shape))
+
+
+def _kron_embed(mat_1d, shape, axis_index):
+    """I (x) ... (x) D (x) ... (x) I in axis order (the layout of numgrids/diff.py:162-171, :226-239)."""
+    if len(shape) == 1:
+        return mat_1d
+    result = None
+    for i, n in enumerate(shape):
+        m = mat_1d if i == axis_index else scipy.sparse.identity(n)
+        result = m if result is None else scipy.sparse.kron(result, m)
+    return result
+
+
+class GridDiff:
+    """Base class: partial derivative of a given order along one grid axis."""
+
+    def __init__(self, grid, order, axis_index):
+        self.axis = grid.get_axis(axis_index)
+        self.order = order
+        self.grid = grid
+        self.axis_index = axis_index
+
+    def __call__(self, f):
+        return self.operator(f)
+
+    def as_matrix(self):
+        raise NotImplementedError
+
+
+# ---------------------------------------------------------------------------------------------
+class _StencilMixin:
+    """Shared by FiniteDifferenceDiff and LogDiff: findiff-style three-scheme stencil plan."""
+
+    def _stencil_setup(self, h, x_div):
+        self._h = h
+        self._schemes = _tables.fd_schemes(self.order, self.acc)
+        n = len(self.axis)
+        need = _tables.fd_min_points(self.order, self.acc)
+        if n < need:
+            raise ValueError(f"axis with {n} points is too short for order={self.order}, "
+                             f"acc={self.acc} finite differences (needs {need})")
+        self._x_div = x_div
+        self.operator = DeviceOperator(self.grid.shape, self._make_plan)
+
+    def _make_plan(self) -> _lib.Plan:
+        lib = _lib.load()
+        oc, wc = self._schemes["center"]
+        of, wf = self._schemes["forward"]
+        ob, wb = self._schemes["backward"]
+        keep = [_lib.as_f64(_tables.snap_unit_weights(w)) for w in (wc, wf, wb)]
+        offs = [_lib.as_i32(o) for o in (oc, of, ob)]
+        shp, shp_p = _shape_arg(self.grid)
+        inv_h_pow = 1.0 / self._h ** self.order
+        xd = _lib.as_f64(self._x_div) if self._x_div is not None else (None, None)
+        out = C.c_void_p()
+        _lib.check(lib.ng_fd_plan_create(
+            len(shp), shp_p, self.axis_index, len(oc), keep[0][1], offs[0][1], len(of),
+            keep[1][1], offs[1][1], keep[2][1], offs[2][1], float(inv_h_pow), xd[1],
+            C.byref(out)), "ng_fd_plan_create")
+        return _lib.Plan(out.value)
+
+    def _stencil_matrix_1d(self):
+        n = len(self.axis)
+        nb = len(self._schemes["center"][0]) // 2
+        rows, cols, vals = [], [], []
+        for i in range(n):
+            key = "forward" if i < nb else ("backward" if i >= n - nb else "center")
+            offs, w = self._schemes[key]
+            for o, wk in zip(offs, w):
+                rows.append(i)
+                cols.append(i + o)
+                vals.append(wk / self._h ** self.order)
+        return scipy.sparse.csr_matrix((vals, (rows, cols)), shape=(n, n))
+
+
+class FiniteDifferenceDiff(_StencilMixin, GridDiff):
+    """Finite differences on an equidistant, non-periodic axis (reference numgrids/diff.py:82-91)."""
+
+    def __init__(self, grid, order, axis_index, acc=4):
+        super().__init__(grid, order, axis_index)
+        if not isinstance(self.axis, EquidistantAxis):
+            raise TypeError(f"Axis must be of type EquidistantAxis. Got: {type(self.axis)}")
+        self.acc = acc
+        self._stencil_setup(self.axis.spacing, None)
+
+    def as_matrix(self):
+        return scipy.sparse.csr_matrix(
+            _kron_embed(self._stencil_matrix_1d(), self.grid.shape, self.axis_index))
+
+
+class LogDiff(_StencilMixin, GridDiff):
+    """FD on ln x, then ``/ x`` once for any order (reference numgrids/diff.py:252-275)."""
+
+    def __init__(self, grid, order, axis_index, acc=6):
+        super().__init__(grid, order, axis_index)
+        if not isinstance(self.axis, LogAxis):
+            raise TypeError(f"Axis must be of type LogAxis. Got: {type(self.axis)}")
+        self.acc = acc
+        xi = self.axis.coords_internal
+        self._stencil_setup(xi[1] - xi[0], self.axis.coords)
+
+    def as_matrix(self):
+        D_log = _kron_embed(self._stencil_matrix_1d(), self.grid.shape, self.axis_index)
+        shp = [1] * self.grid.ndims
+        shp[self.axis_index] = len(self.axis)
+        x = np.broadcast_to(self.axis.coords.reshape(shp), self.grid.shape)
+        return scipy.sparse.diags(1.0 / x.ravel()) @ scipy.sparse.csr_matrix(D_log)
+
+
+# ---------------------------------------------------------------------------------------------
+class FFTDiff(GridDiff):
+    """Spectral derivative on a periodic equidistant axis (reference numgrids/diff.py:109-171)."""
+
+    def __init__(self, grid, order, axis_index, acc=6):
+        super().__init__(grid, order, axis_index)
+        if not isinstance(self.axis, EquidistantAxis):
+            raise TypeError("Spectral FFT differentiation requires equidistant axis.")
+        if not self.axis.periodic:
+            raise TypeError("Spectral FFT differentiation requires periodic boundary conditions.")
+        self.acc = acc
+        n = len(self.axis)
+        self._W_1d = _tables.fft_multiplier(n, self.axis.spacing, order)
+        self._dense = None
+        self._D = None
+        self.operator = DeviceOperator(grid.shape, self._make_plan)
+
+    def _dense_matrix(self):
+        if self._dense is None:
+            self._dense = _tables.fft_dense_matrix(self._W_1d)
+        return self._dense
+
+    def _make_plan(self) -> _lib.Plan:
+        lib = _lib.load()
+        shp, shp_p = _shape_arg(self.grid)
+        W = np.ascontiguousarray(self._W_1d, dtype=np.complex128).view(np.float64)
+        Wk, W_p = _lib.as_f64(W)
+        n = len(self.axis)
+        Dk, D_p = (None, None) if _tables.is_pow2(n) and n <= 8192 else _lib.as_f64(self._dense_matrix())
+        out = C.c_void_p()
+        _lib.check(lib.ng_fft_plan_create(len(shp), shp_p, self.axis_index, W_p, D_p, C.byref(out)),
+                   "ng_fft_plan_create")
+        return _lib.Plan(out.value)
+
+    def as_matrix(self):
+        if self._D is None:
+            self._D = _kron_embed(scipy.sparse.csc_matrix(self._dense_matrix()),
+                                  self.grid.shape, self.axis_index)
+        return self._D
+
+
+# ---------------------------------------------------------------------------------------------
+class ChebyshevDiff(GridDiff):
+    """Chebyshev spectral derivative (reference numgrids/diff.py:186-239).
+
+    The kernel sums ``y_i = sum_j M_ij f_j`` one j at a time in the direction scipy's matvec uses on
+    the reference's Kronecker matrix, without FMA, so results match the reference bit for bit.
+    """
+
+    def __init__(self, grid, order, axis_index):
+        super().__init__(grid, order, axis_index)
+        self._scale = self.axis[-1] - self.axis[0]
+        last_nd = grid.ndims > 1 and axis_index == grid.ndims - 1
+        self._M = _tables.chebyshev_matrix(self.axis.coords_internal, self.axis.coords, order, last_nd)
+        self._descending = _tables.chebyshev_descending(order, axis_index, grid.ndims)
+        self._sparse = None
+        self.operator = DeviceOperator(grid.shape, self._make_plan)
+
+    def _make_plan(self) -> _lib.Plan:
+        lib = _lib.load()
+        shp, shp_p = _shape_arg(self.grid)
+        Mk, M_p = _lib.as_f64(self._M)
+        out = C.c_void_p()
+        _lib.check(lib.ng_cheb_plan_create(len(shp), shp_p, self.axis_index, M_p,
+                                           int(self._descending), C.byref(out)), "ng_cheb_plan_create")
+        return _lib.Plan(out.value)
+
+    def as_matrix(self):
+        if self._sparse is None:
+            self._sparse = _kron_embed(scipy.sparse.csc_matrix(self._M), self.grid.shape,
+                                       self.axis_index)
+        return self._sparse
