@@ -1,0 +1,525 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the numgrids hot path on B200 (contract: see the task brief).
+
+Headline workload (BASELINE.json configs[4], the one the metric's 1/2/4/8-GPU scaling is quoted
+on): fused Cartesian FD Laplacian  Diff(g,2,0)(f)+Diff(g,2,1)(f)+Diff(g,2,2)(f)  on an
+equidistant grid with 1024^3 points PER GPU, slab-sharded along the last axis with a halo
+exchange (weak scaling: 1024^3, 1024x1024x2048, 1024x2048x2048, 2048^3 at N = 1, 2, 4, 8).
+A "step" is one Laplacian apply over the whole (global) grid.  The other BASELINE configs
+(cfg1 FD 512^2, cfg2 Chebyshev 256^3, cfg3 FFT 512x512x1024, cfg4 spherical 128x128x256) are
+timed at N=1 and reported under "per_config" in the same JSON line.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # CPU arm: the oracle port on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gpts/s per Laplacian apply (fp64), fused Cartesian FD Laplacian, 1024^3 points per GPU"
+UNIT = "Gpts/s"
+
+GLOBAL_SHAPES = {1: (1024, 1024, 1024), 2: (1024, 1024, 2048), 4: (1024, 2048, 2048),
+                 8: (2048, 2048, 2048)}
+
+
+def global_shape_for(n_gpus: int, scale: int):
+    if n_gpus in GLOBAL_SHAPES:
+        g = GLOBAL_SHAPES[n_gpus]
+    else:                                           # other N: grow the sharded axis only
+        g = (1024, 1024, 1024 * n_gpus)
+    return tuple(max(16, s // scale) for s in g)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy restatement of findiff + the reference idiom)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_shape(scale: int):
+    return tuple(max(16, s // scale) for s in (512, 256, 256))
+
+
+def time_cpu_oracle(shape, repeats: int):
+    """Oracle (oracle/pencil.py, kind 'port') on a bounded sub-block of the headline workload."""
+    from oracle import pencil
+    hs = [1.0 / 1023.0] * 3
+    x, y, z = (np.arange(n) * h for n, h in zip(shape, hs))
+    f = (np.sin(2 * np.pi * x)[:, None, None] * np.cos(2 * np.pi * y)[None, :, None]
+         * np.exp(z)[None, None, :])
+    pencil.cartesian_laplacian(f[:32], hs, 4)                 # warm-up (BLAS/solve init)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        pencil.cartesian_laplacian(f, hs, 4)
+        best = min(best, time.perf_counter() - t0)
+    return best, int(np.prod(shape))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scale = args.scale
+    shape = cpu_sample_shape(scale)
+    times = []
+    from oracle import pencil  # noqa: F401
+    for _ in range(args.warmup):
+        time_cpu_oracle(shape, 1)
+    for _ in range(args.steps):
+        t, pts = time_cpu_oracle(shape, 1)
+        times.append(t)
+    t_step = sum(times) / len(times)
+    value = pts / t_step / 1e9
+    gshape = global_shape_for(args.gpus, scale)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "cfg5: fused Cartesian FD Laplacian (acc=4), 1024^3 points per GPU, "
+                               "last-axis slabs", "global_shape": list(gshape),
+                   "sample_shape": list(shape)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-block of the workload, numpy "
+                                   "restatement of findiff (oracle/pencil.py), single-threaded like the reference; "
+                                   f"host has {os.cpu_count()} cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def make_local_field(torch, gshape, z0, z1, device):
+    """f = sin(2 pi X) cos(2 pi Y) exp(Z) from GLOBAL coordinates (no global meshgrid)."""
+    xs = [torch.linspace(0, 1, n, dtype=torch.float64, device=device) for n in gshape]
+    fx = torch.sin(2 * np.pi * xs[0])[:, None, None]
+    fy = torch.cos(2 * np.pi * xs[1])[None, :, None]
+    fz = torch.exp(xs[2][z0:z1])[None, None, :]
+    return (fx * fy * fz).contiguous()
+
+
+def time_events(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in ev]
+    return ts
+
+
+def per_config_extras(torch, ng, peak_gbs, quick):
+    """cfg1-cfg4 at N=1: device-resident timings (median over a few launches)."""
+    A = ng.AxisType
+    out = {}
+    dev = "cuda"
+
+    def med(ts):
+        return statistics.median(ts)
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # 256 MiB > L2
+
+    def timed(fn, steps=10, warmup=3, flush_l2=False):
+        def wrapped():
+            fn()
+        for _ in range(warmup):
+            wrapped()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            if flush_l2:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            wrapped()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return med(ts)
+
+    try:
+        # cfg1: Diff(Grid(eq512, eq512), 1, 0); launch-bound -> also graph replay over rotating buffers
+        ax = ng.create_axis(A.EQUIDISTANT, 512, 0.0, 1.0)
+        g = ng.Grid(ax, ax)
+        op = ng.Diff(g, 1, 0).operator.operator
+        nbuf = 80                                                     # 80 x 2 x 2 MiB = 320 MiB > L2
+        ins = torch.randn(nbuf, 512, 512, dtype=torch.float64, device=dev)
+        outs = torch.empty_like(ins)
+        ms_single = timed(lambda: op.apply_ptr(ins[0].data_ptr(), outs[0].data_ptr()), 20, 5, True)
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for i in range(nbuf):
+                op.apply_ptr(ins[i].data_ptr(), outs[i].data_ptr(), stream=s.cuda_stream)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=s):
+                for rep in range(5):
+                    for i in range(nbuf):
+                        op.apply_ptr(ins[i].data_ptr(), outs[i].data_ptr(), stream=s.cuda_stream)
+        torch.cuda.current_stream().wait_stream(s)
+        ms_graph = timed(graph.replay, 5, 2) / (5 * nbuf)
+        pts = 512 * 512
+        out["cfg1_fd_512x512_order1_axis0"] = {
+            "gpts_single_launch_cold_l2": pts / ms_single / 1e6, "ms_single_launch": ms_single,
+            "gpts_graph_replay_rotating_320MiB": pts / ms_graph / 1e6, "ms_per_apply_graph": ms_graph,
+            "hbm_frac_graph": 16 * pts / ms_graph / 1e6 / peak_gbs}
+        del ins, outs, graph
+    except Exception as e:  # pragma: no cover
+        out["cfg1_fd_512x512_order1_axis0"] = {"error": repr(e)}
+
+    try:
+        # cfg2: Diff(g, 2, 0) on Chebyshev 256^3 -- FP64-pipe-bound ordered DGEMM (2*256 instr/pt)
+        n = 128 if quick else 256
+        ax = ng.create_axis(A.CHEBYSHEV, n, 0.0, 1.0)
+        g = ng.Grid(ax, ax, ax)
+        f = torch.randn(n, n, n, dtype=torch.float64, device=dev)
+        o = torch.empty_like(f)
+        res = {}
+        for order, axis in ((2, 0), (2, 2), (1, 1)):
+            op = ng.Diff(g, order, axis).operator.operator
+            ms = timed(lambda: op.apply_ptr(f.data_ptr(), o.data_ptr()), 10, 3, True)
+            instr = 2.0 * n * n ** 3
+            res[f"order{order}_axis{axis}"] = {
+                "gpts": n ** 3 / ms / 1e6, "ms": ms, "fp64_instr_per_s_T": instr / ms / 1e9,
+                "fp64_pipe_frac_at_1965MHz": instr / ms / 1e9 / (148 * 64 * 1.965e-3)}
+        out[f"cfg2_chebyshev_{n}cubed"] = res
+        del f, o
+    except Exception as e:  # pragma: no cover
+        out["cfg2_chebyshev"] = {"error": repr(e)}
+
+    try:
+        # cfg3: Diff(g, 1, 2), periodic 1024 last axis, batch 512x512
+        b = 128 if quick else 512
+        e_ax = ng.create_axis(A.EQUIDISTANT, b, 0.0, 1.0)
+        p_ax = ng.create_axis(A.EQUIDISTANT_PERIODIC, 1024, 0.0, 2 * np.pi)
+        g = ng.Grid(e_ax, e_ax, p_ax)
+        f = torch.randn(b, b, 1024, dtype=torch.float64, device=dev)
+        o = torch.empty_like(f)
+        op = ng.Diff(g, 1, 2).operator.operator
+        ms = timed(lambda: op.apply_ptr(f.data_ptr(), o.data_ptr()), 10, 3, b < 512)
+        pts = b * b * 1024
+        out[f"cfg3_fft_{b}x{b}x1024_order1_axis2"] = {
+            "gpts": pts / ms / 1e6, "ms": ms, "hbm_frac": 16 * pts / ms / 1e6 / peak_gbs}
+        del f, o
+    except Exception as e:  # pragma: no cover
+        out["cfg3_fft"] = {"error": repr(e)}
+
+    try:
+        # cfg4: SphericalGrid(Cheb 128, Cheb 128, periodic 256): laplacian / gradient / divergence
+        r = ng.create_axis(A.CHEBYSHEV, 128, 0.5, 2.0)
+        th = ng.create_axis(A.CHEBYSHEV, 128, 0.3, np.pi - 0.3)
+        ph = ng.create_axis(A.EQUIDISTANT_PERIODIC, 256, 0.0, 2 * np.pi)
+        g = ng.SphericalGrid(r, th, ph)
+        R, T, P = (torch.from_numpy(c).cuda() for c in g.meshed_coords)
+        f = R ** 2 * torch.sin(T) ** 2 * torch.cos(2 * P) + torch.exp(-R) * torch.cos(T)
+        v = (R.contiguous(), torch.sin(T).contiguous(), torch.cos(P).contiguous())
+        pts = 128 * 128 * 256
+        res = {}
+        for name, fn in (("laplacian", lambda: g.laplacian(f)), ("gradient", lambda: g.gradient(f)),
+                         ("divergence", lambda: g.divergence(*v)), ("curl", lambda: g.curl(*v))):
+            ms = timed(fn, 10, 3, True)
+            res[name] = {"gpts": pts / ms / 1e6, "ms": ms}
+        out["cfg4_spherical_128x128x256"] = res
+    except Exception as e:  # pragma: no cover
+        out["cfg4_spherical"] = {"error": repr(e)}
+    return out
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import numgrids_b200 as ng
+    from numgrids_b200 import _lib
+    from numgrids_b200.slab import SlabLaplacian, neighbours, exchange_halos
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (numgrids_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    scale = args.scale
+    gshape = global_shape_for(n_gpus, scale)
+    hs = [1.0 / (n - 1) for n in gshape]
+    # spacing with the reference's bits: coords[1]-coords[0] of linspace(0,1,n)
+    hs = [float(np.linspace(0, 1, n)[1] - np.linspace(0, 1, n)[0]) for n in gshape]
+    slab = SlabLaplacian(gshape, hs, rank=rank, nranks=world, acc=4)
+    f = make_local_field(torch, gshape, slab.z0, slab.z1, dev)
+    out = torch.empty_like(f)
+    local_pts = f.numel()
+    global_pts = int(np.prod(gshape))
+    peak_gbs, peak_src = measured_peaks()
+    lo_n, hi_n = neighbours(rank, world)
+
+    kernel_ms = []
+
+    def step(record=False):
+        if world == 1:
+            if record:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            slab.apply_local(f, out)
+            if record:
+                b.record()
+                kernel_ms.append((a, b))
+            return
+        bufs = slab.pack(f)
+        exchange_halos(bufs["lo_planes"], bufs["hi_planes"], bufs["lo_halo"], bufs["hi_halo"], rank, world)
+        if record:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        slab.apply_local(f, out, bufs["lo_halo"] if lo_n is not None else None,
+                         bufs["hi_halo"] if hi_n is not None else None)
+        if record:
+            b.record()
+            kernel_ms.append((a, b))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    k_ms = [a.elapsed_time(b) for a, b in kernel_ms]
+    t = torch.tensor([elapsed_ms, statistics.mean(k_ms), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, kern_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    else:
+        kern_ms = float(t[1])
+    ms_per_step = elapsed_ms / args.steps
+    value = global_pts / ms_per_step / 1e6
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
+    e2e = None
+    try:
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        h_in = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
+        h_in.copy_(f)
+        if world == 1:
+            lap = _lib.load()
+
+            def e2e_step():     # the C-ABI host call: H2D + kernel + D2H, synchronous
+                _lib.check(lap.ng_fdlap_apply_host(slab.plan.handle, h_in.data_ptr(), h_out.data_ptr()))
+        else:
+            d_in = torch.empty_like(f)
+
+            def e2e_step():
+                d_in.copy_(h_in, non_blocking=True)
+                bufs = slab.pack(d_in)
+                exchange_halos(bufs["lo_planes"], bufs["hi_planes"], bufs["lo_halo"], bufs["hi_halo"],
+                               rank, world)
+                slab.apply_local(d_in, out, bufs["lo_halo"] if lo_n is not None else None,
+                                 bufs["hi_halo"] if hi_n is not None else None)
+                h_out.copy_(out, non_blocking=True)
+                torch.cuda.synchronize()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        ok = bool(torch.equal(h_out.to(dev), out))
+        e2e = {"value": global_pts / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * local_pts * world,
+               "d2h_bytes_per_step": 8 * local_pts * world, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "matches_device_result": ok,
+               "path": "ng_fdlap_apply_host (C ABI, pinned host buffers)" if world == 1 else
+                       "pinned H2D + slab apply + D2H per rank"}
+        del h_in, h_out
+    except Exception as e:  # pragma: no cover
+        e2e = {"value": None, "unit": UNIT, "error": repr(e), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (fdlap3d_march_kernel): 16 B/point algorithmic
+    alg_bytes = 16.0 * local_pts
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_fdlap3d.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("local_shape") == list(f.shape):
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "fdlap3d_march_kernel", "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "fp64_instr_per_point": 33,
+                "fp64_pipe_frac_at_1965MHz": 33.0 * local_pts / (kern_ms * 1e-3) / (148 * 64 * 1.965e9)}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        shape = cpu_sample_shape(scale)
+        tbest, pts = time_cpu_oracle(shape, 3)
+        cpu_baseline = {"value": pts / tbest / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-block of the workload, best of 3, "
+                                  "numpy restatement of findiff (oracle/pencil.py), single-threaded like the "
+                                  f"reference; host has {os.cpu_count()} cores"}
+
+    extras = None
+    if world == 1 and not args.no_extras:
+        del out
+        torch.cuda.empty_cache()
+        extras = per_config_extras(torch, ng, peak_gbs, quick=scale > 1)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg5: fused Cartesian FD Laplacian Diff(g,2,0)+Diff(g,2,1)+Diff(g,2,2) "
+                               "(acc=4), 1024^3 points per GPU, last-axis slabs + halo exchange",
+                   "global_shape": list(gshape), "local_shape": list(f.shape),
+                   "l2": "inputs (8 GiB in + 8 GiB out per GPU) are far larger than the 126 MB L2; no flush needed",
+                   "field": "sin(2 pi X) cos(2 pi Y) exp(Z) from global coordinates"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks, "per_config": extras,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("NG_BENCH_SCALE", "1")),
+                    help="divide every extent by this (debug only; 1 = the named workload)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

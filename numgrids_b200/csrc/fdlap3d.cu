@@ -205,7 +205,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
     if (nz % 2 || nx < 6 || ny < 6 || nz < 8 || nx * ny * nz >= (1LL << 40)) return NG_OK;
     if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)lo | (uintptr_t)hi) & 15) != 0) return NG_OK;
     for (int a = 0; a < 3; ++a) if (!tables_match(p->lap[a])) return NG_OK;
-    static const int force_generic = env_int("NG_FDLAP_GENERIC", 0);
+    const int force_generic = env_int("NG_FDLAP_GENERIC", 0);
     if (force_generic) return NG_OK;
 
     Lap3W W;
@@ -214,8 +214,8 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         for (int k = 0; k < 6; ++k) { W.wf[a][k] = p->lap[a].wf[k]; W.wb[a][k] = p->lap[a].wb[k]; }
         W.ih[a] = p->lap[a].inv_h_pow;
     }
-    static const int cfg_R = env_int("NG_FDLAP_R", 4);
-    static const int cfg_xchunk = env_int("NG_FDLAP_XCHUNK", 128);
+    const int cfg_R = env_int("NG_FDLAP_R", 4);
+    const int cfg_xchunk = env_int("NG_FDLAP_XCHUNK", 128);
     int xchunk = cfg_xchunk < 1 ? 1 : cfg_xchunk;
     if (xchunk > nx) xchunk = (int)nx;
     const unsigned gx = (unsigned)((nz + 63) / 64);

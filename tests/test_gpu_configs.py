@@ -1,0 +1,136 @@
+"""GPU parity at (or near) BASELINE.json config sizes against the pencil oracle, plus
+size-independent properties at full size.  Inputs are the analytic fields of SURVEY.md 8(d)."""
+import numpy as np
+import pytest
+
+import numgrids_b200 as ng
+from conftest import TOL_FFT, rel_linf
+from oracle import pencil
+
+pytestmark = pytest.mark.gpu
+A = ng.AxisType
+
+
+def test_cfg1_fd_512x512_bit_exact(gpu_ready):
+    ax = ng.create_axis(A.EQUIDISTANT, 512, 0.0, 1.0)
+    g = ng.Grid(ax, ax)
+    X, Y = g.meshed_coords
+    f = np.sin(2 * np.pi * X) * np.cos(3 * Y) + 0.3 * np.exp(-X * Y)
+    for order, axis in ((1, 0), (1, 1), (2, 0), (2, 1)):
+        out = ng.Diff(g, order, axis)(f)
+        ref = pencil.fd_apply(f, axis, ax.spacing, order, 4)
+        assert np.array_equal(out, ref), (order, axis, rel_linf(out, ref))
+
+
+@pytest.mark.parametrize("n", [48, 128])
+def test_cfg2_chebyshev_cube_bit_exact(gpu_ready, n):
+    """Diff(g,2,0) on Chebyshev^3 (descending-j order) and the other axes/orders; 256^3 runs in bench."""
+    ax = ng.create_axis(A.CHEBYSHEV, n, 0.0, 1.0)
+    g = ng.Grid(ax, ax, ax)
+    x = ax.coords
+    f = (np.sin(3 * x)[:, None, None] * np.cos(2 * x)[None, :, None] * np.exp(-x)[None, None, :])
+    pax = [pencil.make_axis("chebyshev", n, 0.0, 1.0)] * 3
+    for order, axis in ((2, 0), (2, 1), (2, 2), (1, 0), (1, 2)):
+        out = ng.Diff(g, order, axis)(f)
+        ref = pencil.make_diff(pax, order, axis)(f)
+        assert np.array_equal(out, ref), (n, order, axis, rel_linf(out, ref))
+
+
+def test_cfg3_fft_axis_1024(gpu_ready):
+    """Periodic 1024-point last axis, reduced batch (32x32), Nyquist zeroed; tolerance 1e-11."""
+    e = ng.create_axis(A.EQUIDISTANT, 32, 0.0, 1.0)
+    p = ng.create_axis(A.EQUIDISTANT_PERIODIC, 1024, 0.0, 2 * np.pi)
+    g = ng.Grid(e, e, p)
+    X, Y, P = g.meshed_coords
+    f = np.exp(np.sin(P)) * np.cos(2 * X) + Y * np.sin(3 * P)
+    for order in (1, 2):
+        out = ng.Diff(g, order, 2)(f)
+        W = pencil.fft_multiplier(1024, p.spacing, order)
+        ref = pencil.fft_apply(f, 2, W)
+        err = rel_linf(out, ref)
+        print(f"cfg3 order {order}: rel Linf {err:.3e}")
+        assert err <= TOL_FFT
+    # analytic check (reference tests/test_diff.py:44-60 style)
+    np.testing.assert_allclose(ng.Diff(g, 1, 2)(np.exp(np.sin(P))), np.cos(P) * np.exp(np.sin(P)), atol=1e-10)
+
+
+def test_fft_non_last_axis_and_odd_sizes(gpu_ready):
+    for shape_axis in (((64, 12), 0), ((6, 128, 10), 1), ((21, 9), 0), ((7, 30), 1), ((100,), 0)):
+        shape, axis = shape_axis
+        axes = [ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi) for n in shape]
+        g = ng.Grid(*axes)
+        rng = np.random.default_rng(1)
+        f = rng.standard_normal(shape)
+        for order in (1, 2, 3):
+            out = ng.Diff(g, order, axis)(f)
+            ref = pencil.fft_apply(f, axis, pencil.fft_multiplier(shape[axis], axes[axis].spacing, order))
+            assert rel_linf(out, ref) <= TOL_FFT, (shape, axis, order, rel_linf(out, ref))
+
+
+def test_cfg4_spherical_full_size(gpu_ready):
+    """SphericalGrid(Cheb 128, Cheb 128, periodic 256): laplacian + gradient + divergence (+ curl)."""
+    r = ng.create_axis(A.CHEBYSHEV, 128, 0.5, 2.0)
+    th = ng.create_axis(A.CHEBYSHEV, 128, 0.3, np.pi - 0.3)
+    ph = ng.create_axis(A.EQUIDISTANT_PERIODIC, 256, 0.0, 2 * np.pi)
+    g = ng.SphericalGrid(r, th, ph)
+    R, T, P = g.meshed_coords
+    f = R ** 2 * np.sin(T) ** 2 * np.cos(2 * P) + np.exp(-R) * np.cos(T)
+    pax = [pencil.make_axis("chebyshev", 128, 0.5, 2.0), pencil.make_axis("chebyshev", 128, 0.3, np.pi - 0.3),
+           pencil.make_axis("periodic", 256, 0.0, 2 * np.pi)]
+    D = [pencil.make_diff(pax, 1, i) for i in range(3)]
+    h = (np.ones_like(R), R, R * np.sin(T))
+    lap = g.laplacian(f)
+    ref = pencil.laplacian(f, h, D)
+    print(f"cfg4 laplacian rel Linf {rel_linf(lap, ref):.3e}")
+    assert rel_linf(lap, ref) <= 1e-12
+    grad = g.gradient(f)
+    gref = pencil.gradient(f, h, D)
+    assert np.array_equal(grad[0], gref[0]) and np.array_equal(grad[1], gref[1])      # Chebyshev axes: bit-exact
+    assert rel_linf(grad[2], gref[2]) <= TOL_FFT
+    v = (R, np.sin(T), np.cos(P))
+    div = g.divergence(*v)
+    assert rel_linf(div, pencil.divergence(v, h, D)) <= 1e-12
+    curl = g.curl(*v)
+    cref = pencil.curl(v, h, D)
+    for i in range(3):
+        assert rel_linf(curl[i], cref[i]) <= TOL_FFT
+
+
+def test_cfg5_cartesian_laplacian_bit_exact_and_slabs(gpu_ready):
+    """Fused Laplacian vs the oracle idiom at 96x80x128; then the last axis split into 2 and 4
+    slabs with packed halos (one GPU emulating all ranks): every slab equals the global result."""
+    import torch
+    from numgrids_b200.slab import SlabLaplacian
+    shape = (96, 80, 128)
+    axes = [ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0 + i) for i, n in enumerate(shape)]
+    g = ng.Grid(*axes)
+    x, y, zc = (a.coords for a in axes)
+    f = (np.sin(2 * np.pi * x)[:, None, None] * np.cos(2 * np.pi * y)[None, :, None] * np.exp(zc)[None, None, :])
+    ref = pencil.cartesian_laplacian(f, [a.spacing for a in axes], 4)
+    out = ng.cartesian_laplacian(g, f)
+    assert np.array_equal(out, ref), rel_linf(out, ref)
+    for nranks in (2, 4):
+        parts = SlabLaplacian.emulate_on_one_gpu(g, torch.from_numpy(f).cuda(), nranks)
+        got = torch.cat(parts, dim=2).cpu().numpy()
+        assert np.array_equal(got, ref), nranks
+
+
+def test_linearity_and_constants_full_size(gpu_ready):
+    """Size-independent properties at 256^3-class sizes on the device path: D(const)=0 for FD,
+    D(a f + b g) ~ a D f + b D g, fused Laplacian == three-call idiom."""
+    import torch
+    n = 256
+    ax = ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0)
+    g = ng.Grid(ax, ax, ax)
+    torch.manual_seed(0)
+    f = torch.randn(n, n, n, dtype=torch.float64, device="cuda")
+    h = torch.randn(n, n, n, dtype=torch.float64, device="cuda")
+    lap = ng.CartesianLaplacian(g)
+    idiom = ng.Diff(g, 2, 0)(f) + ng.Diff(g, 2, 1)(f) + ng.Diff(g, 2, 2)(f)
+    assert torch.equal(lap(f), idiom)
+    d = ng.Diff(g, 1, 1)
+    lhs = d(2.0 * f + 0.5 * h)
+    rhs = 2.0 * d(f) + 0.5 * d(h)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-12
+    const = torch.full((n, n, n), 3.25, dtype=torch.float64, device="cuda")
+    assert float(d(const).abs().max()) < 1e-9
