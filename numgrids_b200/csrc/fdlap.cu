@@ -94,5 +94,18 @@ int ng_fdlap_upload_params(ng_plan* p) {
     NG_CUDA_OK(cudaMalloc((void**)&p->d_M, sizeof(LapParams)));
     p->device_bytes += sizeof(LapParams);
     NG_CUDA_OK(cudaMemcpy(p->d_M, &hp, sizeof(LapParams), cudaMemcpyHostToDevice));
+    if (p->ndim == 3) {
+        // one-sided tables of the 3-D march kernel (struct Lap3Side in fdlap3d.cu): wf[3][6], wb[3][6], ih[3]
+        double side[39];
+        for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < 6; ++k) {
+                side[a * 6 + k] = p->lap[a].wf[k];
+                side[18 + a * 6 + k] = p->lap[a].wb[k];
+            }
+        for (int a = 0; a < 3; ++a) side[36 + a] = p->lap[a].inv_h_pow;
+        NG_CUDA_OK(cudaMalloc((void**)&p->d_Mt, sizeof(side)));
+        p->device_bytes += sizeof(side);
+        NG_CUDA_OK(cudaMemcpy(p->d_Mt, side, sizeof(side), cudaMemcpyHostToDevice));
+    }
     return NG_OK;
 }

@@ -182,6 +182,417 @@ fdlap3d_march_kernel(const double* __restrict__ in, double* __restrict__ out, in
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// v2 fast path: full tiles only (nz % 64 == 0, ny % R == 0).  No bounds checks in the steady state:
+// halo rows / tile-edge columns are CLAMPED to valid addresses (their garbage only reaches outputs
+// that the one-sided fix-ups overwrite), the 6-plane register window (x-2 .. x+3, the last one
+// prefetched a step ahead) rotates by renaming through a 6x unrolled march, and every row is
+// finished (dx, dy, dz, combine, store) before the next starts to keep live registers low.
+// -------------------------------------------------------------------------------------------------
+template <int R>
+struct Rows {
+    double2 v[R];
+};
+
+struct Lap3C {            // central weights + scales: kernel parameter (constant bank operands)
+    double wc[3][5], ih[3];
+};
+struct Lap3Side {         // one-sided tables: read from global memory on the rare fix-up path
+    double wf[3][6], wb[3][6], ih[3];
+};
+
+// One-sided replacement of the axis sums that sit on a global boundary, then the final combine.
+// Deliberately NOT inlined: it is executed by <1% of the warp-steps and must not bloat the march.
+__device__ __noinline__ double2 fix_and_combine(const Lap3Side* __restrict__ S, const double* row,
+                                                i64 sx, int sy, int x, int y, int nx, int ny,
+                                                int zfix /*0 none, 1 first pair, 2 last pair*/,
+                                                double2 dx, double2 dy, double2 dz) {
+    if (x < 2) dx = onesided6(S->wf[0], row, sx, S->ih[0]);
+    else if (x >= nx - 2) dx = onesided6(S->wb[0], row, -sx, S->ih[0]);
+    if (y < 2) dy = onesided6(S->wf[1], row, sy, S->ih[1]);
+    else if (y >= ny - 2) dy = onesided6(S->wb[1], row, -(i64)sy, S->ih[1]);
+    if (zfix == 1) {
+        dz.x = onesided6_z(S->wf[2], row, 1, S->ih[2]);
+        dz.y = onesided6_z(S->wf[2], row + 1, 1, S->ih[2]);
+    } else if (zfix == 2) {
+        dz.x = onesided6_z(S->wb[2], row, -1, S->ih[2]);
+        dz.y = onesided6_z(S->wb[2], row + 1, -1, S->ih[2]);
+    }
+    return make_double2(__dadd_rn(__dadd_rn(dx.x, dy.x), dz.x), __dadd_rn(__dadd_rn(dx.y, dy.y), dz.y));
+}
+
+template <int R>
+struct MarchCtx {
+    const double* pc;     // centre plane x, at (row y0, this lane's z)
+    const double* pn;     // plane min(x+3, nx-1), same row/column
+    const double* pe;     // tile-edge column source for this lane (lane 0 / 31), plane x, row y0
+    double* po;           // output plane x, row y0
+    const Lap3Side* side;
+    i64 sx, esx;          // plane strides of pc/po/pn and of pe
+    int esy, sy;          // row strides of pe and of pc
+    int oh[4];            // clamped halo row offsets relative to row y0
+    int y0, ny, nx, lane, zfix;
+    bool is_edge_lane, rowfix;
+};
+
+template <int R>
+__device__ __forceinline__ void march_step(int x, const MarchCtx<R>& c, const Lap3C& W,
+                                           const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
+                                           const Rows<R>& D, const Rows<R>& E, Rows<R>& F) {
+    // ---- loads: prefetch plane x+3, halo rows of plane x, tile-edge columns of plane x
+#pragma unroll
+    for (int r = 0; r < R; ++r) F.v[r] = ld2(c.pn + r * c.sy);
+    double2 col[R + 4];
+    col[0] = ld2(c.pc + c.oh[0]);
+    col[1] = ld2(c.pc + c.oh[1]);
+    col[R + 2] = ld2(c.pc + c.oh[2]);
+    col[R + 3] = ld2(c.pc + c.oh[3]);
+    double2 ed[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        ed[r] = make_double2(0.0, 0.0);
+        if (c.is_edge_lane) ed[r] = ld2(c.pe + r * c.esy);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) col[r + 2] = C.v[r];
+    const bool fix = c.rowfix || (x < 2) || (x >= c.nx - 2);     // warp-uniform
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double2 cc = C.v[r];
+        double2 L = shfl_up2(cc), Rn = shfl_dn2(cc);
+        if (c.lane == 0) L = ed[r];
+        if (c.lane == 31) Rn = ed[r];
+        const double2 dx = central5(W.wc[0], A.v[r], B.v[r], cc, D.v[r], E.v[r], W.ih[0]);
+        const double2 dy = central5(W.wc[1], col[r], col[r + 1], cc, col[r + 3], col[r + 4], W.ih[1]);
+        double2 dz;
+        {
+            double s0 = 0.0, s1 = 0.0;
+            const double* wz = W.wc[2];
+            s0 = mad_rn(s0, wz[0], L.x);  s1 = mad_rn(s1, wz[0], L.y);
+            s0 = mad_rn(s0, wz[1], L.y);  s1 = mad_rn(s1, wz[1], cc.x);
+            s0 = mad_rn(s0, wz[2], cc.x); s1 = mad_rn(s1, wz[2], cc.y);
+            s0 = mad_rn(s0, wz[3], cc.y); s1 = mad_rn(s1, wz[3], Rn.x);
+            s0 = mad_rn(s0, wz[4], Rn.x); s1 = mad_rn(s1, wz[4], Rn.y);
+            dz = make_double2(__dmul_rn(s0, W.ih[2]), __dmul_rn(s1, W.ih[2]));
+        }
+        double2 o;
+        if (fix) {
+            o = fix_and_combine(c.side, c.pc + r * c.sy, c.sx, c.sy, x, c.y0 + r, c.nx, c.ny, c.zfix,
+                                dx, dy, dz);
+        } else {
+            o.x = __dadd_rn(__dadd_rn(dx.x, dy.x), dz.x);
+            o.y = __dadd_rn(__dadd_rn(dx.y, dy.y), dz.y);
+        }
+        *reinterpret_cast<double2*>(c.po + r * c.sy) = o;
+    }
+}
+
+template <int R, int WY, int MINB>
+__global__ void __launch_bounds__(32 * WY, MINB)
+fdlap3d_fast_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
+                    int xchunk, Lap3C W, const Lap3Side* __restrict__ side,
+                    const double* __restrict__ lo, const double* __restrict__ hi) {
+    MarchCtx<R> c;
+    c.lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int z0 = blockIdx.x * 64;
+    const int z = z0 + 2 * c.lane;
+    c.y0 = (blockIdx.y * WY + warp) * R;
+    if (c.y0 >= ny) return;                       // warp-uniform; no block-level sync is used
+    const int xs = blockIdx.z * xchunk;
+    const int xe = min(nx, xs + xchunk);
+    c.nx = nx; c.ny = ny;
+    c.sy = nz;
+    c.sx = (i64)ny * nz;
+    c.side = side;
+    c.oh[0] = (max(c.y0 - 2, 0) - c.y0) * nz;
+    c.oh[1] = (max(c.y0 - 1, 0) - c.y0) * nz;
+    c.oh[2] = (min(c.y0 + R, ny - 1) - c.y0) * nz;
+    c.oh[3] = (min(c.y0 + R + 1, ny - 1) - c.y0) * nz;
+    c.rowfix = (c.y0 < 2) || (c.y0 + R > ny - 2) || ((z0 == 0) && (lo == nullptr)) ||
+               ((z0 + 64 == nz) && (hi == nullptr));
+    c.zfix = 0;
+    if (z0 == 0 && lo == nullptr && c.lane == 0) c.zfix = 1;
+    if (z0 + 64 == nz && hi == nullptr && c.lane == 31) c.zfix = 2;
+    c.is_edge_lane = (c.lane == 0) || (c.lane == 31);
+    const i64 rowbase = (i64)c.y0 * nz + z;
+    // tile-edge column source: neighbour tile in the same row, the slab halo, or (global boundary)
+    // this lane's own pair as a harmless stand-in
+    c.pe = in + xs * c.sx + rowbase;
+    c.esx = c.sx;
+    c.esy = nz;
+    if (c.lane == 0) {
+        if (z0 > 0) c.pe -= 2;
+        else if (lo) { c.pe = lo + ((i64)xs * ny + c.y0) * 2; c.esx = (i64)ny * 2; c.esy = 2; }
+    } else if (c.lane == 31) {
+        if (z0 + 64 < nz) c.pe += 2;
+        else if (hi) { c.pe = hi + ((i64)xs * ny + c.y0) * 2; c.esx = (i64)ny * 2; c.esy = 2; }
+    }
+    c.pc = in + xs * c.sx + rowbase;
+    c.po = out + xs * c.sx + rowbase;
+    c.pn = in + (i64)min(xs + 3, nx - 1) * c.sx + rowbase;
+
+    Rows<R> w0, w1, w2, w3, w4, w5;
+    {   // planes xs-2 .. xs+2 (clamped into the array)
+        const double* p;
+        p = in + (i64)max(xs - 2, 0) * c.sx + rowbase;
+#pragma unroll
+        for (int r = 0; r < R; ++r) w0.v[r] = ld2(p + r * c.sy);
+        p = in + (i64)max(xs - 1, 0) * c.sx + rowbase;
+#pragma unroll
+        for (int r = 0; r < R; ++r) w1.v[r] = ld2(p + r * c.sy);
+        p = c.pc;
+#pragma unroll
+        for (int r = 0; r < R; ++r) w2.v[r] = ld2(p + r * c.sy);
+        p = in + (i64)min(xs + 1, nx - 1) * c.sx + rowbase;
+#pragma unroll
+        for (int r = 0; r < R; ++r) w3.v[r] = ld2(p + r * c.sy);
+        p = in + (i64)min(xs + 2, nx - 1) * c.sx + rowbase;
+#pragma unroll
+        for (int r = 0; r < R; ++r) w4.v[r] = ld2(p + r * c.sy);
+    }
+    int x = xs;
+#define NG_STEP(A, B, C, D, E, F)                       \
+    march_step<R>(x, c, W, A, B, C, D, E, F);           \
+    ++x;                                                \
+    if (x >= xe) break;                                 \
+    c.pc += c.sx; c.po += c.sx; c.pe += c.esx;          \
+    if (x + 3 <= nx - 1) c.pn += c.sx;
+    for (;;) {
+        NG_STEP(w0, w1, w2, w3, w4, w5)
+        NG_STEP(w1, w2, w3, w4, w5, w0)
+        NG_STEP(w2, w3, w4, w5, w0, w1)
+        NG_STEP(w3, w4, w5, w0, w1, w2)
+        NG_STEP(w4, w5, w0, w1, w2, w3)
+        NG_STEP(w5, w0, w1, w2, w3, w4)
+    }
+#undef NG_STEP
+}
+
+// -------------------------------------------------------------------------------------------------
+// v3: shared-memory plane ring fed by the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP).
+//
+// A CTA owns a (TY = R*WY rows) x (64 z) tile and marches along x.  One producer warp streams
+// whole planes of the tile WITH their +-2 halo -- (TY+4) rows x 68 doubles, one 544-byte bulk
+// copy per row and lane -- into a ring of S shared-memory slots, `S-3` planes ahead of the
+// consumers, completing on a per-slot "full" mbarrier (transaction bytes).  WY consumer warps keep
+// the 5-plane x window of their own points in registers (one LDS.128 per row and step) and read
+// the y-halo rows and z neighbours of the centre plane from the ring, so the steady state has no
+// global loads, no shuffles and no bounds checks in the consumer instruction stream; a slot is
+// handed back through its "empty" mbarrier two steps after it was filled.  HBM sees every input
+// point once (+ tile halos, which are L2 hits between neighbouring CTAs) and every output once.
+// One-sided boundary schemes: z and y from the ring (all 7 points are in the tile), x from global
+// memory; each only in warp-uniform branches on the boundary tiles / steps.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                         unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int RING_TZ = 64;            // z points per tile (one double2 per lane)
+constexpr int RING_PITCH = RING_TZ + 4;   // doubles per staged row (2 halo columns each side)
+
+// Boundary fix-up + combine for one row pair (rare; kept out of line).  `cen` points at this
+// lane's pair of the centre plane inside the ring (row pitch RING_PITCH); `grow` at the same pair
+// in global memory (for the x direction, whose one-sided taps are other planes).
+__device__ __noinline__ double2 ring_fix_and_combine(const Lap3Side* __restrict__ S, const double* cen,
+                                                     const double* grow, i64 sx, int x, int y, int nx,
+                                                     int ny, int zfix, double2 dx, double2 dy,
+                                                     double2 dz) {
+    if (x < 2) dx = onesided6(S->wf[0], grow, sx, S->ih[0]);
+    else if (x >= nx - 2) dx = onesided6(S->wb[0], grow, -sx, S->ih[0]);
+    if (y < 2) dy = onesided6(S->wf[1], cen, RING_PITCH, S->ih[1]);
+    else if (y >= ny - 2) dy = onesided6(S->wb[1], cen, -RING_PITCH, S->ih[1]);
+    if (zfix == 1) {
+        dz.x = onesided6_z(S->wf[2], cen, 1, S->ih[2]);
+        dz.y = onesided6_z(S->wf[2], cen + 1, 1, S->ih[2]);
+    } else if (zfix == 2) {
+        dz.x = onesided6_z(S->wb[2], cen, -1, S->ih[2]);
+        dz.y = onesided6_z(S->wb[2], cen + 1, -1, S->ih[2]);
+    }
+    return make_double2(__dadd_rn(__dadd_rn(dx.x, dy.x), dz.x), __dadd_rn(__dadd_rn(dx.y, dy.y), dz.y));
+}
+
+template <int R>
+__device__ __forceinline__ void ring_compute(int x, int y0, int z, int nx, int ny, int nz, i64 sx,
+                                             const Lap3C& W, const Lap3Side* side,
+                                             const double* __restrict__ in, double* __restrict__ out,
+                                             const double* lo_pair, const double* hi_pair,
+                                             const double* cen, bool rowfix, int zfix,
+                                             const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
+                                             const Rows<R>& D, const Rows<R>& E) {
+    double2 colv[R + 4];
+    colv[0] = ld2(cen - 2 * RING_PITCH);
+    colv[1] = ld2(cen - RING_PITCH);
+    colv[R + 2] = ld2(cen + R * RING_PITCH);
+    colv[R + 3] = ld2(cen + (R + 1) * RING_PITCH);
+#pragma unroll
+    for (int r = 0; r < R; ++r) colv[r + 2] = C.v[r];
+    const bool fix = rowfix || (x < 2) || (x >= nx - 2);        // warp-uniform
+    const i64 gbase = x * sx + (i64)y0 * nz + z;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (y0 + r >= ny) break;                                // ragged last tile (warp-uniform)
+        const double2 cc = C.v[r];
+        const double* crow = cen + r * RING_PITCH;
+        double2 L = ld2(crow - 2), Rn = ld2(crow + 2);
+        if (lo_pair) L = ld2(lo_pair + ((i64)x * ny + y0 + r) * 2);      // slab halo (lane 0 only)
+        if (hi_pair) Rn = ld2(hi_pair + ((i64)x * ny + y0 + r) * 2);     // slab halo (lane 31 only)
+        const double2 dx = central5(W.wc[0], A.v[r], B.v[r], cc, D.v[r], E.v[r], W.ih[0]);
+        const double2 dy = central5(W.wc[1], colv[r], colv[r + 1], cc, colv[r + 3], colv[r + 4], W.ih[1]);
+        double2 dz;
+        {
+            double s0 = 0.0, s1 = 0.0;
+            const double* wz = W.wc[2];
+            s0 = mad_rn(s0, wz[0], L.x);  s1 = mad_rn(s1, wz[0], L.y);
+            s0 = mad_rn(s0, wz[1], L.y);  s1 = mad_rn(s1, wz[1], cc.x);
+            s0 = mad_rn(s0, wz[2], cc.x); s1 = mad_rn(s1, wz[2], cc.y);
+            s0 = mad_rn(s0, wz[3], cc.y); s1 = mad_rn(s1, wz[3], Rn.x);
+            s0 = mad_rn(s0, wz[4], Rn.x); s1 = mad_rn(s1, wz[4], Rn.y);
+            dz = make_double2(__dmul_rn(s0, W.ih[2]), __dmul_rn(s1, W.ih[2]));
+        }
+        double2 o;
+        if (fix) {
+            o = ring_fix_and_combine(side, crow, in + gbase + (i64)r * nz, sx, x, y0 + r, nx, ny, zfix,
+                                     dx, dy, dz);
+        } else {
+            o.x = __dadd_rn(__dadd_rn(dx.x, dy.x), dz.x);
+            o.y = __dadd_rn(__dadd_rn(dx.y, dy.y), dz.y);
+        }
+        *reinterpret_cast<double2*>(out + gbase + (i64)r * nz) = o;
+    }
+}
+
+template <int R, int WY, int S, int MINB>
+__global__ void __launch_bounds__(32 * (WY + 1), MINB)
+fdlap3d_ring_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
+                    int xchunk, Lap3C W, const Lap3Side* __restrict__ side,
+                    const double* __restrict__ lo, const double* __restrict__ hi) {
+    constexpr int TY = R * WY;
+    constexpr int ROWS = TY + 4;
+    constexpr int PLANE = ROWS * RING_PITCH;          // doubles per ring slot
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)S * PLANE);
+    unsigned long long* empty = full + S;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int z0 = blockIdx.x * RING_TZ;
+    const int yb = blockIdx.y * TY;                   // first row of the tile
+    const int xs = blockIdx.z * xchunk;
+    const int xe = min(nx, xs + xchunk);
+    const i64 sx = (i64)ny * nz;
+    const int p_first = xs - 2, p_last = xe + 1;      // planes that travel through the ring
+    const int nplanes = p_last - p_first + 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WY); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == WY) {
+        // ================= producer warp: one bulk copy per tile row and plane =================
+        const int zlo = max(z0 - 2, 0), zhi = min(z0 + RING_TZ + 2, nz);     // [zlo, zhi) of each row
+        const unsigned row_bytes = (unsigned)(zhi - zlo) * 8u;
+        const int dst_col = zlo - (z0 - 2);
+        const int ylo = max(yb - 2, 0), yhi = min(yb + TY + 2, ny);          // rows [ylo, yhi)
+        const unsigned plane_bytes = row_bytes * (unsigned)(yhi - ylo);
+        for (int q = 0; q < nplanes; ++q) {
+            const int s = q % S;
+            if (q >= S) mbar_wait(&empty[s], ((q / S) - 1) & 1);
+            const int p = p_first + q;
+            if (p < 0 || p >= nx) {                    // nothing to stage: just complete the phase
+                if (lane == 0) mbar_arrive(&full[s]);
+                continue;
+            }
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], plane_bytes);
+            __syncwarp();
+            double* slot = ring + (size_t)s * PLANE;
+            for (int y = ylo + lane; y < yhi; y += 32)
+                bulk_g2s(slot + (y - (yb - 2)) * RING_PITCH + dst_col, in + p * sx + (i64)y * nz + zlo,
+                         row_bytes, &full[s]);
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int j0 = warp * R;                           // first tile-local row of this warp
+    const int y0 = yb + j0;
+    if (y0 >= ny) {
+        // warp entirely outside the grid (ragged last tile): still hand the slots back
+        for (int q = 2; q < nplanes; ++q) {
+            mbar_wait(&full[q % S], (q / S) & 1);
+            if (lane == 0) mbar_arrive(&empty[(q - 2) % S]);
+        }
+        return;
+    }
+    const int z = z0 + 2 * lane;
+    const int col = 2 + 2 * lane;                      // this lane's pair inside a staged row
+    const bool zfix_lo = (z0 == 0) && (lo == nullptr), zfix_hi = (z0 + RING_TZ == nz) && (hi == nullptr);
+    const bool rowfix = (y0 < 2) || (y0 + R > ny - 2) || zfix_lo || zfix_hi;      // warp-uniform
+    const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
+    const double* lo_pair = ((z0 == 0) && lane == 0) ? lo : nullptr;
+    const double* hi_pair = ((z0 + RING_TZ == nz) && lane == 31) ? hi : nullptr;
+
+    Rows<R> w0, w1, w2, w3, w4;
+    int q = 0;
+    // one ring plane per step: `NEW` receives plane p = p_first + q; the centre is plane p-2 in (A..E)
+#define NG_RING_STEP(A, B, C, D, NEW)                                                            \
+    {                                                                                            \
+        const int s = q % S;                                                                     \
+        mbar_wait(&full[s], (q / S) & 1);                                                        \
+        const double* slot = ring + (size_t)s * PLANE + (j0 + 2) * RING_PITCH + col;             \
+        _Pragma("unroll") for (int r = 0; r < R; ++r) NEW.v[r] = ld2(slot + r * RING_PITCH);     \
+        const int x = p_first + q - 2;                                                           \
+        if (x >= xs) {                                                                           \
+            const double* cen = ring + (size_t)((q - 2) % S) * PLANE + (j0 + 2) * RING_PITCH + col; \
+            ring_compute<R>(x, y0, z, nx, ny, nz, sx, W, side, in, out, lo_pair, hi_pair, cen,   \
+                            rowfix, zfix, A, B, C, D, NEW);                                      \
+        }                                                                                        \
+        if (q >= 2) {                                                                            \
+            __syncwarp();                                                                        \
+            if (lane == 0) mbar_arrive(&empty[(q - 2) % S]);                                     \
+        }                                                                                        \
+        ++q;                                                                                     \
+        if (q >= nplanes) break;                                                                 \
+    }
+    for (;;) {
+        NG_RING_STEP(w1, w2, w3, w4, w0)
+        NG_RING_STEP(w2, w3, w4, w0, w1)
+        NG_RING_STEP(w3, w4, w0, w1, w2)
+        NG_RING_STEP(w4, w0, w1, w2, w3)
+        NG_RING_STEP(w0, w1, w2, w3, w4)
+    }
+#undef NG_RING_STEP
+}
+
 bool tables_match(const FdTables& T) {
     if (T.n_center != 5 || T.n_side != 6 || T.nb != 2) return false;
     for (int k = 0; k < 5; ++k) if (T.oc[k] != k - 2) return false;
@@ -220,7 +631,72 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
     if (xchunk > nx) xchunk = (int)nx;
     const unsigned gx = (unsigned)((nz + 63) / 64);
     const unsigned gz = (unsigned)((nx + xchunk - 1) / xchunk);
-#define NG_LAP_GO(RR, WW)                                                                      \
+    const int cfg_v = env_int("NG_FDLAP_V", 2);
+    const int cfg_wy = env_int("NG_FDLAP_WY", 8);
+    if (cfg_v == 3 && nz % 64 == 0 && ny * nz < (1LL << 28) && p->d_Mt) {
+        Lap3C WC;
+        for (int a = 0; a < 3; ++a) {
+            for (int k = 0; k < 5; ++k) WC.wc[a][k] = W.wc[a][k];
+            WC.ih[a] = W.ih[a];
+        }
+        const int cfg_s = env_int("NG_FDLAP_S", 6);
+        bool launched = false;
+#define NG_RING_GO(RR, WW, SS, MB)                                                                   \
+    if (!launched && cfg_R == RR && cfg_wy == WW && cfg_s == SS &&                                 \
+        (ny % (RR * WW) == 0 || ny % (RR * WW) >= 5)) {                                            \
+        constexpr int plane = (RR * WW + 4) * RING_PITCH;                                          \
+        const size_t smem = (size_t)SS * plane * sizeof(double) + 2 * SS * sizeof(unsigned long long); \
+        static bool attr_done = false;                                                             \
+        if (!attr_done) {                                                                          \
+            NG_CUDA_OK(cudaFuncSetAttribute(fdlap3d_ring_kernel<RR, WW, SS, MB>,                       \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_done = true;                                                                      \
+        }                                                                                          \
+        dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                             \
+        fdlap3d_ring_kernel<RR, WW, SS, MB><<<grid, 32 * (WW + 1), smem, st>>>(                        \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, WC, (const Lap3Side*)p->d_Mt, lo, hi);     \
+        launched = true;                                                                           \
+    }
+        NG_RING_GO(2, 8, 6, 2)
+        NG_RING_GO(2, 8, 5, 2)
+        NG_RING_GO(2, 8, 8, 2)
+        NG_RING_GO(2, 4, 6, 3)
+        NG_RING_GO(2, 4, 8, 3)
+        NG_RING_GO(1, 8, 6, 3)
+        NG_RING_GO(1, 8, 8, 2)
+        NG_RING_GO(4, 4, 6, 2)
+        NG_RING_GO(4, 4, 5, 2)
+        NG_RING_GO(4, 8, 5, 1)
+        NG_RING_GO(3, 8, 6, 1)
+#undef NG_RING_GO
+        if (launched) {
+            NG_LAUNCH_CHECK();
+            *handled = true;
+            return NG_OK;
+        }
+    }
+    if (cfg_v >= 2 && nz % 64 == 0 && ny % cfg_R == 0 && ny * nz < (1LL << 28) && p->d_Mt) {
+        Lap3C WC;
+        for (int a = 0; a < 3; ++a) {
+            for (int k = 0; k < 5; ++k) WC.wc[a][k] = W.wc[a][k];
+            WC.ih[a] = W.ih[a];
+        }
+#define NG_FAST_GO(RR, WW, MB)                                                                 \
+    do {                                                                                       \
+        dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                         \
+        fdlap3d_fast_kernel<RR, WW, MB><<<grid, 32 * WW, 0, st>>>(                             \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, WC, (const Lap3Side*)p->d_Mt, lo, hi); \
+    } while (0)
+        if (cfg_R == 1) { if (cfg_wy == 4) NG_FAST_GO(1, 4, 4); else NG_FAST_GO(1, 8, 2); }
+        else if (cfg_R == 2) { if (cfg_wy == 4) NG_FAST_GO(2, 4, 4); else NG_FAST_GO(2, 8, 2); }
+        else if (cfg_R == 3) { if (cfg_wy == 4) NG_FAST_GO(3, 4, 3); else NG_FAST_GO(3, 8, 1); }
+        else { if (cfg_wy == 4) NG_FAST_GO(4, 4, 2); else NG_FAST_GO(4, 8, 1); }
+#undef NG_FAST_GO
+        NG_LAUNCH_CHECK();
+        *handled = true;
+        return NG_OK;
+    }
+#define NG_LAP_GO(RR, WW)                                                                    \
     do {                                                                                       \
         dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                         \
         fdlap3d_march_kernel<RR, WW><<<grid, 32 * WW, 0, st>>>(in, out, (int)nx, (int)ny,      \
