@@ -464,10 +464,10 @@ def run_gpu_arm(args):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "fdlap3d_march_kernel", "kernel_ms": kern_ms,
+                "kernel": "fdlap3d_ring2_kernel<2,4,8> (plane ring, TMA)", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "fp64_instr_per_point": 33,
-                "fp64_pipe_frac_at_1965MHz": 33.0 * local_pts / (kern_ms * 1e-3) / (148 * 64 * 1.965e9)}
+                "fp64_instr_per_point": 34,
+                "fp64_pipe_frac_at_1965MHz": 34.0 * local_pts / (kern_ms * 1e-3) / (148 * 64 * 1.965e9)}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
     cpu_baseline = None

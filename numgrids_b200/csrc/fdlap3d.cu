@@ -16,6 +16,8 @@
 //     threads from direct loads in warp-uniform branches (rare).
 // Arithmetic is the reference's, bit for bit: per axis acc = 0.0; acc = acc + w_k*f_k in stored
 // tap order; d_a = acc * inv_h2_a; out = (d_x + d_y) + d_z.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace {
@@ -41,6 +43,16 @@ __device__ __forceinline__ double2 central5(const double* w, double2 a, double2 
                                             double2 d, double2 e, double ih) {
     double sx = 0.0, sy = 0.0;
     sx = mad_rn(sx, w[0], a.x); sy = mad_rn(sy, w[0], a.y);
+    sx = mad_rn(sx, w[1], b.x); sy = mad_rn(sy, w[1], b.y);
+    sx = mad_rn(sx, w[2], c.x); sy = mad_rn(sy, w[2], c.y);
+    sx = mad_rn(sx, w[3], d.x); sy = mad_rn(sy, w[3], d.y);
+    sx = mad_rn(sx, w[4], e.x); sy = mad_rn(sy, w[4], e.y);
+    return make_double2(__dmul_rn(sx, ih), __dmul_rn(sy, ih));
+}
+// same without the leading `0.0 +` (see ring2_compute for why this is still bit-exact after a final + 0.0)
+__device__ __forceinline__ double2 central5_nz(const double* w, double2 a, double2 b, double2 c,
+                                               double2 d, double2 e, double ih) {
+    double sx = __dmul_rn(w[0], a.x), sy = __dmul_rn(w[0], a.y);
     sx = mad_rn(sx, w[1], b.x); sy = mad_rn(sy, w[1], b.y);
     sx = mad_rn(sx, w[2], c.x); sy = mad_rn(sy, w[2], c.y);
     sx = mad_rn(sx, w[3], d.x); sy = mad_rn(sy, w[3], d.y);
@@ -593,6 +605,247 @@ fdlap3d_ring_kernel(const double* __restrict__ in, double* __restrict__ out, int
 #undef NG_RING_STEP
 }
 
+// -------------------------------------------------------------------------------------------------
+// v4: same plane ring as v3 with a lean consumer instruction stream:
+//   * one central weight set shared by the three axes (they are the same np.linalg.solve output
+//     when every axis uses the same (order, acc); checked on the host) -> 8 uniform operands;
+//   * 32-bit shared addresses advanced incrementally (no div/mod, no generic->shared conversion),
+//     LDS.128 through inline PTX; running global output offset;
+//   * the 4 prologue steps (window fill) are peeled, so the steady-state step has no prologue tests;
+//   * slab-halo handling compiled in only for the SLAB instantiation.
+// -------------------------------------------------------------------------------------------------
+struct Lap3U {
+    double w[5], ih[3];
+};
+
+__device__ __forceinline__ double2 lds2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_a(unsigned addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+template <int R, bool SLAB>
+__device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int nz, i64 sx, i64 goff,
+                                              const Lap3U& W, const Lap3Side* side,
+                                              const double* __restrict__ in, double* __restrict__ out,
+                                              const double* lo_pair, const double* hi_pair,
+                                              unsigned a_cen, bool rowfix, int zfix,
+                                              const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
+                                              const Rows<R>& D, const Rows<R>& E) {
+    constexpr unsigned PB = RING_PITCH * 8;
+    double2 colv[R + 4];
+    colv[0] = lds2(a_cen - 2 * PB);
+    colv[1] = lds2(a_cen - PB);
+    colv[R + 2] = lds2(a_cen + R * PB);
+    colv[R + 3] = lds2(a_cen + (R + 1) * PB);
+#pragma unroll
+    for (int r = 0; r < R; ++r) colv[r + 2] = C.v[r];
+    const bool fix = rowfix || (x < 2) || (x >= nx - 2);        // warp-uniform
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (y0 + r >= ny) break;                                // ragged last tile (warp-uniform)
+        const double2 cc = C.v[r];
+        double2 L = lds2(a_cen + r * PB - 16), Rn = lds2(a_cen + r * PB + 16);
+        if (SLAB) {
+            if (lo_pair) L = ld2(lo_pair + ((i64)x * ny + y0 + r) * 2);      // lane 0 of the first tile
+            if (hi_pair) Rn = ld2(hi_pair + ((i64)x * ny + y0 + r) * 2);     // lane 31 of the last tile
+        }
+        // The reference starts every tap sum from +0.0.  `0.0 + p` only differs from `p` when p is
+        // -0.0, and a sum that starts from its first product can end as -0.0 only if EVERY product
+        // was -0.0; that sign survives to the output only if all three axis sums are -0.0, which the
+        // single `+ 0.0` after the combine turns back into the reference's +0.0.  Every other value
+        // is bit-identical, so the three leading adds per point are dropped (36 -> 34 FP64 ops/point).
+        const double2 dx = central5_nz(W.w, A.v[r], B.v[r], cc, D.v[r], E.v[r], W.ih[0]);
+        const double2 dy = central5_nz(W.w, colv[r], colv[r + 1], cc, colv[r + 3], colv[r + 4], W.ih[1]);
+        double2 dz;
+        {
+            double s0 = __dmul_rn(W.w[0], L.x), s1 = __dmul_rn(W.w[0], L.y);
+            s0 = mad_rn(s0, W.w[1], L.y);  s1 = mad_rn(s1, W.w[1], cc.x);
+            s0 = mad_rn(s0, W.w[2], cc.x); s1 = mad_rn(s1, W.w[2], cc.y);
+            s0 = mad_rn(s0, W.w[3], cc.y); s1 = mad_rn(s1, W.w[3], Rn.x);
+            s0 = mad_rn(s0, W.w[4], Rn.x); s1 = mad_rn(s1, W.w[4], Rn.y);
+            dz = make_double2(__dmul_rn(s0, W.ih[2]), __dmul_rn(s1, W.ih[2]));
+        }
+        double2 o;
+        if (fix) {
+            const double* crow = (const double*)__cvta_shared_to_generic((size_t)(a_cen + r * PB));
+            o = ring_fix_and_combine(side, crow, in + goff + (i64)r * nz, sx, x, y0 + r, nx, ny, zfix,
+                                     dx, dy, dz);
+        } else {
+            o.x = __dadd_rn(__dadd_rn(dx.x, dy.x), dz.x);
+            o.y = __dadd_rn(__dadd_rn(dx.y, dy.y), dz.y);
+        }
+        o.x = __dadd_rn(o.x, 0.0);
+        o.y = __dadd_rn(o.y, 0.0);
+        *reinterpret_cast<double2*>(out + goff + (i64)r * nz) = o;
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+// TMAP: the producer issues ONE 3-D tensor-map TMA per plane (box 68 x (TY+4) x 1, out-of-bounds
+// elements zero-filled by the hardware) instead of TY+4 row copies.
+template <int R, int WY, int S, int MINB, bool SLAB, bool TMAP>
+__global__ void __launch_bounds__(32 * (WY + 1), MINB)
+fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
+                     int xchunk, Lap3U W, const Lap3Side* __restrict__ side,
+                     const double* __restrict__ lo, const double* __restrict__ hi,
+                     const __grid_constant__ CUtensorMap tmap) {
+    constexpr int TY = R * WY;
+    constexpr int ROWS = TY + 4;
+    constexpr int PLANE = ROWS * RING_PITCH;          // doubles per ring slot
+    constexpr unsigned PLANE_B = PLANE * 8, RING_B = S * PLANE_B, PB = RING_PITCH * 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // TMA destinations must be 128-byte aligned (the launch reserves 128 spare bytes)
+    double* ring = reinterpret_cast<double*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)S * PLANE);
+    unsigned long long* empty = full + S;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int z0 = blockIdx.x * RING_TZ;
+    const int yb = blockIdx.y * TY;
+    const int xs = blockIdx.z * xchunk;
+    const int xe = min(nx, xs + xchunk);
+    const i64 sx = (i64)ny * nz;
+    const int p_first = xs - 2;
+    const int nplanes = xe - xs + 4;                  // planes xs-2 .. xe+1 travel through the ring
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WY); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == WY) {
+        // ================= producer warp: one bulk copy per tile row and plane =================
+        const int zlo = max(z0 - 2, 0), zhi = min(z0 + RING_TZ + 2, nz);
+        const unsigned row_bytes = (unsigned)(zhi - zlo) * 8u;
+        const int dst_col = zlo - (z0 - 2);
+        const int ylo = max(yb - 2, 0), yhi = min(yb + TY + 2, ny);
+        const unsigned plane_bytes = row_bytes * (unsigned)(yhi - ylo);
+        int s = 0;
+        unsigned eph = 1;                              // parity of the `empty` phase to wait for next
+        if (TMAP) {
+            if (lane == 0) {
+                for (int q = 0; q < nplanes; ++q) {
+                    if (q >= S) mbar_wait(&empty[s], eph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], PLANE_B);
+                    tma_load_3d(ring + (size_t)s * PLANE, &tmap, z0 - 2, yb - 2, p_first + q, &full[s]);
+                    if (++s == S) { s = 0; if (q >= S) eph ^= 1; }
+                }
+            }
+            return;
+        }
+        const double* gplane = in + (i64)p_first * sx + zlo;
+        for (int q = 0; q < nplanes; ++q) {
+            if (q >= S) mbar_wait(&empty[s], eph ^ 1);
+            const int p = p_first + q;
+            if (p < 0 || p >= nx) {
+                if (lane == 0) mbar_arrive(&full[s]);
+            } else {
+                if (lane == 0) mbar_arrive_expect_tx(&full[s], plane_bytes);
+                __syncwarp();
+                double* slot = ring + (size_t)s * PLANE + dst_col;
+                for (int y = ylo + lane; y < yhi; y += 32)
+                    bulk_g2s(slot + (y - (yb - 2)) * RING_PITCH, gplane + (i64)y * nz, row_bytes, &full[s]);
+            }
+            gplane += sx;
+            if (++s == S) { s = 0; if (q >= S) eph ^= 1; }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int j0 = warp * R;
+    const int y0 = yb + j0;
+    if (y0 >= ny) {                                    // ragged last tile: only hand the slots back
+        for (int q = 2; q < nplanes; ++q) {
+            mbar_wait(&full[q % S], (q / S) & 1);
+            if (lane == 0) mbar_arrive(&empty[(q - 2) % S]);
+        }
+        return;
+    }
+    const int z = z0 + 2 * lane;
+    const bool zfix_lo = (z0 == 0) && (lo == nullptr), zfix_hi = (z0 + RING_TZ == nz) && (hi == nullptr);
+    const bool rowfix = (y0 < 2) || (y0 + R > ny - 2) || zfix_lo || zfix_hi;      // warp-uniform
+    const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
+    const double* lo_pair = (SLAB && (z0 == 0) && lane == 0) ? lo : nullptr;
+    const double* hi_pair = (SLAB && (z0 + RING_TZ == nz) && lane == 31) ? hi : nullptr;
+
+    const unsigned my_off = (unsigned)(((j0 + 2) * RING_PITCH + 2 + 2 * lane) * 8);
+    const unsigned ring_a = smem_u32(ring) + my_off;
+    unsigned a_new = ring_a, bar_new = smem_u32(full), ph = 0;
+    unsigned a_cen = ring_a, bar_cen = smem_u32(empty);          // centre = plane q-2 (valid from q = 2)
+    int s_new = 0, s_cen = 0;
+    int x = xs - 2;                                               // centre plane index once q >= 2 (x = p_first + q - 2)
+    i64 goff = (i64)(xs) * sx + (i64)y0 * nz + z;                 // offset of (x = xs, y0, z)
+
+    Rows<R> w0, w1, w2, w3, w4;
+#define NG_ADV_NEW()                                                                   \
+    a_new += PLANE_B; bar_new += 8;                                                    \
+    if (++s_new == S) { s_new = 0; a_new -= RING_B; bar_new -= 8 * S; ph ^= 1; }
+#define NG_ADV_CEN()                                                                   \
+    a_cen += PLANE_B; bar_cen += 8;                                                    \
+    if (++s_cen == S) { s_cen = 0; a_cen -= RING_B; bar_cen -= 8 * S; }
+#define NG_LOAD_NEW(NEW)                                                               \
+    mbar_wait_a(bar_new, ph);                                                          \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) NEW.v[r] = lds2(a_new + r * PB);     \
+    NG_ADV_NEW()
+#define NG_RELEASE_CEN()                                                               \
+    __syncwarp();                                                                      \
+    if (lane == 0) mbar_arrive_a(bar_cen);                                             \
+    NG_ADV_CEN()
+    // ---- prologue: planes xs-2 .. xs+1 fill the window; planes xs-2, xs-1 are never a centre
+    NG_LOAD_NEW(w0)
+    NG_LOAD_NEW(w1)
+    NG_LOAD_NEW(w2)
+    NG_RELEASE_CEN()
+    NG_LOAD_NEW(w3)
+    NG_RELEASE_CEN()
+    x = xs;
+    int left = xe - xs;                                           // steps to go
+#define NG_RING2_STEP(A, B, C, D, NEW)                                                 \
+    {                                                                                  \
+        NG_LOAD_NEW(NEW)                                                               \
+        ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, lo_pair, hi_pair, a_cen, \
+                               rowfix, zfix, A, B, C, D, NEW);                         \
+        NG_RELEASE_CEN()                                                               \
+        ++x; goff += sx;                                                               \
+        if (--left == 0) break;                                                        \
+    }
+    for (;;) {
+        NG_RING2_STEP(w0, w1, w2, w3, w4)
+        NG_RING2_STEP(w1, w2, w3, w4, w0)
+        NG_RING2_STEP(w2, w3, w4, w0, w1)
+        NG_RING2_STEP(w3, w4, w0, w1, w2)
+        NG_RING2_STEP(w4, w0, w1, w2, w3)
+    }
+#undef NG_RING2_STEP
+#undef NG_RELEASE_CEN
+#undef NG_LOAD_NEW
+#undef NG_ADV_CEN
+#undef NG_ADV_NEW
+}
+
 bool tables_match(const FdTables& T) {
     if (T.n_center != 5 || T.n_side != 6 || T.nb != 2) return false;
     for (int k = 0; k < 5; ++k) if (T.oc[k] != k - 2) return false;
@@ -601,6 +854,36 @@ bool tables_match(const FdTables& T) {
 }
 
 }  // namespace
+
+// 3-D tensor map over the input array (z fastest): box = 68 x rows x 1, no swizzle, zero OOB fill.
+typedef CUresult (*ng_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmap(CUtensorMap* tm, const double* in, i64 nx, i64 ny, i64 nz, int rows) {
+    static ng_encode_fn encode = nullptr;
+    if (!encode) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NG_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
+        if (!fp || qres != cudaDriverEntryPointSuccess) {
+            ng_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return NG_ECUDA;
+        }
+        encode = (ng_encode_fn)fp;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
+    const cuuint64_t gstr[2] = {(cuuint64_t)nz * 8, (cuuint64_t)ny * nz * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)RING_PITCH, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)in, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ng_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return NG_ECUDA;
+    }
+    return NG_OK;
+}
 
 // tuning knobs (read once from the environment; defaults chosen on B200)
 static int env_int(const char* name, int dflt) {
@@ -625,14 +908,83 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         for (int k = 0; k < 6; ++k) { W.wf[a][k] = p->lap[a].wf[k]; W.wb[a][k] = p->lap[a].wb[k]; }
         W.ih[a] = p->lap[a].inv_h_pow;
     }
-    const int cfg_R = env_int("NG_FDLAP_R", 4);
-    const int cfg_xchunk = env_int("NG_FDLAP_XCHUNK", 128);
-    int xchunk = cfg_xchunk < 1 ? 1 : cfg_xchunk;
-    if (xchunk > nx) xchunk = (int)nx;
+    // Defaults from the B200 sweeps in profiles/ (tools/tune_fdlap.py): plane-ring kernel (v4) with
+    // R=2 rows/warp, 4 consumer warps, 8 ring slots, 64-plane x chunks.  Environment overrides are
+    // for tuning only.
+    const int cfg_R = env_int("NG_FDLAP_R", 2);
+    const int cfg_v = env_int("NG_FDLAP_V", 4);
+    const int cfg_wy = env_int("NG_FDLAP_WY", 4);
     const unsigned gx = (unsigned)((nz + 63) / 64);
+    int xchunk = env_int("NG_FDLAP_XCHUNK", 0);
+    if (xchunk < 1) {
+        // 64 planes per chunk on big grids; shorter chunks when that would leave SMs idle
+        const i64 tiles = (i64)gx * ((ny + cfg_R * cfg_wy - 1) / (cfg_R * cfg_wy));
+        const i64 want_chunks = (148 * 6 + tiles - 1) / tiles;
+        xchunk = 64;
+        if (want_chunks > 1 && nx / want_chunks < 64) xchunk = (int)(nx / want_chunks);
+        if (xchunk < 8) xchunk = 8;
+    }
+    if (xchunk > nx) xchunk = (int)nx;
     const unsigned gz = (unsigned)((nx + xchunk - 1) / xchunk);
-    const int cfg_v = env_int("NG_FDLAP_V", 2);
-    const int cfg_wy = env_int("NG_FDLAP_WY", 8);
+    const bool same_w = memcmp(W.wc[0], W.wc[1], sizeof(W.wc[0])) == 0 &&
+                        memcmp(W.wc[0], W.wc[2], sizeof(W.wc[0])) == 0;
+    if (cfg_v == 4 && same_w && nz % 64 == 0 && ny * nz < (1LL << 28) && p->d_Mt) {
+        Lap3U WU;
+        for (int k = 0; k < 5; ++k) WU.w[k] = W.wc[0][k];
+        for (int a = 0; a < 3; ++a) WU.ih[a] = W.ih[a];
+        const int cfg_s = env_int("NG_FDLAP_S", 8);
+        const bool slab = (lo != nullptr) || (hi != nullptr);
+        const bool use_tmap = env_int("NG_FDLAP_TMAP", 1) != 0;
+        bool launched = false;
+#define NG_RING2_GO1(RR, WW, SS, MB, SL, TM)                                                         \
+    {                                                                                              \
+        constexpr int plane = (RR * WW + 4) * RING_PITCH;                                          \
+        const size_t smem = (size_t)SS * plane * sizeof(double) + 2 * SS * sizeof(unsigned long long); \
+        static bool attr_done = false;                                                             \
+        if (!attr_done) {                                                                          \
+            NG_CUDA_OK(cudaFuncSetAttribute(fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM>,              \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 128)); \
+            attr_done = true;                                                                      \
+        }                                                                                          \
+        dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                             \
+        CUtensorMap tm;                                                                            \
+        memset(&tm, 0, sizeof(tm));                                                                \
+        if (TM) {                                                                                  \
+            int trc = make_tmap(&tm, in, nx, ny, nz, RR * WW + 4);                                 \
+            if (trc) return trc;                                                                   \
+        }                                                                                          \
+        fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM><<<grid, 32 * (WW + 1), smem + 128, st>>>(     \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm); \
+        launched = true;                                                                           \
+    }
+#define NG_RING2_GO(RR, WW, SS, MB)                                                                \
+    if (!launched && cfg_R == RR && cfg_wy == WW && cfg_s == SS &&                                 \
+        (ny % (RR * WW) == 0 || ny % (RR * WW) >= 5)) {                                            \
+        if (use_tmap) {                                                                            \
+            if (slab) NG_RING2_GO1(RR, WW, SS, MB, true, true) else NG_RING2_GO1(RR, WW, SS, MB, false, true) \
+        } else {                                                                                   \
+            if (slab) NG_RING2_GO1(RR, WW, SS, MB, true, false) else NG_RING2_GO1(RR, WW, SS, MB, false, false) \
+        }                                                                                          \
+    }
+        NG_RING2_GO(2, 8, 6, 2)
+        NG_RING2_GO(2, 8, 5, 2)
+        NG_RING2_GO(2, 8, 8, 2)
+        NG_RING2_GO(2, 4, 6, 3)
+        NG_RING2_GO(2, 4, 8, 3)
+        NG_RING2_GO(1, 8, 6, 3)
+        NG_RING2_GO(4, 4, 6, 2)
+        NG_RING2_GO(4, 4, 5, 2)
+        NG_RING2_GO(3, 8, 6, 1)
+        NG_RING2_GO(2, 6, 6, 2)
+        NG_RING2_GO(2, 6, 8, 2)
+#undef NG_RING2_GO
+#undef NG_RING2_GO1
+        if (launched) {
+            NG_LAUNCH_CHECK();
+            *handled = true;
+            return NG_OK;
+        }
+    }
     if (cfg_v == 3 && nz % 64 == 0 && ny * nz < (1LL << 28) && p->d_Mt) {
         Lap3C WC;
         for (int a = 0; a < 3; ++a) {

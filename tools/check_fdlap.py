@@ -10,6 +10,9 @@ from numgrids_b200.slab import SlabLaplacian  # noqa: E402
 variants = [dict(NG_FDLAP_V="3", NG_FDLAP_R=str(r), NG_FDLAP_WY=str(w), NG_FDLAP_S=str(s), NG_FDLAP_XCHUNK=str(xc))
             for (r, w, s) in ((2, 8, 6), (2, 4, 6), (4, 4, 6), (1, 8, 6), (2, 8, 8), (4, 8, 5), (3, 8, 6))
             for xc in (5, 32)]
+variants += [dict(NG_FDLAP_V="4", NG_FDLAP_R=str(r), NG_FDLAP_WY=str(w), NG_FDLAP_S=str(s), NG_FDLAP_XCHUNK=str(xc))
+             for (r, w, s) in ((2, 8, 6), (2, 4, 6), (4, 4, 6), (1, 8, 6), (2, 8, 8), (2, 8, 5), (3, 8, 6), (2, 6, 6))
+             for xc in (1, 7, 32)]
 variants += [dict(NG_FDLAP_V="2", NG_FDLAP_R="2", NG_FDLAP_WY="8", NG_FDLAP_XCHUNK="32")]
 shapes = [(64, 64, 64), (40, 37, 128), (7, 16, 64), (33, 48, 192), (9, 21, 256)]
 bad = 0

@@ -35,13 +35,12 @@ ms = run(3, 1)
 ref = out.clone()
 print(f"generic kernel           : {ms:8.3f} ms  {16 * pts / ms / 1e6:8.1f} GB/s")
 os.environ["NG_FDLAP_GENERIC"] = "0"
-os.environ["NG_FDLAP_V"] = "3"
-for (R, WY, S), xc in itertools.product(((2, 8, 6), (2, 8, 5), (2, 8, 8), (2, 4, 6), (2, 4, 8), (1, 8, 6), (1, 8, 8),
-                                         (4, 4, 6), (4, 4, 5), (4, 8, 5), (3, 8, 6)), (32, 64, 128, 256)):
+os.environ["NG_FDLAP_V"] = os.environ.get("TUNE_V", "4")
+for (R, WY, S), xc in itertools.product(((2, 8, 6), (2, 4, 6), (2, 4, 8), (1, 8, 6), (4, 4, 6)), (8, 16, 24, 32, 48, 64)):
     os.environ["NG_FDLAP_R"] = str(R)
     os.environ["NG_FDLAP_WY"] = str(WY)
     os.environ["NG_FDLAP_S"] = str(S)
     os.environ["NG_FDLAP_XCHUNK"] = str(xc)
     ms = run()
     ok = torch.equal(out, ref)
-    print(f"v3 R={R} WY={WY} S={S} xchunk={xc:5d}    : {ms:8.3f} ms  {16 * pts / ms / 1e6:8.1f} GB/s  bit-equal-to-generic={ok}")
+    print(f"v{os.environ['NG_FDLAP_V']} R={R} WY={WY} S={S} xchunk={xc:5d}    : {ms:8.3f} ms  {16 * pts / ms / 1e6:8.1f} GB/s  bit-equal-to-generic={ok}")
