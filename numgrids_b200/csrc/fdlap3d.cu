@@ -409,10 +409,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// Every wait is bounded: a protocol bug (e.g. a wrong transaction byte count) traps after ~2^24
+// polls instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
-    unsigned done;
+    unsigned done, spins = 0;
     do {
+        if (++spins > (1u << 24)) __trap();
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -624,8 +627,9 @@ __device__ __forceinline__ double2 lds2(unsigned addr) {
     return v;
 }
 __device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity) {
-    unsigned done;
+    unsigned done, spins = 0;
     do {
+        if (++spins > (1u << 24)) __trap();
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -641,7 +645,7 @@ template <int R, bool SLAB>
 __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int nz, i64 sx, i64 goff,
                                               const Lap3U& W, const Lap3Side* side,
                                               const double* __restrict__ in, double* __restrict__ out,
-                                              const double* lo_pair, const double* hi_pair,
+                                              unsigned a_hlo, unsigned a_hhi,
                                               unsigned a_cen, bool rowfix, int zfix,
                                               const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
                                               const Rows<R>& D, const Rows<R>& E) {
@@ -659,9 +663,9 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
         if (y0 + r >= ny) break;                                // ragged last tile (warp-uniform)
         const double2 cc = C.v[r];
         double2 L = lds2(a_cen + r * PB - 16), Rn = lds2(a_cen + r * PB + 16);
-        if (SLAB) {
-            if (lo_pair) L = ld2(lo_pair + ((i64)x * ny + y0 + r) * 2);      // lane 0 of the first tile
-            if (hi_pair) Rn = ld2(hi_pair + ((i64)x * ny + y0 + r) * 2);     // lane 31 of the last tile
+        if (SLAB) {     // neighbour rank's planes, staged next to the ring by the producer's halo TMAs
+            if (a_hlo) L = lds2(a_hlo + r * 16);        // lane 0 of the first z tile
+            if (a_hhi) Rn = lds2(a_hhi + r * 16);       // lane 31 of the last z tile
         }
         // The reference starts every tap sum from +0.0.  `0.0 + p` only differs from `p` when p is
         // -0.0, and a sum that starts from its first product can end as -0.0 only if EVERY product
@@ -709,7 +713,9 @@ __global__ void __launch_bounds__(32 * (WY + 1), MINB)
 fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
                      int xchunk, Lap3U W, const Lap3Side* __restrict__ side,
                      const double* __restrict__ lo, const double* __restrict__ hi,
-                     const __grid_constant__ CUtensorMap tmap) {
+                     const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_lo,
+                     const __grid_constant__ CUtensorMap tmap_hi) {
+    static_assert(!SLAB || TMAP, "slab halos are staged by TMA");
     constexpr int TY = R * WY;
     constexpr int ROWS = TY + 4;
     constexpr int PLANE = ROWS * RING_PITCH;          // doubles per ring slot
@@ -717,13 +723,20 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // TMA destinations must be 128-byte aligned (the launch reserves 128 spare bytes)
     double* ring = reinterpret_cast<double*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)S * PLANE);
+    // slab mode: per slot, the nb=2 neighbour columns of the tile's rows ([ROWS][2] doubles) per side
+    constexpr int HALO = SLAB ? ((ROWS * 2 + 15) / 16) * 16 : 0;   // doubles per slot and side (128-B slots)
+    constexpr unsigned HALO_B = HALO * 8;
+    double* hlo = ring + (size_t)S * PLANE;
+    double* hhi = hlo + (size_t)S * HALO;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(hhi + (size_t)S * HALO);
     unsigned long long* empty = full + S;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int z0 = blockIdx.x * RING_TZ;
     const int yb = blockIdx.y * TY;
     const int xs = blockIdx.z * xchunk;
+    const bool lo_tile = SLAB && (z0 == 0) && (lo != nullptr);
+    const bool hi_tile = SLAB && (z0 + RING_TZ == nz) && (hi != nullptr);
     const int xe = min(nx, xs + xchunk);
     const i64 sx = (i64)ny * nz;
     const int p_first = xs - 2;
@@ -748,8 +761,10 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
             if (lane == 0) {
                 for (int q = 0; q < nplanes; ++q) {
                     if (q >= S) mbar_wait(&empty[s], eph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], PLANE_B);
+                    mbar_arrive_expect_tx(&full[s], PLANE_B + (lo_tile ? ROWS * 16u : 0u) + (hi_tile ? ROWS * 16u : 0u));   // bytes the TMAs deliver (slots are padded to 128 B)
                     tma_load_3d(ring + (size_t)s * PLANE, &tmap, z0 - 2, yb - 2, p_first + q, &full[s]);
+                    if (lo_tile) tma_load_3d(hlo + (size_t)s * HALO, &tmap_lo, 0, yb - 2, p_first + q, &full[s]);
+                    if (hi_tile) tma_load_3d(hhi + (size_t)s * HALO, &tmap_hi, 0, yb - 2, p_first + q, &full[s]);
                     if (++s == S) { s = 0; if (q >= S) eph ^= 1; }
                 }
             }
@@ -788,8 +803,9 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     const bool zfix_lo = (z0 == 0) && (lo == nullptr), zfix_hi = (z0 + RING_TZ == nz) && (hi == nullptr);
     const bool rowfix = (y0 < 2) || (y0 + R > ny - 2) || zfix_lo || zfix_hi;      // warp-uniform
     const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
-    const double* lo_pair = (SLAB && (z0 == 0) && lane == 0) ? lo : nullptr;
-    const double* hi_pair = (SLAB && (z0 + RING_TZ == nz) && lane == 31) ? hi : nullptr;
+    // this lane's halo pair address in slot 0 (0 = not an edge lane of an edge tile)
+    unsigned a_hlo = (lo_tile && lane == 0) ? smem_u32(hlo) + (unsigned)(j0 + 2) * 16u : 0u;
+    unsigned a_hhi = (hi_tile && lane == 31) ? smem_u32(hhi) + (unsigned)(j0 + 2) * 16u : 0u;
 
     const unsigned my_off = (unsigned)(((j0 + 2) * RING_PITCH + 2 + 2 * lane) * 8);
     const unsigned ring_a = smem_u32(ring) + my_off;
@@ -805,7 +821,11 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     if (++s_new == S) { s_new = 0; a_new -= RING_B; bar_new -= 8 * S; ph ^= 1; }
 #define NG_ADV_CEN()                                                                   \
     a_cen += PLANE_B; bar_cen += 8;                                                    \
-    if (++s_cen == S) { s_cen = 0; a_cen -= RING_B; bar_cen -= 8 * S; }
+    if (SLAB) { if (a_hlo) a_hlo += HALO_B; if (a_hhi) a_hhi += HALO_B; }              \
+    if (++s_cen == S) {                                                                \
+        s_cen = 0; a_cen -= RING_B; bar_cen -= 8 * S;                                  \
+        if (SLAB) { if (a_hlo) a_hlo -= S * HALO_B; if (a_hhi) a_hhi -= S * HALO_B; }  \
+    }
 #define NG_LOAD_NEW(NEW)                                                               \
     mbar_wait_a(bar_new, ph);                                                          \
     _Pragma("unroll") for (int r = 0; r < R; ++r) NEW.v[r] = lds2(a_new + r * PB);     \
@@ -826,7 +846,7 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
 #define NG_RING2_STEP(A, B, C, D, NEW)                                                 \
     {                                                                                  \
         NG_LOAD_NEW(NEW)                                                               \
-        ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, lo_pair, hi_pair, a_cen, \
+        ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, a_hlo, a_hhi, a_cen, \
                                rowfix, zfix, A, B, C, D, NEW);                         \
         NG_RELEASE_CEN()                                                               \
         ++x; goff += sx;                                                               \
@@ -859,7 +879,7 @@ bool tables_match(const FdTables& T) {
 typedef CUresult (*ng_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_tmap(CUtensorMap* tm, const double* in, i64 nx, i64 ny, i64 nz, int rows) {
+static int make_tmap(CUtensorMap* tm, const double* in, i64 nx, i64 ny, i64 nz, int box_z, int rows) {
     static ng_encode_fn encode = nullptr;
     if (!encode) {
         void* fp = nullptr;
@@ -873,7 +893,7 @@ static int make_tmap(CUtensorMap* tm, const double* in, i64 nx, i64 ny, i64 nz, 
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
     const cuuint64_t gstr[2] = {(cuuint64_t)nz * 8, (cuuint64_t)ny * nz * 8};
-    const cuuint32_t box[3] = {(cuuint32_t)RING_PITCH, (cuuint32_t)rows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_z, (cuuint32_t)rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)in, gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -939,7 +959,8 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
 #define NG_RING2_GO1(RR, WW, SS, MB, SL, TM)                                                         \
     {                                                                                              \
         constexpr int plane = (RR * WW + 4) * RING_PITCH;                                          \
-        const size_t smem = (size_t)SS * plane * sizeof(double) + 2 * SS * sizeof(unsigned long long); \
+        const size_t smem = (size_t)SS * plane * sizeof(double) + 2 * SS * sizeof(unsigned long long) + \
+                            (SL ? (size_t)SS * 2 * ((((RR * WW + 4) * 2 + 15) / 16) * 16) * sizeof(double) : 0); \
         static bool attr_done = false;                                                             \
         if (!attr_done) {                                                                          \
             NG_CUDA_OK(cudaFuncSetAttribute(fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM>,              \
@@ -947,23 +968,26 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
             attr_done = true;                                                                      \
         }                                                                                          \
         dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                             \
-        CUtensorMap tm;                                                                            \
-        memset(&tm, 0, sizeof(tm));                                                                \
+        CUtensorMap tm, tm_lo, tm_hi;                                                              \
+        memset(&tm, 0, sizeof(tm)); memset(&tm_lo, 0, sizeof(tm)); memset(&tm_hi, 0, sizeof(tm));  \
         if (TM) {                                                                                  \
-            int trc = make_tmap(&tm, in, nx, ny, nz, RR * WW + 4);                                 \
+            int trc = make_tmap(&tm, in, nx, ny, nz, RING_PITCH, RR * WW + 4);                     \
+            if (!trc && SL && lo) trc = make_tmap(&tm_lo, lo, nx, ny, 2, 2, RR * WW + 4);          \
+            if (!trc && SL && hi) trc = make_tmap(&tm_hi, hi, nx, ny, 2, 2, RR * WW + 4);          \
             if (trc) return trc;                                                                   \
         }                                                                                          \
         fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM><<<grid, 32 * (WW + 1), smem + 128, st>>>(     \
-            in, out, (int)nx, (int)ny, (int)nz, xchunk, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm); \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
+            tm_lo, tm_hi);                                                                         \
         launched = true;                                                                           \
     }
 #define NG_RING2_GO(RR, WW, SS, MB)                                                                \
     if (!launched && cfg_R == RR && cfg_wy == WW && cfg_s == SS &&                                 \
         (ny % (RR * WW) == 0 || ny % (RR * WW) >= 5)) {                                            \
-        if (use_tmap) {                                                                            \
-            if (slab) NG_RING2_GO1(RR, WW, SS, MB, true, true) else NG_RING2_GO1(RR, WW, SS, MB, false, true) \
+        if (slab) {                                                                                \
+            if (use_tmap) NG_RING2_GO1(RR, WW, SS, MB, true, true)                                 \
         } else {                                                                                   \
-            if (slab) NG_RING2_GO1(RR, WW, SS, MB, true, false) else NG_RING2_GO1(RR, WW, SS, MB, false, false) \
+            if (use_tmap) NG_RING2_GO1(RR, WW, SS, MB, false, true) else NG_RING2_GO1(RR, WW, SS, MB, false, false) \
         }                                                                                          \
     }
         NG_RING2_GO(2, 8, 6, 2)
