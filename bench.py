@@ -341,6 +341,7 @@ def run_gpu_arm(args):
     lo_n, hi_n = neighbours(rank, world)
 
     kernel_ms = []
+    stencil_ev = []      # N > 1 with overlap: (start_A, end_A, start_B, end_B) of the two stencil launches
 
     def step(record=False):
         if world == 1:
@@ -352,14 +353,12 @@ def run_gpu_arm(args):
                 b.record()
                 kernel_ms.append((a, b))
             return
-        bufs = slab.pack(f)
-        exchange_halos(bufs["lo_planes"], bufs["hi_planes"], bufs["lo_halo"], bufs["hi_halo"], rank, world)
-        if record:
+        slab.stencil_events = stencil_ev if (record and not args.no_overlap) else None
+        if record and args.no_overlap:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        slab.apply_local(f, out, bufs["lo_halo"] if lo_n is not None else None,
-                         bufs["hi_halo"] if hi_n is not None else None)
-        if record:
+        slab(f, out=out, overlap=not args.no_overlap)       # pack -> exchange (overlapped) -> stencil
+        if record and args.no_overlap:
             b.record()
             kernel_ms.append((a, b))
 
@@ -387,6 +386,7 @@ def run_gpu_arm(args):
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     k_ms = [a.elapsed_time(b) for a, b in kernel_ms]
+    k_ms += [e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in stencil_ev]
     t = torch.tensor([elapsed_ms, statistics.mean(k_ms), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -416,11 +416,7 @@ def run_gpu_arm(args):
 
             def e2e_step():
                 d_in.copy_(h_in, non_blocking=True)
-                bufs = slab.pack(d_in)
-                exchange_halos(bufs["lo_planes"], bufs["hi_planes"], bufs["lo_halo"], bufs["hi_halo"],
-                               rank, world)
-                slab.apply_local(d_in, out, bufs["lo_halo"] if lo_n is not None else None,
-                                 bufs["hi_halo"] if hi_n is not None else None)
+                slab(d_in, out=out, overlap=not args.no_overlap)
                 h_out.copy_(out, non_blocking=True)
                 torch.cuda.synchronize()
         e2e_step()
@@ -515,6 +511,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="serialise halo exchange and stencil (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -132,6 +132,12 @@ int ng_fdlap_plan_create(int ndim, const int64_t* shape, ng_plan* const* axis_pl
 int ng_fdlap_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream);
 int ng_fdlap_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
                         const double* d_lo_halo, const double* d_hi_halo, void* stream);
+/* Output planes [x_begin, x_end) of axis 0 only (the input must be complete; halos are needed only
+ * for those planes).  Lets the host overlap the halo exchange of one plane range with the stencil
+ * of another. */
+int ng_fdlap_apply_slab_range(const ng_plan* plan, const double* d_in, double* d_out,
+                              const double* d_lo_halo, const double* d_hi_halo, int64_t x_begin,
+                              int64_t x_end, void* stream);
 int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out);
 
 /* ---- curvilinear composites: CurvilinearGrid.gradient/divergence/laplacian/curl ---------------

@@ -341,7 +341,18 @@ int ng_fdlap_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
                         const double* d_lo_halo, const double* d_hi_halo, void* stream) {
     NG_REQUIRE(plan && plan->kind == PK_FDLAP, "ng_fdlap_apply: Laplacian plan required");
     NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fdlap_apply: bad buffers");
-    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, (cudaStream_t)stream);
+    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, 0, plan->shape[0], (cudaStream_t)stream);
+}
+
+int ng_fdlap_apply_slab_range(const ng_plan* plan, const double* d_in, double* d_out,
+                              const double* d_lo_halo, const double* d_hi_halo, int64_t x_begin,
+                              int64_t x_end, void* stream) {
+    NG_REQUIRE(plan && plan->kind == PK_FDLAP, "ng_fdlap_apply_slab_range: Laplacian plan required");
+    NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fdlap_apply_slab_range: bad buffers");
+    NG_REQUIRE(0 <= x_begin && x_begin <= x_end && x_end <= plan->shape[0],
+               "ng_fdlap_apply_slab_range: [%lld, %lld) is not inside axis 0 of %lld planes",
+               (long long)x_begin, (long long)x_end, (long long)plan->shape[0]);
+    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, x_begin, x_end, (cudaStream_t)stream);
 }
 
 int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
@@ -352,7 +363,7 @@ int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
     if (rc) return rc;
     const size_t bytes = sizeof(double) * (size_t)plan->size;
     NG_CUDA_OK(cudaMemcpyAsync(plan->d_stage_in, h_in, bytes, cudaMemcpyHostToDevice, 0));
-    rc = ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, 0);
+    rc = ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, 0, plan->shape[0], 0);
     if (rc) return rc;
     NG_CUDA_OK(cudaMemcpyAsync(h_out, plan->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
     NG_CUDA_OK(cudaStreamSynchronize(0));

@@ -135,6 +135,17 @@ __global__ void fd_pack_halo_kernel(const double* __restrict__ in, double* __res
     }
 }
 
+// last-axis, nb == 2 fast path: one thread per row moves both 16-byte ends with 128-bit accesses
+__global__ void fd_pack_halo_last2_kernel(const double* __restrict__ in, double2* __restrict__ lo_planes,
+                                          double2* __restrict__ hi_planes, i64 rows, i64 n) {
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < rows;
+         row += (i64)gridDim.x * blockDim.x) {
+        const double* p = in + row * n;
+        if (lo_planes) lo_planes[row] = *reinterpret_cast<const double2*>(p);
+        if (hi_planes) hi_planes[row] = *reinterpret_cast<const double2*>(p + n - 2);
+    }
+}
+
 inline int grid_for(i64 work_items, int block) {
     i64 g = (work_items + block - 1) / block;
     const i64 cap = 148LL * 64;   // grid-stride beyond 64 CTAs per SM
@@ -180,6 +191,13 @@ extern "C" int ng_fd_pack_halo(const ng_plan* p, const double* d_in, double* d_l
     if (p->kind == PK_FDLAP) { n = p->shape[p->ndim - 1]; outer = p->size / n; inner = 1; }
     const i64 total = outer * inner * nb;
     if (total == 0) return NG_OK;
+    const bool al = (((uintptr_t)d_in | (uintptr_t)d_lo_planes | (uintptr_t)d_hi_planes) & 15) == 0;
+    if (inner == 1 && nb == 2 && n % 2 == 0 && al) {
+        fd_pack_halo_last2_kernel<<<grid_for(outer, 256), 256, 0, (cudaStream_t)stream>>>(
+            d_in, (double2*)d_lo_planes, (double2*)d_hi_planes, outer, n);
+        NG_LAUNCH_CHECK();
+        return NG_OK;
+    }
     fd_pack_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         d_in, d_lo_planes, d_hi_planes, outer, n, inner, nb);
     NG_LAUNCH_CHECK();

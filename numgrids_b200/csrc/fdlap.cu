@@ -28,10 +28,10 @@ struct LapParams {
 
 __global__ void __launch_bounds__(256)
 fdlap_generic_kernel(const double* __restrict__ in, double* __restrict__ out,
-                     const LapParams* __restrict__ Pp, i64 total, const double* __restrict__ lo,
-                     const double* __restrict__ hi) {
+                     const LapParams* __restrict__ Pp, i64 first, i64 total,
+                     const double* __restrict__ lo, const double* __restrict__ hi) {
     const LapParams& P = *Pp;
-    for (i64 lin = (i64)blockIdx.x * blockDim.x + threadIdx.x; lin < total;
+    for (i64 lin = first + (i64)blockIdx.x * blockDim.x + threadIdx.x; lin < total;
          lin += (i64)gridDim.x * blockDim.x) {
         const Idx4 ix = unravel4(lin, P.shape);
         double res = 0.0;
@@ -63,17 +63,20 @@ fdlap_generic_kernel(const double* __restrict__ in, double* __restrict__ out,
 }  // namespace
 
 int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                          const double* hi, cudaStream_t st, bool* handled);
+                          const double* hi, int xbeg, int xend, cudaStream_t st, bool* handled);
 
+// Output planes [xbeg, xend) along axis 0 (the whole array when xbeg = 0, xend = shape[0]).
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                    const double* hi, cudaStream_t st) {
-    if (p->size == 0) return NG_OK;
+                    const double* hi, i64 xbeg, i64 xend, cudaStream_t st) {
+    if (p->size == 0 || xend <= xbeg) return NG_OK;
     bool handled = false;
-    int rc = ng_fdlap3d_try_launch(p, in, out, lo, hi, st, &handled);
+    int rc = ng_fdlap3d_try_launch(p, in, out, lo, hi, (int)xbeg, (int)xend, st, &handled);
     if (rc != NG_OK || handled) return rc;
-    i64 g = (p->size + 255) / 256;
+    const i64 plane = p->size / p->shape[0];
+    const i64 first = xbeg * plane, last = xend * plane;
+    i64 g = (last - first + 255) / 256;
     if (g > 148LL * 64) g = 148LL * 64;
-    fdlap_generic_kernel<<<(unsigned)g, 256, 0, st>>>(in, out, (const LapParams*)p->d_M, p->size,
+    fdlap_generic_kernel<<<(unsigned)g, 256, 0, st>>>(in, out, (const LapParams*)p->d_M, first, last,
                                                       lo, hi);
     NG_LAUNCH_CHECK();
     return NG_OK;

@@ -81,14 +81,14 @@ __device__ __forceinline__ double onesided6_z(const double* w, const double* p, 
 template <int R, int WY>
 __global__ void __launch_bounds__(32 * WY)
 fdlap3d_march_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
-                     int xchunk, Lap3W W, const double* __restrict__ lo,
+                     int xchunk, int xbeg, int xend, Lap3W W, const double* __restrict__ lo,
                      const double* __restrict__ hi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int z0 = blockIdx.x * 64;
     const int z = z0 + 2 * lane;
     const int y0 = (blockIdx.y * WY + warp) * R;
-    const int xs = blockIdx.z * xchunk;
-    const int xe = min(nx, xs + xchunk);
+    const int xs = xbeg + blockIdx.z * xchunk;
+    const int xe = min(xend, xs + xchunk);
     if (y0 >= ny) return;                       // warp-uniform
     const bool zok = z < nz;                    // nz is even: the pair is valid or not as a whole
     const i64 sy = nz, sx = (i64)ny * nz;
@@ -302,7 +302,7 @@ __device__ __forceinline__ void march_step(int x, const MarchCtx<R>& c, const La
 template <int R, int WY, int MINB>
 __global__ void __launch_bounds__(32 * WY, MINB)
 fdlap3d_fast_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
-                    int xchunk, Lap3C W, const Lap3Side* __restrict__ side,
+                    int xchunk, int xbeg, int xend, Lap3C W, const Lap3Side* __restrict__ side,
                     const double* __restrict__ lo, const double* __restrict__ hi) {
     MarchCtx<R> c;
     c.lane = threadIdx.x & 31;
@@ -311,8 +311,8 @@ fdlap3d_fast_kernel(const double* __restrict__ in, double* __restrict__ out, int
     const int z = z0 + 2 * c.lane;
     c.y0 = (blockIdx.y * WY + warp) * R;
     if (c.y0 >= ny) return;                       // warp-uniform; no block-level sync is used
-    const int xs = blockIdx.z * xchunk;
-    const int xe = min(nx, xs + xchunk);
+    const int xs = xbeg + blockIdx.z * xchunk;
+    const int xe = min(xend, xs + xchunk);
     c.nx = nx; c.ny = ny;
     c.sy = nz;
     c.sx = (i64)ny * nz;
@@ -507,7 +507,7 @@ __device__ __forceinline__ void ring_compute(int x, int y0, int z, int nx, int n
 template <int R, int WY, int S, int MINB>
 __global__ void __launch_bounds__(32 * (WY + 1), MINB)
 fdlap3d_ring_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
-                    int xchunk, Lap3C W, const Lap3Side* __restrict__ side,
+                    int xchunk, int xbeg, int xend, Lap3C W, const Lap3Side* __restrict__ side,
                     const double* __restrict__ lo, const double* __restrict__ hi) {
     constexpr int TY = R * WY;
     constexpr int ROWS = TY + 4;
@@ -520,8 +520,8 @@ fdlap3d_ring_kernel(const double* __restrict__ in, double* __restrict__ out, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int z0 = blockIdx.x * RING_TZ;
     const int yb = blockIdx.y * TY;                   // first row of the tile
-    const int xs = blockIdx.z * xchunk;
-    const int xe = min(nx, xs + xchunk);
+    const int xs = xbeg + blockIdx.z * xchunk;
+    const int xe = min(xend, xs + xchunk);
     const i64 sx = (i64)ny * nz;
     const int p_first = xs - 2, p_last = xe + 1;      // planes that travel through the ring
     const int nplanes = p_last - p_first + 1;
@@ -619,7 +619,21 @@ fdlap3d_ring_kernel(const double* __restrict__ in, double* __restrict__ out, int
 // -------------------------------------------------------------------------------------------------
 struct Lap3U {
     double w[5], ih[3];
+    double wfz[6], wbz[6];     // one-sided tables of the contiguous axis (global z boundary, inline fix)
 };
+
+__device__ __forceinline__ double lds1(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// one-sided 6-tap sum along z read from the ring: taps at addr + k*step bytes
+__device__ __forceinline__ double onesided6_z_smem(const double* w, unsigned addr, int step, double ih) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s = mad_rn(s, w[k], lds1(addr + k * step));
+    return __dmul_rn(s, ih);
+}
 
 __device__ __forceinline__ double2 lds2(unsigned addr) {
     double2 v;
@@ -646,7 +660,7 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
                                               const Lap3U& W, const Lap3Side* side,
                                               const double* __restrict__ in, double* __restrict__ out,
                                               unsigned a_hlo, unsigned a_hhi,
-                                              unsigned a_cen, bool rowfix, int zfix,
+                                              unsigned a_cen, bool rowfix, bool ztile, int zfix,
                                               const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
                                               const Rows<R>& D, const Rows<R>& E) {
     constexpr unsigned PB = RING_PITCH * 8;
@@ -683,10 +697,21 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
             s0 = mad_rn(s0, W.w[4], Rn.x); s1 = mad_rn(s1, W.w[4], Rn.y);
             dz = make_double2(__dmul_rn(s0, W.ih[2]), __dmul_rn(s1, W.ih[2]));
         }
+        // global z boundary (first / last z tile without a slab halo): the owning lane replaces its
+        // two z sums by the one-sided schemes, all 7 points come from the ring (warp-uniform test)
+        if (ztile) {
+            if (zfix == 1) {
+                dz.x = onesided6_z_smem(W.wfz, a_cen + r * PB, 8, W.ih[2]);
+                dz.y = onesided6_z_smem(W.wfz, a_cen + r * PB + 8, 8, W.ih[2]);
+            } else if (zfix == 2) {
+                dz.x = onesided6_z_smem(W.wbz, a_cen + r * PB, -8, W.ih[2]);
+                dz.y = onesided6_z_smem(W.wbz, a_cen + r * PB + 8, -8, W.ih[2]);
+            }
+        }
         double2 o;
         if (fix) {
             const double* crow = (const double*)__cvta_shared_to_generic((size_t)(a_cen + r * PB));
-            o = ring_fix_and_combine(side, crow, in + goff + (i64)r * nz, sx, x, y0 + r, nx, ny, zfix,
+            o = ring_fix_and_combine(side, crow, in + goff + (i64)r * nz, sx, x, y0 + r, nx, ny, 0,
                                      dx, dy, dz);
         } else {
             o.x = __dadd_rn(__dadd_rn(dx.x, dy.x), dz.x);
@@ -711,7 +736,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* t
 template <int R, int WY, int S, int MINB, bool SLAB, bool TMAP>
 __global__ void __launch_bounds__(32 * (WY + 1), MINB)
 fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
-                     int xchunk, Lap3U W, const Lap3Side* __restrict__ side,
+                     int xchunk, int xbeg, int xend, Lap3U W, const Lap3Side* __restrict__ side,
                      const double* __restrict__ lo, const double* __restrict__ hi,
                      const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_lo,
                      const __grid_constant__ CUtensorMap tmap_hi) {
@@ -734,10 +759,10 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int z0 = blockIdx.x * RING_TZ;
     const int yb = blockIdx.y * TY;
-    const int xs = blockIdx.z * xchunk;
+    const int xs = xbeg + blockIdx.z * xchunk;
     const bool lo_tile = SLAB && (z0 == 0) && (lo != nullptr);
     const bool hi_tile = SLAB && (z0 + RING_TZ == nz) && (hi != nullptr);
-    const int xe = min(nx, xs + xchunk);
+    const int xe = min(xend, xs + xchunk);
     const i64 sx = (i64)ny * nz;
     const int p_first = xs - 2;
     const int nplanes = xe - xs + 4;                  // planes xs-2 .. xe+1 travel through the ring
@@ -801,7 +826,8 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     }
     const int z = z0 + 2 * lane;
     const bool zfix_lo = (z0 == 0) && (lo == nullptr), zfix_hi = (z0 + RING_TZ == nz) && (hi == nullptr);
-    const bool rowfix = (y0 < 2) || (y0 + R > ny - 2) || zfix_lo || zfix_hi;      // warp-uniform
+    const bool rowfix = (y0 < 2) || (y0 + R > ny - 2);                            // warp-uniform, rare
+    const bool ztile = zfix_lo || zfix_hi;                                        // warp-uniform
     const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
     // this lane's halo pair address in slot 0 (0 = not an edge lane of an edge tile)
     unsigned a_hlo = (lo_tile && lane == 0) ? smem_u32(hlo) + (unsigned)(j0 + 2) * 16u : 0u;
@@ -847,7 +873,7 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     {                                                                                  \
         NG_LOAD_NEW(NEW)                                                               \
         ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, a_hlo, a_hhi, a_cen, \
-                               rowfix, zfix, A, B, C, D, NEW);                         \
+                               rowfix, ztile, zfix, A, B, C, D, NEW);                         \
         NG_RELEASE_CEN()                                                               \
         ++x; goff += sx;                                                               \
         if (--left == 0) break;                                                        \
@@ -912,7 +938,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                          const double* hi, cudaStream_t st, bool* handled) {
+                          const double* hi, int xbeg, int xend, cudaStream_t st, bool* handled) {
     *handled = false;
     if (p->ndim != 3) return NG_OK;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
@@ -941,17 +967,18 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         const i64 tiles = (i64)gx * ((ny + cfg_R * cfg_wy - 1) / (cfg_R * cfg_wy));
         const i64 want_chunks = (148 * 6 + tiles - 1) / tiles;
         xchunk = 64;
-        if (want_chunks > 1 && nx / want_chunks < 64) xchunk = (int)(nx / want_chunks);
+        if (want_chunks > 1 && (xend - xbeg) / want_chunks < 64) xchunk = (int)((xend - xbeg) / want_chunks);
         if (xchunk < 8) xchunk = 8;
     }
-    if (xchunk > nx) xchunk = (int)nx;
-    const unsigned gz = (unsigned)((nx + xchunk - 1) / xchunk);
+    if (xchunk > xend - xbeg) xchunk = xend - xbeg;
+    const unsigned gz = (unsigned)((xend - xbeg + xchunk - 1) / xchunk);
     const bool same_w = memcmp(W.wc[0], W.wc[1], sizeof(W.wc[0])) == 0 &&
                         memcmp(W.wc[0], W.wc[2], sizeof(W.wc[0])) == 0;
     if (cfg_v == 4 && same_w && nz % 64 == 0 && ny * nz < (1LL << 28) && p->d_Mt) {
         Lap3U WU;
         for (int k = 0; k < 5; ++k) WU.w[k] = W.wc[0][k];
         for (int a = 0; a < 3; ++a) WU.ih[a] = W.ih[a];
+        for (int k = 0; k < 6; ++k) { WU.wfz[k] = W.wf[2][k]; WU.wbz[k] = W.wb[2][k]; }
         const int cfg_s = env_int("NG_FDLAP_S", 8);
         const bool slab = (lo != nullptr) || (hi != nullptr);
         const bool use_tmap = env_int("NG_FDLAP_TMAP", 1) != 0;
@@ -977,7 +1004,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
             if (trc) return trc;                                                                   \
         }                                                                                          \
         fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM><<<grid, 32 * (WW + 1), smem + 128, st>>>(     \
-            in, out, (int)nx, (int)ny, (int)nz, xchunk, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
             tm_lo, tm_hi);                                                                         \
         launched = true;                                                                           \
     }
@@ -1030,7 +1057,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         }                                                                                          \
         dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                             \
         fdlap3d_ring_kernel<RR, WW, SS, MB><<<grid, 32 * (WW + 1), smem, st>>>(                        \
-            in, out, (int)nx, (int)ny, (int)nz, xchunk, WC, (const Lap3Side*)p->d_Mt, lo, hi);     \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, WC, (const Lap3Side*)p->d_Mt, lo, hi);     \
         launched = true;                                                                           \
     }
         NG_RING_GO(2, 8, 6, 2)
@@ -1061,7 +1088,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
     do {                                                                                       \
         dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                         \
         fdlap3d_fast_kernel<RR, WW, MB><<<grid, 32 * WW, 0, st>>>(                             \
-            in, out, (int)nx, (int)ny, (int)nz, xchunk, WC, (const Lap3Side*)p->d_Mt, lo, hi); \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, WC, (const Lap3Side*)p->d_Mt, lo, hi); \
     } while (0)
         if (cfg_R == 1) { if (cfg_wy == 4) NG_FAST_GO(1, 4, 4); else NG_FAST_GO(1, 8, 2); }
         else if (cfg_R == 2) { if (cfg_wy == 4) NG_FAST_GO(2, 4, 4); else NG_FAST_GO(2, 8, 2); }
@@ -1076,7 +1103,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
     do {                                                                                       \
         dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                         \
         fdlap3d_march_kernel<RR, WW><<<grid, 32 * WW, 0, st>>>(in, out, (int)nx, (int)ny,      \
-                                                               (int)nz, xchunk, W, lo, hi);    \
+                                                               (int)nz, xchunk, xbeg, xend, W, lo, hi);    \
     } while (0)
     if (cfg_R == 1) NG_LAP_GO(1, 8);
     else if (cfg_R == 2) NG_LAP_GO(2, 8);
