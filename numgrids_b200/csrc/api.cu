@@ -242,6 +242,17 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h
         }
         rc = upload(p, &p->d_W, Wbr.data(), 2 * n);
         if (!rc) rc = upload(p, &p->d_tw, tw.data(), n);
+        // tables of the two-pass register kernel: natural-order multipliers / n, full twiddle circle
+        std::vector<double> Wn((size_t)(2 * n)), twn((size_t)(2 * n));
+        for (i64 k = 0; k < n; ++k) {
+            Wn[(size_t)(2 * k)] = h_W_re_im[2 * k] / (double)n;
+            Wn[(size_t)(2 * k + 1)] = h_W_re_im[2 * k + 1] / (double)n;
+            const long double a = two_pi * (long double)k / (long double)n;
+            twn[(size_t)(2 * k)] = (double)cosl(a);
+            twn[(size_t)(2 * k + 1)] = (double)(-sinl(a));
+        }
+        if (!rc) rc = upload(p, &p->d_Wn, Wn.data(), 2 * n);
+        if (!rc) rc = upload(p, &p->d_twn, twn.data(), 2 * n);
     } else {
         if (!h_D) {
             ng_set_error("n = %lld is not a power of two <= 8192: the dense spectral matrix is required",
@@ -375,7 +386,7 @@ int64_t ng_plan_device_bytes(const ng_plan* plan) { return plan ? plan->device_b
 int ng_plan_destroy(ng_plan* p) {
     if (!p) return NG_OK;
     auto fr = [](double* q) { if (q) cudaFree(q); };
-    fr(p->d_xdiv); fr(p->d_M); fr(p->d_Mt); fr(p->d_W); fr(p->d_tw); fr(p->d_work);
+    fr(p->d_xdiv); fr(p->d_M); fr(p->d_Mt); fr(p->d_W); fr(p->d_tw); fr(p->d_Wn); fr(p->d_twn); fr(p->d_work);
     fr(p->d_stage_in); fr(p->d_stage_out);
     fr(p->cJ.d_ptr);
     for (int a = 0; a < NG_MAX_DIM; ++a) {

@@ -108,7 +108,9 @@ struct ng_plan {
     int fft_pow2 = 0;
     int log2n = 0;
     double* d_W = nullptr;    // [n][2]
-    double* d_tw = nullptr;   // [n][2] forward twiddles exp(-2 pi i k / n)
+    double* d_tw = nullptr;   // [n/2][2] forward twiddles exp(-2 pi i k / n) (radix-2 kernel)
+    double* d_Wn = nullptr;   // [n][2] multipliers / n in natural order (two-pass kernel, fft2.cu)
+    double* d_twn = nullptr;  // [n][2] exp(-2 pi i k / n), k < n (two-pass kernel)
 
     // PK_FDLAP
     FdTables lap[NG_MAX_DIM];
@@ -132,6 +134,8 @@ int ng_dense_launch(const ng_plan* p, const double* in, double* out, const FuseD
                     cudaStream_t st);
 int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                   cudaStream_t st);
+int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                       cudaStream_t st, bool* handled);
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
                     const double* hi, i64 xbeg, i64 xend, cudaStream_t st);
 int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,

@@ -113,6 +113,142 @@ dense_apply_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Production kernel for the config shapes (axis not last, n % 128 == 0, inner % 128 == 0):
+// 128 x 128 output tile, 256 threads, 8 x 8 register tile per thread laid out as 2-wide pairs
+// strided by 32 (conflict-free LDS.128: 'a' pairs broadcast per half-warp, 'b' pairs contiguous),
+// k panels of 16 double-buffered in shared memory with cp.async (LDGSTS) so the next panel streams
+// in under the 2048 FP64 instructions of the current one.  Same arithmetic contract as above.
+// -------------------------------------------------------------------------------------------------
+constexpr int FM = 128, FN = 128, FK = 16;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool DESC, bool FMA, bool FUSED>
+__global__ void __launch_bounds__(256, 1)
+dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
+                  const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F) {
+    extern __shared__ __align__(16) double dsm[];
+    double (*Ms)[FK][FM] = reinterpret_cast<double (*)[FK][FM]>(dsm);                 // [2][FK][FM]
+    double (*Fs)[FK][FN] = reinterpret_cast<double (*)[FK][FN]>(dsm + 2 * FK * FM);   // [2][FK][FN]
+    const i64 col0 = (i64)blockIdx.x * FN;          // flattened (o, c) column; tiles never straddle o
+    const int row0 = blockIdx.y * FM;
+    const i64 o = col0 / inner, c0 = col0 - o * inner;
+    const double* fbase = in + o * (i64)n * inner + c0;        // element (k, c) at fbase + k*inner + c
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+
+    const int npanel = n / FK;
+    auto stage = [&](int p, int buf) {
+        const int k0 = p * FK;
+        // 16 x 128 doubles each = 1024 16-byte chunks per operand; 256 threads x 4 chunks
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 256;
+            const int kk = e >> 6, ch = (e & 63) * 2;
+            cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * n + row0 + ch);
+            cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
+        }
+        cp_async_commit();
+    };
+    stage(DESC ? npanel - 1 : 0, 0);
+    for (int pp = 0; pp < npanel; ++pp) {
+        const int buf = pp & 1;
+        if (pp + 1 < npanel) {
+            stage(DESC ? npanel - 2 - pp : pp + 1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = 0; q < FK; ++q) {
+            const int kk = DESC ? FK - 1 - q : q;
+            double a[8], b[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 av = *reinterpret_cast<const double2*>(&Ms[buf][kk][ty * 2 + 32 * j]);
+                const double2 bv = *reinterpret_cast<const double2*>(&Fs[buf][kk][tx * 2 + 32 * j]);
+                a[2 * j] = av.x; a[2 * j + 1] = av.y;
+                b[2 * j] = bv.x; b[2 * j + 1] = bv.y;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    if (FMA) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+                    else acc[x][y] = __dadd_rn(acc[x][y], __dmul_rn(a[x], b[y]));
+                }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: rows ty*2 + {0,1} + 32*jr, column pairs tx*2 + 32*jc.  One unravel per column
+    // pair (the row only changes the coordinate along `axis`).
+#pragma unroll
+    for (int jc = 0; jc < 4; ++jc) {
+        const i64 lin0 = (o * n) * inner + c0 + tx * 2 + 32 * jc;       // row 0 of this column pair
+        Idx4 ix0;
+        if (FUSED) ix0 = unravel4(lin0, F.shape);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int i = row0 + ty * 2 + (x & 1) + 32 * (x >> 1);
+            const i64 lin = lin0 + (i64)i * inner;
+            double2 v = make_double2(acc[x][2 * jc], acc[x][2 * jc + 1]);
+            if (FUSED) {
+                Idx4 ix = ix0;
+                ix.i[axis] = i;
+                v.x = fuse_tail(F, v.x, lin, ix);
+                ix.i[F.vec_axis] += 1;                  // the pair stays inside the innermost row
+                v.y = fuse_tail(F, v.y, lin + 1, ix);
+            }
+            *reinterpret_cast<double2*>(out + lin) = v;
+        }
+    }
+}
+
+template <bool DESC, bool FMA>
+int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    const i64 ncols = p->outer * p->inner;
+    dim3 grid((unsigned)(ncols / FN), (unsigned)(p->n / FM));
+    const size_t smem = (size_t)2 * FK * (FM + FN) * sizeof(double);     // 64 KB
+#define NG_DENSE_FAST(FU)                                                                       \
+    do {                                                                                        \
+        static bool attr_done = false;                                                          \
+        if (!attr_done) {                                                                       \
+            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU>,                   \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                            (int)smem));                                        \
+            attr_done = true;                                                                   \
+        }                                                                                       \
+        dense_fast_kernel<DESC, FMA, FU><<<grid, 256, smem, st>>>(in, out, p->d_Mt, (int)p->n,  \
+                                                                  p->inner, p->axis, F);        \
+    } while (0)
+    if (F.any) NG_DENSE_FAST(true); else NG_DENSE_FAST(false);
+#undef NG_DENSE_FAST
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+bool fast_ok(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
+    if (p->inner == 1 || p->n % FM != 0 || p->inner % FN != 0) return false;
+    if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
+    if (F.pre.ptr) return false;                         // prologue multiply: general kernel
+    if (F.any && F.shape[F.vec_axis] % 2 != 0) return false;
+    const char* e = getenv("NG_DENSE_FAST");
+    return !(e && atoi(e) == 0);
+}
+
 template <bool LAST, bool DESC, bool FMA>
 int launch3(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     const i64 ncols = p->outer * p->inner;
@@ -139,5 +275,10 @@ int launch1(const ng_plan* p, const double* in, double* out, const FuseDev& F, c
 int ng_dense_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                     cudaStream_t st) {
     if (p->size == 0) return NG_OK;
+    if (fast_ok(p, in, out, F)) {
+        if (p->use_fma) return launch_fast<false, true>(p, in, out, F, st);
+        if (p->descending) return launch_fast<true, false>(p, in, out, F, st);
+        return launch_fast<false, false>(p, in, out, F, st);
+    }
     return p->inner == 1 ? launch1<true>(p, in, out, F, st) : launch1<false>(p, in, out, F, st);
 }

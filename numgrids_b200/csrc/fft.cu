@@ -125,6 +125,11 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
                   cudaStream_t st) {
     if (p->size == 0) return NG_OK;
     if (!p->fft_pow2) return ng_dense_launch(p, in, out, F, st);
+    {   // contiguous axis, 64 <= n <= 1024: two-pass register kernel (fft2.cu)
+        bool handled = false;
+        const int rc = ng_fft2_try_launch(p, in, out, F, st, &handled);
+        if (rc != NG_OK || handled) return rc;
+    }
     const int n = (int)p->n;
     const i64 npencil = p->outer * p->inner;
     // pencil pairs per CTA: enough butterflies for 256 threads, bounded by shared memory

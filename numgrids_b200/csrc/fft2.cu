@@ -1,0 +1,243 @@
+// fft2.cu -- production kernel of the periodic spectral derivative for a contiguous (last) axis,
+// n = 64 .. 1024 a power of two:  out = real(ifft(W * fft(f))) (reference numgrids/diff.py:133-143).
+//
+// Two-pass ("four-step") FFT held in registers, one transform per T = n/RT lanes:
+//   pass 1   each lane loads RT strided samples of TWO real pencils straight from global memory
+//            (coalesced across lanes) as one complex value a + i b, runs a radix-RT DIF network in
+//            registers (compile-time twiddles), applies the inter-pass twiddles exp(-2 pi i k t / n)
+//            from a host-built table and parks the row in shared memory (padded: conflict-free);
+//   pass 2   each lane owns G = RT/R2 sub-transforms of length R2: DIF forward, multiply by the
+//            reference's (ik)^order table (already divided by n), DIT inverse -- all in registers;
+//   pass 1'  rows come back from shared memory, conjugate twiddles, radix-RT DIT inverse, and the
+//            real / imaginary parts are stored as the two output pencils.
+// Because W is Hermitian the operator is real, so Re/Im of the complex result are D a and D b.
+// Per complex sample: 2 shared-memory round trips (64 B, i.e. 32 B per real point) instead of the
+// 2*log2(n) of the radix-2 kernel in fft.cu; only __syncwarp() is needed.  HBM traffic 16 B/point.
+// FMA is used freely: this path's tolerance is 1e-11 (BASELINE.json).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double cos32(int k) {      // cos(2 pi k / 32), k = 0..15, correctly rounded
+    switch (k) {
+        case 0: return 1.0;
+        case 1: return 0.9807852804032304;
+        case 2: return 0.9238795325112867;
+        case 3: return 0.8314696123025452;
+        case 4: return 0.7071067811865476;
+        case 5: return 0.5555702330196022;
+        case 6: return 0.3826834323650898;
+        case 7: return 0.19509032201612828;
+        case 8: return 0.0;
+        case 9: return -0.19509032201612828;
+        case 10: return -0.3826834323650898;
+        case 11: return -0.5555702330196022;
+        case 12: return -0.7071067811865476;
+        case 13: return -0.8314696123025452;
+        case 14: return -0.9238795325112867;
+        default: return -0.9807852804032304;
+    }
+}
+__device__ __forceinline__ double sin32(int k) { return cos32(k < 8 ? 8 - k : k - 8); }
+// sin(2 pi k/32) = cos(2 pi (8-k)/32) for k <= 8 and cos(2 pi (k-8)/32) for k >= 8 (both non-negative)
+
+__device__ __forceinline__ double2 cmul(double2 a, double c, double s) {     // a * (c + i s)
+    return make_double2(fma(a.x, c, -(a.y * s)), fma(a.x, s, a.y * c));
+}
+
+// multiply by exp(SIGN * 2 pi i k / 32), k in [0, 16), with the trivial cases folded at compile time
+template <int SIGN>
+__device__ __forceinline__ double2 rot32(double2 a, int k) {
+    if (k == 0) return a;
+    if (k == 8) return SIGN < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+    return cmul(a, cos32(k), SIGN < 0 ? -sin32(k) : sin32(k));
+}
+
+__host__ __device__ __forceinline__ constexpr int bitrev(int v, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) if (v & (1 << b)) r |= 1 << (bits - 1 - b);
+    return r;
+}
+template <int R> struct Log2 { static constexpr int v = 1 + Log2<R / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// Forward DIF network on x[0..R): natural order in, X[k] ends in x[bitrev(k)].
+template <int R>
+__device__ __forceinline__ void dif_forward(double2* x) {
+#pragma unroll
+    for (int s = R / 2; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if ((i & s) == 0) {
+                const double2 u = x[i], v = x[i + s];
+                x[i] = make_double2(u.x + v.x, u.y + v.y);
+                const double2 d = make_double2(u.x - v.x, u.y - v.y);
+                x[i + s] = rot32<-1>(d, (i & (s - 1)) * (16 / s));       // exp(-2 pi i j / (2s))
+            }
+        }
+    }
+}
+// Inverse DIT network: x[bitrev(k)] = X[k] in, natural order out (unnormalised).
+template <int R>
+__device__ __forceinline__ void dit_inverse(double2* x) {
+#pragma unroll
+    for (int s = 1; s <= R / 2; s <<= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if ((i & s) == 0) {
+                const double2 u = x[i];
+                const double2 v = rot32<+1>(x[i + s], (i & (s - 1)) * (16 / s));
+                x[i] = make_double2(u.x + v.x, u.y + v.y);
+                x[i + s] = make_double2(u.x - v.x, u.y - v.y);
+            }
+        }
+    }
+}
+
+// RT samples per lane in pass 1, R2 = n / RT = lanes per transform, G = RT / R2 sub-transforms per lane
+template <int RT, int R2, bool FUSED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
+                const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, FuseDev F) {
+    constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
+    constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
+    constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
+    extern __shared__ double2 fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tr = lane / T, t = lane - tr * T;
+    const i64 pair = ((i64)blockIdx.x * (blockDim.x >> 5) + warp) * TPW + tr;
+    const i64 pa = 2 * pair, pb = pa + 1;
+    const bool va = pa < npencil, vb = pb < npencil;
+    double2* S = fsm + (size_t)(warp * TPW + tr) * UNITS;
+
+    // multi-index of sample 0 of each pencil (one unravel per pencil; the FFT axis is the innermost
+    // non-unit axis, so sample idx only changes that coordinate)
+    Idx4 ia, ib;
+    if (FUSED) {
+        ia = unravel4(va ? pa * N : 0, F.shape);
+        ib = unravel4(vb ? pb * N : 0, F.shape);
+    }
+    double2 x[RT];
+    // ---- pass 1: strided samples r*R2 + t of both pencils
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const int idx = r * R2 + t;
+        double a = 0.0, b = 0.0;
+        if (va) a = in[pa * N + idx];
+        if (vb) b = in[pb * N + idx];
+        if (FUSED && F.pre.ptr) {
+            ia.i[F.vec_axis] = idx;
+            ib.i[F.vec_axis] = idx;
+            if (va) a = __dmul_rn(F.pre.ptr[coef_off(F.pre, ia)], a);
+            if (vb) b = __dmul_rn(F.pre.ptr[coef_off(F.pre, ib)], b);
+        }
+        x[r] = make_double2(a, b);
+    }
+    dif_forward<RT>(x);
+#pragma unroll
+    for (int q = 0; q < RT; ++q) {
+        const int kr = bitrev(q, LRT);
+        double2 v = x[q];
+        if (kr != 0) {
+            const double2 w = tw[kr * t];              // exp(-2 pi i kr t / n)
+            v = cmul(v, w.x, w.y);
+        }
+        S[kr * PITCH + t] = v;
+    }
+    __syncwarp();
+    // ---- pass 2: G sub-transforms of length R2, rows kr = t + T*g
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int kr = t + T * g;
+        double2* y = x + g * R2;
+#pragma unroll
+        for (int j = 0; j < R2; ++j) y[j] = S[kr * PITCH + j];
+        dif_forward<R2>(y);
+#pragma unroll
+        for (int q = 0; q < R2; ++q) {
+            const int k2 = bitrev(q, LR2);
+            const double2 w = Wn[kr + RT * k2];        // (ik)^order / n at frequency kr + RT*k2
+            y[q] = cmul(y[q], w.x, w.y);
+        }
+        dit_inverse<R2>(y);
+#pragma unroll
+        for (int j = 0; j < R2; ++j) S[kr * PITCH + j] = y[j];
+    }
+    __syncwarp();
+    // ---- pass 1': rows back, conjugate twiddles, inverse radix-RT
+#pragma unroll
+    for (int q = 0; q < RT; ++q) {
+        const int kr = bitrev(q, LRT);
+        double2 v = S[kr * PITCH + t];
+        if (kr != 0) {
+            const double2 w = tw[kr * t];
+            v = cmul(v, w.x, -w.y);
+        }
+        x[q] = v;
+    }
+    dit_inverse<RT>(x);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const int idx = r * R2 + t;
+        double a = x[r].x, b = x[r].y;
+        if (FUSED) {
+            ia.i[F.vec_axis] = idx;
+            ib.i[F.vec_axis] = idx;
+            if (va) a = fuse_tail(F, a, pa * N + idx, ia);
+            if (vb) b = fuse_tail(F, b, pb * N + idx, ib);
+        }
+        if (va) out[pa * N + idx] = a;
+        if (vb) out[pb * N + idx] = b;
+    }
+}
+
+template <int RT, int R2, int MINB>
+int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    constexpr int T = R2, TPW = 32 / T, WARPS = 8;
+    const i64 npencil = p->outer;                       // last axis: one pencil per outer index
+    const i64 pairs = (npencil + 1) / 2;
+    const i64 per_block = (i64)WARPS * TPW;
+    const unsigned grid = (unsigned)((pairs + per_block - 1) / per_block);
+    const size_t smem = (size_t)WARPS * TPW * RT * (R2 + 1) * sizeof(double2);
+#define NG_FFT2_GO(FU)                                                                            \
+    do {                                                                                          \
+        static bool attr_done = false;                                                            \
+        if (!attr_done) {                                                                         \
+            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_kernel<RT, R2, FU, MINB>,                          \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                            (int)smem));                                          \
+            attr_done = true;                                                                     \
+        }                                                                                         \
+        fft2pass_kernel<RT, R2, FU, MINB><<<grid, 32 * WARPS, smem, st>>>(                              \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
+    } while (0)
+    if (F.any) NG_FFT2_GO(true); else NG_FFT2_GO(false);
+#undef NG_FFT2_GO
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+}  // namespace
+
+// Returns NG_OK and sets *handled when this kernel family covers the plan.
+int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                       cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (p->inner != 1 || !p->d_Wn || !p->d_twn) return NG_OK;
+    const char* e = getenv("NG_FFT_TWOPASS");
+    if (e && atoi(e) == 0) return NG_OK;
+    int rc = NG_OK;
+    const char* mb = getenv("NG_FFT_MINB");
+    const int minb = mb ? atoi(mb) : 0;                 // tuning override: CTAs per SM (register cap)
+    switch (p->n) {
+        case 1024: rc = minb == 2 ? launch<32, 32, 2>(p, in, out, F, st) : launch<32, 32, 1>(p, in, out, F, st); break;
+        case 512: rc = minb == 2 ? launch<32, 16, 2>(p, in, out, F, st) : launch<32, 16, 1>(p, in, out, F, st); break;
+        case 256: rc = minb == 1 ? launch<16, 16, 1>(p, in, out, F, st)
+                     : (minb == 3 ? launch<16, 16, 3>(p, in, out, F, st) : launch<16, 16, 2>(p, in, out, F, st)); break;
+        case 128: rc = minb == 1 ? launch<16, 8, 1>(p, in, out, F, st) : launch<16, 8, 2>(p, in, out, F, st); break;
+        case 64: rc = launch<8, 8, 2>(p, in, out, F, st); break;
+        default: return NG_OK;
+    }
+    *handled = (rc == NG_OK);
+    return rc;
+}
