@@ -112,54 +112,93 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (numpy restatement of findiff + the reference idiom)
 # ---------------------------------------------------------------------------------------------
-def cpu_sample_shape(scale: int):
-    return tuple(max(16, s // scale) for s in (512, 256, 256))
+def cpu_sample_shape(scale: int, threaded: bool = True):
+    base = (1024, 512, 512) if threaded else (512, 256, 256)
+    return tuple(max(16, s // scale) for s in base)
 
 
-def time_cpu_oracle(shape, repeats: int):
-    """Oracle (oracle/pencil.py, kind 'port') on a bounded sub-block of the headline workload."""
-    from oracle import pencil
+def _cpu_field(shape):
     hs = [1.0 / 1023.0] * 3
     x, y, z = (np.arange(n) * h for n, h in zip(shape, hs))
     f = (np.sin(2 * np.pi * x)[:, None, None] * np.cos(2 * np.pi * y)[None, :, None]
          * np.exp(z)[None, None, :])
-    pencil.cartesian_laplacian(f[:32], hs, 4)                 # warm-up (BLAS/solve init)
+    return f, hs
+
+
+def time_cpu_oracle(shape, repeats: int, threaded: bool = True):
+    """The CPU restatement of the reference path on a bounded sub-block of the headline workload.
+
+    threaded: oracle/pencil_c.c (C/OpenMP, every host thread) -- same arithmetic, bit-identical to
+    the NumPy port; else oracle/pencil.py (NumPy, one thread, like the reference itself).
+    Returns (best seconds, points, cores used).
+    """
+    from oracle import pencil
+    f, hs = _cpu_field(shape)
+    if threaded:
+        from oracle import pencil_c
+        fn = lambda a: pencil_c.cartesian_laplacian3(a, hs, 4)
+        cores = pencil_c.threads()
+    else:
+        fn = lambda a: pencil.cartesian_laplacian(a, hs, 4)
+        cores = 1
+    small = np.ascontiguousarray(f[:32])
+    assert np.array_equal(fn(small), pencil.cartesian_laplacian(small, hs, 4))     # same bits as the NumPy port
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        pencil.cartesian_laplacian(f, hs, 4)
+        fn(f)
         best = min(best, time.perf_counter() - t0)
-    return best, int(np.prod(shape))
+    return best, int(np.prod(shape)), cores
+
+
+def cpu_baseline_record(scale: int, repeats: int = 3):
+    shape = cpu_sample_shape(scale, True)
+    t, pts, cores = time_cpu_oracle(shape, repeats, True)
+    shape1 = cpu_sample_shape(scale, False)
+    t1, pts1, _ = time_cpu_oracle(shape1, 1, False)
+    return {"value": pts / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-block of the workload, best of {repeats}, C/OpenMP "
+                      f"restatement (oracle/pencil_c.c, bit-identical to the NumPy port) on {cores} threads; "
+                      f"host has {os.cpu_count()} cores",
+            "numpy_1thread": {"value": pts1 / t1 / 1e9, "unit": UNIT,
+                              "sample": f"{shape1[0]}x{shape1[1]}x{shape1[2]}, oracle/pencil.py (NumPy, single-threaded "
+                                        "like the reference's findiff path)"}}
 
 
 def run_reference_arm(args):
+    """CPU arm: the reference's algorithm for the path on the host cores (every thread it can use)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     scale = args.scale
-    shape = cpu_sample_shape(scale)
+    shape = cpu_sample_shape(scale, True)
     times = []
-    from oracle import pencil  # noqa: F401
+    cores = 1
     for _ in range(args.warmup):
-        time_cpu_oracle(shape, 1)
+        time_cpu_oracle(shape, 1, True)
     for _ in range(args.steps):
-        t, pts = time_cpu_oracle(shape, 1)
+        t, pts, cores = time_cpu_oracle(shape, 1, True)
         times.append(t)
     t_step = sum(times) / len(times)
     value = pts / t_step / 1e9
     gshape = global_shape_for(args.gpus, scale)
+    shape1 = cpu_sample_shape(scale, False)
+    t1, pts1, _ = time_cpu_oracle(shape1, 1, False)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "cfg5: fused Cartesian FD Laplacian (acc=4), 1024^3 points per GPU, "
-                               "last-axis slabs", "global_shape": list(gshape),
-                   "sample_shape": list(shape)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-block of the workload, numpy "
-                                   "restatement of findiff (oracle/pencil.py), single-threaded like the reference; "
-                                   f"host has {os.cpu_count()} cores"},
+        "config": {"workload": "cfg5: fused Cartesian FD Laplacian Diff(g,2,0)+Diff(g,2,1)+Diff(g,2,2) "
+                               "(acc=4), 1024^3 points per GPU, last-axis slabs + halo exchange",
+                   "global_shape": list(gshape), "sample_shape": list(shape)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"each step = one Laplacian of a {shape[0]}x{shape[1]}x{shape[2]} sub-block of the "
+                                   f"workload; C/OpenMP restatement of the reference path (oracle/pencil_c.c, "
+                                   f"bit-identical to the NumPy port) on {cores} threads; host has {os.cpu_count()} cores",
+                         "numpy_1thread": {"value": pts1 / t1 / 1e9, "unit": UNIT,
+                                           "sample": f"{shape1[0]}x{shape1[1]}x{shape1[2]}, oracle/pencil.py (NumPy, "
+                                                     "single-threaded like the reference's findiff path)"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -468,12 +507,7 @@ def run_gpu_arm(args):
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        shape = cpu_sample_shape(scale)
-        tbest, pts = time_cpu_oracle(shape, 3)
-        cpu_baseline = {"value": pts / tbest / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-block of the workload, best of 3, "
-                                  "numpy restatement of findiff (oracle/pencil.py), single-threaded like the "
-                                  f"reference; host has {os.cpu_count()} cores"}
+        cpu_baseline = cpu_baseline_record(scale)
 
     extras = None
     if world == 1 and not args.no_extras:

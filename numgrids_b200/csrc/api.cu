@@ -285,20 +285,101 @@ int ng_apply_fused(const ng_plan* plan, const double* d_in, double* d_out, const
     return ng_apply_any(plan, d_in, d_out, F, (cudaStream_t)stream);
 }
 
+// Host-buffer pipeline shared by ng_apply_host / ng_fdlap_apply_host: the array is cut in chunks of
+// axis-0 planes; chunk k+1 is copied in (stream 0 of 3) while chunk k is computed (stream 1) and
+// chunk k-1 is copied out (stream 2), so H2D and D2H use both PCIe directions at once and the
+// kernels hide under the copies.  `launch(first_plane, last_plane, stream)` computes output planes
+// [first, last); `halo` = input planes it needs on either side (2 for the Laplacian / FD along axis
+// 0 would need the whole axis -> those run unchunked).  Pageable host memory degrades to serialised
+// copies but stays correct.
+extern "C++" {
+template <class Launch>
+static int host_pipeline(ng_plan* plan, const double* h_in, double* h_out, i64 halo, bool chunkable,
+                         Launch launch) {
+    int rc = ensure_stage(plan, 1);
+    if (rc) return rc;
+    const i64 n0 = plan->shape[0];
+    const i64 plane = plan->size / n0;                       // elements per axis-0 plane
+    static cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    if (!st[0])
+        for (int i = 0; i < 3; ++i) NG_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    // ~256 MiB chunks, at least 8 planes, at most 64 chunks
+    i64 cp = (32LL << 20) / (plane > 0 ? plane : 1);
+    if (cp < 8) cp = 8;
+    if (!chunkable || plan->size * 8 < (64LL << 20) || cp >= n0) cp = n0;
+    const int nchunk = (int)((n0 + cp - 1) / cp);
+    if (nchunk > 256) {                                       // keep the event arrays bounded
+        cp = (n0 + 255) / 256;
+    }
+    const int nc = (int)((n0 + cp - 1) / cp);
+    std::vector<cudaEvent_t> in_done((size_t)nc), out_done((size_t)nc);
+    for (int k = 0; k < nc; ++k) {
+        NG_CUDA_OK(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
+        NG_CUDA_OK(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
+    }
+    rc = NG_OK;
+    auto run_chunk = [&](int c, cudaEvent_t ready) -> int {       // compute + copy-out of chunk c
+        const i64 ca = c * cp, cb = (ca + cp < n0) ? ca + cp : n0;
+        cudaStreamWaitEvent(st[1], ready, 0);
+        int r = launch(ca, cb, st[1]);
+        if (r) return r;
+        cudaEventRecord(out_done[c], st[1]);
+        cudaStreamWaitEvent(st[2], out_done[c], 0);
+        if (cudaMemcpyAsync(h_out + ca * plane, plan->d_stage_out + ca * plane,
+                            sizeof(double) * (size_t)((cb - ca) * plane), cudaMemcpyDeviceToHost,
+                            st[2]) != cudaSuccess) return NG_ECUDA;
+        return NG_OK;
+    };
+    for (int k = 0; k < nc && rc == NG_OK; ++k) {
+        const i64 a = k * cp, b = (a + cp < n0) ? a + cp : n0;
+        if (cudaMemcpyAsync(plan->d_stage_in + a * plane, h_in + a * plane,
+                            sizeof(double) * (size_t)((b - a) * plane), cudaMemcpyHostToDevice,
+                            st[0]) != cudaSuccess) { rc = NG_ECUDA; break; }
+        cudaEventRecord(in_done[k], st[0]);
+        if (halo == 0) {
+            rc = run_chunk(k, in_done[k]);
+        } else {
+            // chunk k-1 can run once chunk k (its upper halo) has landed; the last chunk follows at once
+            if (k >= 1) rc = run_chunk(k - 1, in_done[k]);
+            if (rc == NG_OK && k == nc - 1) rc = run_chunk(k, in_done[k]);
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3; ++i) {
+        cudaError_t ei = cudaStreamSynchronize(st[i]);
+        if (ei != cudaSuccess) e = ei;
+    }
+    for (int k = 0; k < nc; ++k) { cudaEventDestroy(in_done[k]); cudaEventDestroy(out_done[k]); }
+    if (rc) return rc;
+    if (e != cudaSuccess) {
+        ng_set_error("host pipeline failed: %s", cudaGetErrorString(e));
+        return NG_ECUDA;
+    }
+    return NG_OK;
+}
+}  // extern "C++"
+
 int ng_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
     NG_REQUIRE(plan && h_in && h_out, "ng_apply_host: NULL plan or buffer");
+    NG_REQUIRE(plan->kind == PK_FD || plan->kind == PK_CHEB || plan->kind == PK_FFT,
+               "plan kind %d cannot be applied with ng_apply_host", plan->kind);
     int rc = require_device();
     if (rc) return rc;
-    rc = ensure_stage(plan, 1);
-    if (rc) return rc;
-    const size_t bytes = sizeof(double) * (size_t)plan->size;
-    NG_CUDA_OK(cudaMemcpyAsync(plan->d_stage_in, h_in, bytes, cudaMemcpyHostToDevice, 0));
-    FuseDev F = no_fuse(plan);
-    rc = ng_apply_any(plan, plan->d_stage_in, plan->d_stage_out, F, 0);
-    if (rc) return rc;
-    NG_CUDA_OK(cudaMemcpyAsync(h_out, plan->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
-    NG_CUDA_OK(cudaStreamSynchronize(0));
-    return NG_OK;
+    // pencils along an axis other than 0 are independent across axis-0 planes: chunk a shallow view
+    const bool chunkable = plan->axis != 0 && plan->ndim > 1;
+    const i64 plane = plan->size / plan->shape[0];
+    return host_pipeline(plan, h_in, h_out, 0, chunkable, [&](i64 a, i64 b, cudaStream_t s) -> int {
+        if (a == 0 && b == plan->shape[0]) {
+            FuseDev F = no_fuse(plan);
+            return ng_apply_any(plan, plan->d_stage_in, plan->d_stage_out, F, s);
+        }
+        ng_plan view = *plan;                                // tables are shared, nothing is owned
+        view.shape[0] = b - a;
+        view.size = (b - a) * plane;
+        view.outer = plan->outer / plan->shape[0] * (b - a);
+        FuseDev F = no_fuse(&view);
+        return ng_apply_any(&view, plan->d_stage_in + a * plane, plan->d_stage_out + a * plane, F, s);
+    });
 }
 
 int ng_plan_halo_width(const ng_plan* plan) {
@@ -370,15 +451,11 @@ int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
     NG_REQUIRE(plan && plan->kind == PK_FDLAP && h_in && h_out, "ng_fdlap_apply_host: bad arguments");
     int rc = require_device();
     if (rc) return rc;
-    rc = ensure_stage(plan, 1);
-    if (rc) return rc;
-    const size_t bytes = sizeof(double) * (size_t)plan->size;
-    NG_CUDA_OK(cudaMemcpyAsync(plan->d_stage_in, h_in, bytes, cudaMemcpyHostToDevice, 0));
-    rc = ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, 0, plan->shape[0], 0);
-    if (rc) return rc;
-    NG_CUDA_OK(cudaMemcpyAsync(h_out, plan->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
-    NG_CUDA_OK(cudaStreamSynchronize(0));
-    return NG_OK;
+    // output planes [a, b) need input planes [a-2, b+2) (and up to 5 further in on the global
+    // boundary, which the >= 8-plane chunks cover): run chunk k when chunk k+1 has landed
+    return host_pipeline(plan, h_in, h_out, 2, plan->ndim > 1, [&](i64 a, i64 b, cudaStream_t s) -> int {
+        return ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, a, b, s);
+    });
 }
 
 int64_t ng_plan_device_bytes(const ng_plan* plan) { return plan ? plan->device_bytes : 0; }

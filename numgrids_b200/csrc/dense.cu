@@ -150,6 +150,8 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
 
     const int npanel = n / FK;
+    Idx4 pre_ix;                                   // multi-index of (row 0, this thread's chunk column)
+    if (FUSED && F.pre.ptr) pre_ix = unravel4((o * n) * inner + c0 + (tid & 63) * 2, F.shape);
     auto stage = [&](int p, int buf) {
         const int k0 = p * FK;
         // 16 x 128 doubles each = 1024 16-byte chunks per operand; 256 threads x 4 chunks
@@ -170,6 +172,21 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
+        }
+        if (FUSED && F.pre.ptr) {
+            // prologue multiply (`coeff * v[i]`, curvilinear.py:212): each thread scales the chunks it
+            // copied itself (visible to it after wait_group), before the panel is published
+            const int k0 = (DESC ? npanel - 1 - pp : pp) * FK;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = tid + q * 256;
+                const int kk = e >> 6, ch = (e & 63) * 2;
+                Idx4 ix = pre_ix;
+                ix.i[axis] = k0 + kk;
+                const i64 po = coef_off(F.pre, ix);
+                Fs[buf][kk][ch] = __dmul_rn(F.pre.ptr[po], Fs[buf][kk][ch]);
+                Fs[buf][kk][ch + 1] = __dmul_rn(F.pre.ptr[po + F.pre.s[F.vec_axis]], Fs[buf][kk][ch + 1]);
+            }
         }
         __syncthreads();
 #pragma unroll 4
@@ -243,7 +260,6 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
 bool fast_ok(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
     if (p->inner == 1 || p->n % FM != 0 || p->inner % FN != 0) return false;
     if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
-    if (F.pre.ptr) return false;                         // prologue multiply: general kernel
     if (F.any && F.shape[F.vec_axis] % 2 != 0) return false;
     const char* e = getenv("NG_DENSE_FAST");
     return !(e && atoi(e) == 0);
