@@ -138,6 +138,12 @@ int ng_fdlap_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
 int ng_fdlap_apply_slab_range(const ng_plan* plan, const double* d_in, double* d_out,
                               const double* d_lo_halo, const double* d_hi_halo, int64_t x_begin,
                               int64_t x_end, void* stream);
+/* Halo/compute overlap along the sharded axis: z_part 1 computes the part of the slab whose
+ * stencils never touch a neighbour rank's planes (it can run while the exchange is in flight,
+ * the halo pointers are not read), z_part 2 the remaining boundary part, 0 everything.  Parts 1
+ * and 2 together always cover the slab exactly once. */
+int ng_fdlap_apply_slab_part(const ng_plan* plan, const double* d_in, double* d_out,
+                             const double* d_lo_halo, const double* d_hi_halo, int z_part, void* stream);
 int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out);
 
 /* ---- curvilinear composites: CurvilinearGrid.gradient/divergence/laplacian/curl ---------------

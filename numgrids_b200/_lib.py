@@ -57,6 +57,7 @@ SIGNATURES = {
     "ng_fdlap_apply": (C.c_int, [_P, _P, _P, _P]),
     "ng_fdlap_apply_slab": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ng_fdlap_apply_slab_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "ng_fdlap_apply_slab_part": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "ng_fdlap_apply_host": (C.c_int, [_P, _P, _P]),
     "ng_curv_plan_create": (C.c_int, [C.c_int, _I64, _PP, _PP]),
     "ng_curv_set_coef": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int64, _I64]),

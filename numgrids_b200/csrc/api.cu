@@ -304,9 +304,12 @@ static int host_pipeline(ng_plan* plan, const double* h_in, double* h_out, i64 h
     if (!st[0])
         for (int i = 0; i < 3; ++i) NG_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
     // ~256 MiB chunks, at least 8 planes, at most 64 chunks
-    i64 cp = (32LL << 20) / (plane > 0 ? plane : 1);
+    i64 chunk_elems = 32LL << 20;                             // 256 MiB
+    if (const char* e = getenv("NG_HOST_CHUNK_MB")) chunk_elems = (i64)atoi(e) * 131072;   // tests
+    if (chunk_elems < 1) chunk_elems = 1;
+    i64 cp = chunk_elems / (plane > 0 ? plane : 1);
     if (cp < 8) cp = 8;
-    if (!chunkable || plan->size * 8 < (64LL << 20) || cp >= n0) cp = n0;
+    if (!chunkable || plan->size <= chunk_elems || cp >= n0) cp = n0;
     const int nchunk = (int)((n0 + cp - 1) / cp);
     if (nchunk > 256) {                                       // keep the event arrays bounded
         cp = (n0 + 255) / 256;
@@ -433,7 +436,7 @@ int ng_fdlap_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
                         const double* d_lo_halo, const double* d_hi_halo, void* stream) {
     NG_REQUIRE(plan && plan->kind == PK_FDLAP, "ng_fdlap_apply: Laplacian plan required");
     NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fdlap_apply: bad buffers");
-    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, 0, plan->shape[0], (cudaStream_t)stream);
+    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, 0, plan->shape[0], 0, (cudaStream_t)stream);
 }
 
 int ng_fdlap_apply_slab_range(const ng_plan* plan, const double* d_in, double* d_out,
@@ -444,7 +447,15 @@ int ng_fdlap_apply_slab_range(const ng_plan* plan, const double* d_in, double* d
     NG_REQUIRE(0 <= x_begin && x_begin <= x_end && x_end <= plan->shape[0],
                "ng_fdlap_apply_slab_range: [%lld, %lld) is not inside axis 0 of %lld planes",
                (long long)x_begin, (long long)x_end, (long long)plan->shape[0]);
-    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, x_begin, x_end, (cudaStream_t)stream);
+    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, x_begin, x_end, 0, (cudaStream_t)stream);
+}
+
+int ng_fdlap_apply_slab_part(const ng_plan* plan, const double* d_in, double* d_out,
+                             const double* d_lo_halo, const double* d_hi_halo, int z_part, void* stream) {
+    NG_REQUIRE(plan && plan->kind == PK_FDLAP, "ng_fdlap_apply_slab_part: Laplacian plan required");
+    NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fdlap_apply_slab_part: bad buffers");
+    NG_REQUIRE(z_part >= 0 && z_part <= 2, "ng_fdlap_apply_slab_part: z_part must be 0, 1 or 2");
+    return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, 0, plan->shape[0], z_part, (cudaStream_t)stream);
 }
 
 int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
@@ -454,7 +465,7 @@ int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
     // output planes [a, b) need input planes [a-2, b+2) (and up to 5 further in on the global
     // boundary, which the >= 8-plane chunks cover): run chunk k when chunk k+1 has landed
     return host_pipeline(plan, h_in, h_out, 2, plan->ndim > 1, [&](i64 a, i64 b, cudaStream_t s) -> int {
-        return ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, a, b, s);
+        return ng_fdlap_launch(plan, plan->d_stage_in, plan->d_stage_out, nullptr, nullptr, a, b, 0, s);
     });
 }
 

@@ -137,7 +137,7 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
 int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                        cudaStream_t st, bool* handled);
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                    const double* hi, i64 xbeg, i64 xend, cudaStream_t st);
+                    const double* hi, i64 xbeg, i64 xend, int zmode, cudaStream_t st);
 int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                  cudaStream_t st);
 void ng_fuse_to_dev(const ng_plan* p, const ng_fuse* f, FuseDev* out);

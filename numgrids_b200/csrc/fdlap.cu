@@ -63,15 +63,17 @@ fdlap_generic_kernel(const double* __restrict__ in, double* __restrict__ out,
 }  // namespace
 
 int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                          const double* hi, int xbeg, int xend, cudaStream_t st, bool* handled);
+                          const double* hi, int xbeg, int xend, int zmode, cudaStream_t st, bool* handled);
 
 // Output planes [xbeg, xend) along axis 0 (the whole array when xbeg = 0, xend = shape[0]).
+// zmode: 0 = all of the last axis; 1 = only the part that needs no slab halo; 2 = the rest.
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                    const double* hi, i64 xbeg, i64 xend, cudaStream_t st) {
+                    const double* hi, i64 xbeg, i64 xend, int zmode, cudaStream_t st) {
     if (p->size == 0 || xend <= xbeg) return NG_OK;
     bool handled = false;
-    int rc = ng_fdlap3d_try_launch(p, in, out, lo, hi, (int)xbeg, (int)xend, st, &handled);
+    int rc = ng_fdlap3d_try_launch(p, in, out, lo, hi, (int)xbeg, (int)xend, zmode, st, &handled);
     if (rc != NG_OK || handled) return rc;
+    if (zmode == 1) return NG_OK;                 // generic kernel: part 2 computes everything
     const i64 plane = p->size / p->shape[0];
     const i64 first = xbeg * plane, last = xend * plane;
     i64 g = (last - first + 255) / 256;

@@ -736,7 +736,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* t
 template <int R, int WY, int S, int MINB, bool SLAB, bool TMAP>
 __global__ void __launch_bounds__(32 * (WY + 1), MINB)
 fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz,
-                     int xchunk, int xbeg, int xend, Lap3U W, const Lap3Side* __restrict__ side,
+                     int xchunk, int xbeg, int xend, int zmode, Lap3U W, const Lap3Side* __restrict__ side,
                      const double* __restrict__ lo, const double* __restrict__ hi,
                      const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_lo,
                      const __grid_constant__ CUtensorMap tmap_hi) {
@@ -757,7 +757,10 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     unsigned long long* empty = full + S;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int z0 = blockIdx.x * RING_TZ;
+    // zmode 0: every z tile; 1: interior tiles only (no halo dependence); 2: the first and last tile
+    const int zt_idx = zmode == 1 ? (int)blockIdx.x + 1
+                                  : (zmode == 2 ? (blockIdx.x == 0 ? 0 : nz / RING_TZ - 1) : (int)blockIdx.x);
+    const int z0 = zt_idx * RING_TZ;
     const int yb = blockIdx.y * TY;
     const int xs = xbeg + blockIdx.z * xchunk;
     const bool lo_tile = SLAB && (z0 == 0) && (lo != nullptr);
@@ -938,7 +941,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const double* lo,
-                          const double* hi, int xbeg, int xend, cudaStream_t st, bool* handled) {
+                          const double* hi, int xbeg, int xend, int zmode, cudaStream_t st, bool* handled) {
     *handled = false;
     if (p->ndim != 3) return NG_OK;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
@@ -982,7 +985,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         const int cfg_s = env_int("NG_FDLAP_S", 8);
         const bool slab = (lo != nullptr) || (hi != nullptr);
         const bool use_tmap = env_int("NG_FDLAP_TMAP", 1) != 0;
-        bool launched = false;
+        bool launched = false, skip_count = false;
 #define NG_RING2_GO1(RR, WW, SS, MB, SL, TM)                                                         \
     {                                                                                              \
         constexpr int plane = (RR * WW + 4) * RING_PITCH;                                          \
@@ -994,7 +997,10 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 128)); \
             attr_done = true;                                                                      \
         }                                                                                          \
-        dim3 grid(gx, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                             \
+        const unsigned ztiles = (unsigned)(nz / RING_TZ);                                          \
+        const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2) : gx); \
+        if (gxz == 0) { launched = true; skip_count = true; } else {                               \
+        dim3 grid(gxz, (unsigned)((ny + RR * WW - 1) / (RR * WW)), gz);                            \
         CUtensorMap tm, tm_lo, tm_hi;                                                              \
         memset(&tm, 0, sizeof(tm)); memset(&tm_lo, 0, sizeof(tm)); memset(&tm_hi, 0, sizeof(tm));  \
         if (TM) {                                                                                  \
@@ -1004,17 +1010,17 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
             if (trc) return trc;                                                                   \
         }                                                                                          \
         fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM><<<grid, 32 * (WW + 1), smem + 128, st>>>(     \
-            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, zmode, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
             tm_lo, tm_hi);                                                                         \
-        launched = true;                                                                           \
+        launched = true; }                                                                         \
     }
 #define NG_RING2_GO(RR, WW, SS, MB)                                                                \
     if (!launched && cfg_R == RR && cfg_wy == WW && cfg_s == SS &&                                 \
         (ny % (RR * WW) == 0 || ny % (RR * WW) >= 5)) {                                            \
         if (slab) {                                                                                \
-            if (use_tmap) NG_RING2_GO1(RR, WW, SS, MB, true, true)                                 \
+            if (use_tmap) { NG_RING2_GO1(RR, WW, SS, MB, true, true) }                             \
         } else {                                                                                   \
-            if (use_tmap) NG_RING2_GO1(RR, WW, SS, MB, false, true) else NG_RING2_GO1(RR, WW, SS, MB, false, false) \
+            if (use_tmap) { NG_RING2_GO1(RR, WW, SS, MB, false, true) } else { NG_RING2_GO1(RR, WW, SS, MB, false, false) } \
         }                                                                                          \
     }
         NG_RING2_GO(2, 8, 6, 2)
@@ -1030,12 +1036,17 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         NG_RING2_GO(2, 6, 8, 2)
 #undef NG_RING2_GO
 #undef NG_RING2_GO1
+        if (launched && skip_count) {          // nothing to do for this z part (e.g. no interior tiles)
+            *handled = true;
+            return NG_OK;
+        }
         if (launched) {
             NG_LAUNCH_CHECK();
             *handled = true;
             return NG_OK;
         }
     }
+    if (zmode == 1) { *handled = true; return NG_OK; }     // fallback kernels: part 2 computes everything
     if (cfg_v == 3 && nz % 64 == 0 && ny * nz < (1LL << 28) && p->d_Mt) {
         Lap3C WC;
         for (int a = 0; a < 3; ++a) {

@@ -141,12 +141,22 @@ class SlabLaplacian:
                    "ng_fdlap_apply_slab_range")
         return out
 
+    def apply_part(self, f, out, z_part, lo_halo=None, hi_halo=None):
+        """z_part 1: the columns whose stencils never read a neighbour rank (no halo needed);
+        z_part 2: the remaining boundary columns; 0: everything."""
+        lo = lo_halo.data_ptr() if lo_halo is not None else None
+        hi = hi_halo.data_ptr() if hi_halo is not None else None
+        _lib.check(_lib.load().ng_fdlap_apply_slab_part(self.plan.handle, f.data_ptr(), out.data_ptr(), lo, hi,
+                                                        int(z_part), _device.current_stream_ptr()),
+                   "ng_fdlap_apply_slab_part")
+        return out
+
     def __call__(self, f, out=None, overlap=True):
         """One distributed apply.  `f` is the local CUDA slab.
 
-        pack (one kernel) -> halo exchange -> fused stencil.  With `overlap`, axis 0 is cut in two
-        plane ranges: the exchange of the large second range runs on a side stream under the
-        stencil of the small first one, so only the pack and a 1/8-size message stay exposed.
+        pack (one kernel) -> halo exchange -> fused stencil.  With `overlap` the exchange runs on a
+        side stream while the main stream computes the interior z tiles (which never read a halo);
+        the two boundary z tiles follow once the neighbours' planes have arrived.
         """
         t = _device.torch()
         f = _device.as_device_tensor(f, self.local_shape)
@@ -157,40 +167,33 @@ class SlabLaplacian:
         lo_n, hi_n = neighbours(self.rank, self.nranks)
         lo_h = b["lo_halo"] if lo_n is not None else None
         hi_h = b["hi_halo"] if hi_n is not None else None
-        nx = self.local_shape[0]
-        if not overlap or len(self.local_shape) != 3 or nx < 32:
+        tm = getattr(self, "stencil_events", None)        # optional [(e0, e1, e2, e3), ...] sink for bench.py
+        if not overlap or len(self.local_shape) != 3:
             exchange_halos(b["lo_planes"], b["hi_planes"], b["lo_halo"], b["hi_halo"], self.rank, self.nranks,
                            self.group)
             return self.apply_local(f, out, lo_h, hi_h)
-        xa = max(8, nx // 8)
-        ra = xa * (self.rows // nx)                       # halo rows of planes [0, xa)
         main = t.cuda.current_stream()
         if getattr(self, "_comm_stream", None) is None:
             self._comm_stream = t.cuda.Stream()
         comm = self._comm_stream
         comm.wait_stream(main)                            # the pack kernel
         with t.cuda.stream(comm):
-            exchange_halos(b["lo_planes"][:ra], b["hi_planes"][:ra], b["lo_halo"][:ra], b["hi_halo"][:ra],
-                           self.rank, self.nranks, self.group)
-            ev_a = comm.record_event()
-            exchange_halos(b["lo_planes"][ra:], b["hi_planes"][ra:], b["lo_halo"][ra:], b["hi_halo"][ra:],
-                           self.rank, self.nranks, self.group)
-            ev_b = comm.record_event()
-        tm = getattr(self, "stencil_events", None)        # optional [(start, end), ...] sink for bench.py
-        main.wait_event(ev_a)
+            exchange_halos(b["lo_planes"], b["hi_planes"], b["lo_halo"], b["hi_halo"], self.rank, self.nranks,
+                           self.group)
+            ev = comm.record_event()
         if tm is not None:
             e = [t.cuda.Event(enable_timing=True) for _ in range(4)]
             e[0].record()
-        self.apply_range(f, out, 0, xa, lo_h, hi_h)
+        self.apply_part(f, out, 1, lo_h, hi_h)            # interior z tiles: no halo dependence
         if tm is not None:
             e[1].record()
-        main.wait_event(ev_b)
+        main.wait_event(ev)
         if tm is not None:
             e[2].record()
-        self.apply_range(f, out, xa, nx, lo_h, hi_h)
+        self.apply_part(f, out, 2, lo_h, hi_h)            # first / last z tile (or everything on fallbacks)
         if tm is not None:
             e[3].record()
-            tm.append((e[0], e[1], e[2], e[3]))
+            tm.append(tuple(e))
         return out
 
     # -- single-GPU emulation of all ranks (tests; no inter-process waits, see B200_PROFILING.md) ----

@@ -143,8 +143,10 @@ def test_linearity_and_constants_full_size(gpu_ready):
 def test_host_pipeline_chunked_paths(gpu_ready):
     """Arrays >= 64 MiB go through the chunked H2D / compute / D2H pipeline of the *_host entry
     points; results must equal the device-resident path bit for bit."""
+    import os
     import torch
-    n = 224                                            # 224^3 doubles = 86 MiB -> several axis-0 chunks
+    os.environ["NG_HOST_CHUNK_MB"] = "8"               # force chunking (default chunk is 256 MiB)
+    n = 224                                            # 224^3 doubles = 86 MiB -> 11 axis-0 chunks
     ax = ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0)
     g = ng.Grid(ax, ax, ax)
     rng = np.random.default_rng(5)
@@ -160,6 +162,7 @@ def test_host_pipeline_chunked_paths(gpu_ready):
     f2 = rng.standard_normal(g2.shape)
     d = ng.Diff(g2, 1, 2)
     assert np.array_equal(d(f2), d(torch.from_numpy(f2).cuda()).cpu().numpy())
+    del os.environ["NG_HOST_CHUNK_MB"]
 
 
 def test_laplacian_plane_ranges(gpu_ready):
@@ -176,3 +179,22 @@ def test_laplacian_plane_ranges(gpu_ready):
         for a, b in zip(cuts[:-1], cuts[1:]):
             lap.apply_range(f, out, a, b)
         assert torch.equal(out, ref), cuts
+
+
+def test_laplacian_z_parts(gpu_ready):
+    """Interior + boundary z parts (the halo/compute overlap split) cover the slab exactly once."""
+    import torch
+    from numgrids_b200.slab import SlabLaplacian
+    for shape in ((24, 40, 256), (20, 16, 64), (18, 24, 128), (9, 11, 70)):
+        lap = SlabLaplacian(shape, [0.01, 0.02, 0.03])
+        torch.manual_seed(3)
+        f = torch.randn(*shape, dtype=torch.float64, device="cuda")
+        rows = shape[0] * shape[1]
+        lo = torch.randn(rows, 2, dtype=torch.float64, device="cuda")
+        hi = torch.randn(rows, 2, dtype=torch.float64, device="cuda")
+        for halos in ((None, None), (lo, hi), (lo, None)):
+            ref = lap.apply_local(f, torch.empty_like(f), *halos)
+            out = torch.full_like(f, float("nan"))
+            lap.apply_part(f, out, 1, *halos)
+            lap.apply_part(f, out, 2, *halos)
+            assert torch.equal(out, ref), (shape, [h is not None for h in halos])
