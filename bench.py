@@ -523,7 +523,11 @@ def run_gpu_arm(args):
                                "(acc=4), 1024^3 points per GPU, last-axis slabs + halo exchange",
                    "global_shape": list(gshape), "local_shape": list(f.shape),
                    "l2": "inputs (8 GiB in + 8 GiB out per GPU) are far larger than the 126 MB L2; no flush needed",
-                   "field": "sin(2 pi X) cos(2 pi Y) exp(Z) from global coordinates"},
+                   "field": "sin(2 pi X) cos(2 pi Y) exp(Z) from global coordinates",
+                   "halo_exchange": ("none (1 GPU)" if world == 1 else
+                                     ("NVLink peer stores from the pack kernel (symmetric memory) + per-neighbour signals"
+                                      if getattr(slab, "_symm", None) is not None else
+                                      "NCCL send/recv: " + str(getattr(slab, "_symm_error", "disabled"))))},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "per_config": extras,
     }

@@ -73,6 +73,53 @@ def make_fd_plan(shape, axis_index, order, acc, h) -> _lib.Plan:
     return _lib.Plan(out.value)
 
 
+class SymmetricHalo:
+    """Halo buffers in NVLink peer memory (torch symmetric memory): a rank's pack kernel stores its
+    boundary planes DIRECTLY into the neighbours' halo buffers (P2P stores over NVLink/NVSwitch),
+    followed by a per-neighbour signal -- pack and exchange are one kernel, no NCCL send/recv
+    kernels compete with the stencil for SMs.  Two buffer sets alternate per step; the signal chain
+    orders a rank's overwrite of set q after the neighbour's last read of it (the neighbour signals
+    step s only after its stencil of step s-1 was enqueued ahead on the same stream dependency).
+    """
+
+    def __init__(self, rows, nb, device, rank, nranks, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.nranks = rank, nranks
+        self.shape = (2, 2, rows, nb)                     # [set][side: 0 = lo halo, 1 = hi halo][rows][nb]
+        self.buf = symm.empty(self.shape, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.lo_n, self.hi_n = neighbours(rank, nranks)
+        self.peer_lo = self.hdl.get_buffer(self.lo_n, self.shape, torch.float64) if self.lo_n is not None else None
+        self.peer_hi = self.hdl.get_buffer(self.hi_n, self.shape, torch.float64) if self.hi_n is not None else None
+        self.step = 0
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=0)
+
+    def targets(self, q):
+        """Where my first / last planes go: the lower neighbour's hi halo, the upper neighbour's lo halo."""
+        return (self.peer_lo[q, 1] if self.peer_lo is not None else None,
+                self.peer_hi[q, 0] if self.peer_hi is not None else None)
+
+    def mine(self, q):
+        return (self.buf[q, 0] if self.lo_n is not None else None,
+                self.buf[q, 1] if self.hi_n is not None else None)
+
+    def signal_and_wait(self, q, timeout_ms=20000):
+        """After the pack kernel on the current stream: tell both neighbours their halo set q is
+        complete, then wait for theirs (channels 2q / 2q+1 keep the two directions apart)."""
+        if self.hi_n is not None:
+            self.hdl.put_signal(self.hi_n, 2 * q, timeout_ms)          # upward traffic
+        if self.lo_n is not None:
+            self.hdl.put_signal(self.lo_n, 2 * q + 1, timeout_ms)      # downward traffic
+        if self.lo_n is not None:
+            self.hdl.wait_signal(self.lo_n, 2 * q, timeout_ms)
+        if self.hi_n is not None:
+            self.hdl.wait_signal(self.hi_n, 2 * q + 1, timeout_ms)
+
+
 class SlabLaplacian:
     """Fused Cartesian Laplacian on this rank's last-axis slab of a global equidistant grid."""
 
@@ -163,6 +210,8 @@ class SlabLaplacian:
         out = t.empty_like(f) if out is None else out
         if self.nranks == 1:
             return self.apply_local(f, out)
+        if self._use_symm(f):
+            return self._call_symm(f, out)
         b = self.pack(f)
         lo_n, hi_n = neighbours(self.rank, self.nranks)
         lo_h = b["lo_halo"] if lo_n is not None else None
@@ -191,6 +240,55 @@ class SlabLaplacian:
         if tm is not None:
             e[2].record()
         self.apply_part(f, out, 2, lo_h, hi_h)            # first / last z tile (or everything on fallbacks)
+        if tm is not None:
+            e[3].record()
+            tm.append(tuple(e))
+        return out
+
+    # -- NVLink peer-memory exchange (pack kernel stores straight into the neighbours' halos) -------
+    def _use_symm(self, f):
+        import os
+        mode = os.environ.get("NG_SLAB_EXCHANGE", "symm")
+        if mode != "symm" or len(self.local_shape) != 3 or getattr(self, "_symm_failed", False):
+            return False
+        if getattr(self, "_symm", None) is None:
+            try:
+                self._symm = SymmetricHalo(self.rows, self.nb, f.device, self.rank, self.nranks, self.group)
+            except Exception as e:          # symmetric memory not available: NCCL send/recv path
+                self._symm_failed = True
+                self._symm_error = repr(e)
+                return False
+        return True
+
+    def _call_symm(self, f, out):
+        t = _device.torch()
+        sh = self._symm
+        q = sh.step & 1
+        sh.step += 1
+        main = t.cuda.current_stream()
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = t.cuda.Stream()
+        comm = self._comm_stream
+        comm.wait_stream(main)            # f is ready; my previous stencil (reader of set q) is ordered before
+        with t.cuda.stream(comm):
+            to_lo, to_hi = sh.targets(q)
+            _lib.check(_lib.load().ng_fd_pack_halo(
+                self.plan.handle, f.data_ptr(), to_lo.data_ptr() if to_lo is not None else None,
+                to_hi.data_ptr() if to_hi is not None else None, _device.current_stream_ptr()), "ng_fd_pack_halo")
+            sh.signal_and_wait(q)
+            ev = comm.record_event()
+        lo_h, hi_h = sh.mine(q)
+        tm = getattr(self, "stencil_events", None)
+        if tm is not None:
+            e = [t.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
+        self.apply_part(f, out, 1, lo_h, hi_h)            # interior z tiles under the exchange
+        if tm is not None:
+            e[1].record()
+        main.wait_event(ev)
+        if tm is not None:
+            e[2].record()
+        self.apply_part(f, out, 2, lo_h, hi_h)
         if tm is not None:
             e[3].record()
             tm.append(tuple(e))
