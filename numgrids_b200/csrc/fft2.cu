@@ -191,6 +191,188 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Persistent variant with asynchronous input staging (n >= 512, where 32 samples per lane leave only
+// 8 warps per SM and global-load latency was exposed): every transform slot owns a raw-input
+// buffer filled by cp.async.bulk (one 8 KB copy per pencil, completing on the slot's mbarrier).
+// As soon as a slot has pulled its samples into registers it issues the copy for its NEXT pair,
+// which lands under the three compute passes of the current one.
+// -------------------------------------------------------------------------------------------------
+constexpr int PF_WARPS = 6;
+
+__device__ __forceinline__ unsigned pf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pf_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pf_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pf_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pf_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pf_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = pf_smem_u32(bar);
+    unsigned done, spins = 0;
+    do {
+        if (++spins > (1u << 24)) __trap();          // bounded: a protocol bug must not hang the GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void pf_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(pf_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pf_smem_u32(bar)) : "memory");
+}
+
+template <int RT, int R2, bool FUSED>
+__global__ void __launch_bounds__(32 * PF_WARPS, 1)
+fft2pass_pf_kernel(const double* __restrict__ in, double* __restrict__ out,
+                   const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, FuseDev F) {
+    constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
+    constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
+    constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
+    constexpr int NSLOT = PF_WARPS * TPW;
+    extern __shared__ __align__(128) double2 psm[];
+    double2* Sall = psm;                                            // [NSLOT][UNITS]
+    double* rawall = reinterpret_cast<double*>(psm + (size_t)NSLOT * UNITS);   // [NSLOT][2][N]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rawall + (size_t)NSLOT * 2 * N);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tr = lane / T, t = lane - tr * T;
+    const int slot = warp * TPW + tr;
+    double2* S = Sall + (size_t)slot * UNITS;
+    double* raw = rawall + (size_t)slot * 2 * N;
+    unsigned long long* bar = bars + slot;
+    const i64 npairs = (npencil + 1) / 2;
+    const i64 stride = (i64)gridDim.x * NSLOT;
+
+    if (t == 0) pf_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    auto issue = [&](i64 pair) {                 // called by lane t == 0 of the slot
+        const i64 pa = 2 * pair, pb = pa + 1;
+        const bool vb = pb < npencil;
+        pf_mbar_expect_tx(bar, (unsigned)(N * 8 * (vb ? 2 : 1)));
+        pf_bulk_g2s(raw, in + pa * N, N * 8, bar);
+        if (vb) pf_bulk_g2s(raw + N, in + pb * N, N * 8, bar);
+    };
+    i64 pair = (i64)blockIdx.x * NSLOT + slot;
+    if (t == 0 && pair < npairs) issue(pair);
+    unsigned phase = 0;
+    for (; pair < npairs; pair += stride) {
+        const i64 pa = 2 * pair, pb = pa + 1;
+        const bool vb = pb < npencil;
+        Idx4 ia, ib;
+        if (FUSED) {
+            ia = unravel4(pa * N, F.shape);
+            ib = unravel4(vb ? pb * N : 0, F.shape);
+        }
+        pf_mbar_wait(bar, phase);
+        phase ^= 1;
+        double2 x[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int idx = r * R2 + t;
+            double a = raw[idx], b = vb ? raw[N + idx] : 0.0;
+            if (FUSED && F.pre.ptr) {
+                ia.i[F.vec_axis] = idx;
+                ib.i[F.vec_axis] = idx;
+                a = __dmul_rn(F.pre.ptr[coef_off(F.pre, ia)], a);
+                if (vb) b = __dmul_rn(F.pre.ptr[coef_off(F.pre, ib)], b);
+            }
+            x[r] = make_double2(a, b);
+        }
+        __syncwarp();                              // every lane of the slot has its samples in registers
+        if (t == 0 && pair + stride < npairs) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(pair + stride);                  // next pair streams in under the compute below
+        }
+        dif_forward<RT>(x);
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const int kr = bitrev(q, LRT);
+            double2 v = x[q];
+            if (kr != 0) {
+                const double2 w = tw[kr * t];
+                v = cmul(v, w.x, w.y);
+            }
+            S[kr * PITCH + t] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int kr = t + T * g;
+            double2* y = x + g * R2;
+#pragma unroll
+            for (int j = 0; j < R2; ++j) y[j] = S[kr * PITCH + j];
+            dif_forward<R2>(y);
+#pragma unroll
+            for (int q = 0; q < R2; ++q) {
+                const int k2 = bitrev(q, LR2);
+                const double2 w = Wn[kr + RT * k2];
+                y[q] = cmul(y[q], w.x, w.y);
+            }
+            dit_inverse<R2>(y);
+#pragma unroll
+            for (int j = 0; j < R2; ++j) S[kr * PITCH + j] = y[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const int kr = bitrev(q, LRT);
+            double2 v = S[kr * PITCH + t];
+            if (kr != 0) {
+                const double2 w = tw[kr * t];
+                v = cmul(v, w.x, -w.y);
+            }
+            x[q] = v;
+        }
+        dit_inverse<RT>(x);
+        __syncwarp();                              // S is rewritten by the next transform's pass 1
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int idx = r * R2 + t;
+            double a = x[r].x, b = x[r].y;
+            if (FUSED) {
+                ia.i[F.vec_axis] = idx;
+                ib.i[F.vec_axis] = idx;
+                a = fuse_tail(F, a, pa * N + idx, ia);
+                if (vb) b = fuse_tail(F, b, pb * N + idx, ib);
+            }
+            out[pa * N + idx] = a;
+            if (vb) out[pb * N + idx] = b;
+        }
+    }
+}
+
+template <int RT, int R2>
+int launch_pf(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    constexpr int T = R2, TPW = 32 / T, N = RT * R2, NSLOT = PF_WARPS * TPW;
+    const i64 npencil = p->outer;
+    const i64 pairs = (npencil + 1) / 2;
+    i64 g = (pairs + NSLOT - 1) / NSLOT;
+    if (g > 148) g = 148;                                // persistent: one CTA per SM
+    const size_t smem = (size_t)NSLOT * (RT * (R2 + 1) * sizeof(double2) + 2 * N * sizeof(double) + 8) + 128;
+#define NG_FFT2_PF(FU)                                                                            \
+    do {                                                                                          \
+        static bool attr_done = false;                                                            \
+        if (!attr_done) {                                                                         \
+            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_pf_kernel<RT, R2, FU>,                       \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                            (int)smem));                                          \
+            attr_done = true;                                                                     \
+        }                                                                                         \
+        fft2pass_pf_kernel<RT, R2, FU><<<(unsigned)g, 32 * PF_WARPS, smem, st>>>(                 \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
+    } while (0)
+    if (F.any) NG_FFT2_PF(true); else NG_FFT2_PF(false);
+#undef NG_FFT2_PF
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
 template <int RT, int R2, int MINB>
 int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     constexpr int T = R2, TPW = 32 / T, WARPS = 8;
@@ -229,13 +411,15 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
     int rc = NG_OK;
     const char* mb = getenv("NG_FFT_MINB");
     const int minb = mb ? atoi(mb) : 0;                 // tuning override: CTAs per SM (register cap)
+    (void)minb;
+    const char* pfe = getenv("NG_FFT_PREFETCH");
+    const bool pf = !(pfe && atoi(pfe) == 0) && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * PF_WARPS;
     switch (p->n) {
-        case 1024: rc = minb == 2 ? launch<32, 32, 2>(p, in, out, F, st) : launch<32, 32, 1>(p, in, out, F, st); break;
-        case 512: rc = minb == 2 ? launch<32, 16, 2>(p, in, out, F, st) : launch<32, 16, 1>(p, in, out, F, st); break;
-        case 256: rc = minb == 1 ? launch<16, 16, 1>(p, in, out, F, st)
-                     : (minb == 3 ? launch<16, 16, 3>(p, in, out, F, st) : launch<16, 16, 2>(p, in, out, F, st)); break;
-        case 128: rc = minb == 1 ? launch<16, 8, 1>(p, in, out, F, st) : launch<16, 8, 2>(p, in, out, F, st); break;
-        case 64: rc = launch<8, 8, 2>(p, in, out, F, st); break;
+        case 1024: rc = pf ? launch_pf<32, 32>(p, in, out, F, st) : launch<32, 32, 1>(p, in, out, F, st); break;
+        case 512: rc = pf ? launch_pf<32, 16>(p, in, out, F, st) : launch<32, 16, 1>(p, in, out, F, st); break;
+        case 256: rc = launch<16, 16, 1>(p, in, out, F, st); break;
+        case 128: rc = launch<16, 8, 1>(p, in, out, F, st); break;
+        case 64: rc = launch<8, 8, 1>(p, in, out, F, st); break;
         default: return NG_OK;
     }
     *handled = (rc == NG_OK);
