@@ -130,36 +130,45 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool DESC, bool FMA, bool FUSED>
-__global__ void __launch_bounds__(256, 1)
+// NCP = column pairs per thread: 4 -> 128-column tiles (8x8 outputs per thread, big problems),
+// 1 -> 32-column tiles (8x2 per thread, several CTAs per SM): small grids such as cfg4 need the finer
+// tiles to balance 148 SMs (256 big tiles would leave a 27 % idle tail).
+template <bool DESC, bool FMA, bool FUSED, int NCP>
+__global__ void __launch_bounds__(256, NCP == 4 ? 1 : 2)
 dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                   const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F) {
+    constexpr int TFN = 32 * NCP, HALF = TFN / 2;
     extern __shared__ __align__(16) double dsm[];
-    double (*Ms)[FK][FM] = reinterpret_cast<double (*)[FK][FM]>(dsm);                 // [2][FK][FM]
-    double (*Fs)[FK][FN] = reinterpret_cast<double (*)[FK][FN]>(dsm + 2 * FK * FM);   // [2][FK][FN]
-    const i64 col0 = (i64)blockIdx.x * FN;          // flattened (o, c) column; tiles never straddle o
+    double (*Ms)[FK][FM] = reinterpret_cast<double (*)[FK][FM]>(dsm);                  // [2][FK][FM]
+    double (*Fs)[FK][TFN] = reinterpret_cast<double (*)[FK][TFN]>(dsm + 2 * FK * FM);  // [2][FK][TFN]
+    const i64 col0 = (i64)blockIdx.x * TFN;         // flattened (o, c) column; tiles never straddle o
     const int row0 = blockIdx.y * FM;
     const i64 o = col0 / inner, c0 = col0 - o * inner;
     const double* fbase = in + o * (i64)n * inner + c0;        // element (k, c) at fbase + k*inner + c
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
-    double acc[8][8];
+    double acc[8][2 * NCP];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < 2 * NCP; ++b) acc[a][b] = 0.0;
 
     const int npanel = n / FK;
     Idx4 pre_ix;                                   // multi-index of (row 0, this thread's chunk column)
-    if (FUSED && F.pre.ptr) pre_ix = unravel4((o * n) * inner + c0 + (tid & 63) * 2, F.shape);
+    if (FUSED && F.pre.ptr) pre_ix = unravel4((o * n) * inner + c0 + (tid % HALF) * 2, F.shape);
     auto stage = [&](int p, int buf) {
         const int k0 = p * FK;
-        // 16 x 128 doubles each = 1024 16-byte chunks per operand; 256 threads x 4 chunks
+        // M panel: 16 x 128 doubles = 1024 16-byte chunks (4 per thread); F panel: 16 x TFN (NCP per thread)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int e = tid + q * 256;
             const int kk = e >> 6, ch = (e & 63) * 2;
             cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * n + row0 + ch);
+        }
+#pragma unroll
+        for (int q = 0; q < NCP; ++q) {
+            const int e = tid + q * 256;
+            const int kk = e / HALF, ch = (e % HALF) * 2;
             cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
         }
         cp_async_commit();
@@ -178,9 +187,9 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             // copied itself (visible to it after wait_group), before the panel is published
             const int k0 = (DESC ? npanel - 1 - pp : pp) * FK;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NCP; ++q) {
                 const int e = tid + q * 256;
-                const int kk = e >> 6, ch = (e & 63) * 2;
+                const int kk = e / HALF, ch = (e % HALF) * 2;
                 Idx4 ix = pre_ix;
                 ix.i[axis] = k0 + kk;
                 const i64 po = coef_off(F.pre, ix);
@@ -192,18 +201,21 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll 4
         for (int q = 0; q < FK; ++q) {
             const int kk = DESC ? FK - 1 - q : q;
-            double a[8], b[8];
+            double a[8], b[2 * NCP];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const double2 av = *reinterpret_cast<const double2*>(&Ms[buf][kk][ty * 2 + 32 * j]);
-                const double2 bv = *reinterpret_cast<const double2*>(&Fs[buf][kk][tx * 2 + 32 * j]);
                 a[2 * j] = av.x; a[2 * j + 1] = av.y;
+            }
+#pragma unroll
+            for (int j = 0; j < NCP; ++j) {
+                const double2 bv = *reinterpret_cast<const double2*>(&Fs[buf][kk][tx * 2 + 32 * j]);
                 b[2 * j] = bv.x; b[2 * j + 1] = bv.y;
             }
 #pragma unroll
             for (int x = 0; x < 8; ++x)
 #pragma unroll
-                for (int y = 0; y < 8; ++y) {
+                for (int y = 0; y < 2 * NCP; ++y) {
                     if (FMA) acc[x][y] = fma(a[x], b[y], acc[x][y]);
                     else acc[x][y] = __dadd_rn(acc[x][y], __dmul_rn(a[x], b[y]));
                 }
@@ -213,7 +225,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     // ---- epilogue: rows ty*2 + {0,1} + 32*jr, column pairs tx*2 + 32*jc.  One unravel per column
     // pair (the row only changes the coordinate along `axis`).
 #pragma unroll
-    for (int jc = 0; jc < 4; ++jc) {
+    for (int jc = 0; jc < NCP; ++jc) {
         const i64 lin0 = (o * n) * inner + c0 + tx * 2 + 32 * jc;       // row 0 of this column pair
         Idx4 ix0;
         if (FUSED) ix0 = unravel4(lin0, F.shape);
@@ -234,22 +246,23 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
-template <bool DESC, bool FMA>
-int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+template <bool DESC, bool FMA, int NCP>
+int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    constexpr int TFN = 32 * NCP;
     const i64 ncols = p->outer * p->inner;
-    dim3 grid((unsigned)(ncols / FN), (unsigned)(p->n / FM));
-    const size_t smem = (size_t)2 * FK * (FM + FN) * sizeof(double);     // 64 KB
+    dim3 grid((unsigned)(ncols / TFN), (unsigned)(p->n / FM));
+    const size_t smem = (size_t)2 * FK * (FM + TFN) * sizeof(double);
 #define NG_DENSE_FAST(FU)                                                                       \
     do {                                                                                        \
         static bool attr_done = false;                                                          \
         if (!attr_done) {                                                                       \
-            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU>,                   \
+            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU, NCP>,              \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                             (int)smem));                                        \
             attr_done = true;                                                                   \
         }                                                                                       \
-        dense_fast_kernel<DESC, FMA, FU><<<grid, 256, smem, st>>>(in, out, p->d_Mt, (int)p->n,  \
-                                                                  p->inner, p->axis, F);        \
+        dense_fast_kernel<DESC, FMA, FU, NCP><<<grid, 256, smem, st>>>(                         \
+            in, out, p->d_Mt, (int)p->n, p->inner, p->axis, F);                                 \
     } while (0)
     if (F.any) NG_DENSE_FAST(true); else NG_DENSE_FAST(false);
 #undef NG_DENSE_FAST
@@ -257,8 +270,18 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
     return NG_OK;
 }
 
+template <bool DESC, bool FMA>
+int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    const i64 big_tiles = (p->outer * p->inner / FN) * (p->n / FM);
+    const char* e = getenv("NG_DENSE_NCP");
+    const int force = e ? atoi(e) : 0;
+    const bool wide = force ? force == 4 : (big_tiles >= 4 * 148 && p->inner % FN == 0);
+    if (wide && p->inner % FN == 0) return launch_fast2<DESC, FMA, 4>(p, in, out, F, st);
+    return launch_fast2<DESC, FMA, 1>(p, in, out, F, st);
+}
+
 bool fast_ok(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
-    if (p->inner == 1 || p->n % FM != 0 || p->inner % FN != 0) return false;
+    if (p->inner == 1 || p->n % FM != 0 || p->inner % 32 != 0) return false;
     if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
     if (F.any && F.shape[F.vec_axis] % 2 != 0) return false;
     const char* e = getenv("NG_DENSE_FAST");
