@@ -126,6 +126,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -133,7 +137,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // NCP = column pairs per thread: 4 -> 128-column tiles (8x8 outputs per thread, big problems),
 // 1 -> 32-column tiles (8x2 per thread, several CTAs per SM): small grids such as cfg4 need the finer
 // tiles to balance 148 SMs (256 big tiles would leave a 27 % idle tail).
-template <bool DESC, bool FMA, bool FUSED, int NCP>
+// LASTAX: the contraction axis is the contiguous one (pencil r = row of a [R][n] matrix, Out = F Mt):
+// the F panel is transposed on the fly by 8-byte cp.async (source coalesced along k), outputs are
+// stored as (i, i+1) pairs of one pencil.
+template <bool DESC, bool FMA, bool FUSED, int NCP, bool LASTAX>
 __global__ void __launch_bounds__(256, NCP == 4 ? 1 : 2)
 dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                   const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F) {
@@ -143,8 +150,9 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     double (*Fs)[FK][TFN] = reinterpret_cast<double (*)[FK][TFN]>(dsm + 2 * FK * FM);  // [2][FK][TFN]
     const i64 col0 = (i64)blockIdx.x * TFN;         // flattened (o, c) column; tiles never straddle o
     const int row0 = blockIdx.y * FM;
-    const i64 o = col0 / inner, c0 = col0 - o * inner;
-    const double* fbase = in + o * (i64)n * inner + c0;        // element (k, c) at fbase + k*inner + c
+    const i64 o = LASTAX ? 0 : col0 / inner, c0 = LASTAX ? 0 : col0 - o * inner;
+    // element (k, c): fbase + k*inner + c;  LASTAX: pencil r = col0 + c, element (k, c) at fbase + c*n + k
+    const double* fbase = LASTAX ? in + col0 * (i64)n : in + o * (i64)n * inner + c0;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
     double acc[8][2 * NCP];
@@ -155,7 +163,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 
     const int npanel = n / FK;
     Idx4 pre_ix;                                   // multi-index of (row 0, this thread's chunk column)
-    if (FUSED && F.pre.ptr) pre_ix = unravel4((o * n) * inner + c0 + (tid % HALF) * 2, F.shape);
+    if (FUSED && F.pre.ptr && !LASTAX) pre_ix = unravel4((o * n) * inner + c0 + (tid % HALF) * 2, F.shape);
     auto stage = [&](int p, int buf) {
         const int k0 = p * FK;
         // M panel: 16 x 128 doubles = 1024 16-byte chunks (4 per thread); F panel: 16 x TFN (NCP per thread)
@@ -165,11 +173,21 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             const int kk = e >> 6, ch = (e & 63) * 2;
             cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * n + row0 + ch);
         }
+        if (LASTAX) {
+            // 16 x TFN doubles as 8-byte copies: consecutive threads walk k (128 B contiguous per pencil)
 #pragma unroll
-        for (int q = 0; q < NCP; ++q) {
-            const int e = tid + q * 256;
-            const int kk = e / HALF, ch = (e % HALF) * 2;
-            cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
+            for (int q = 0; q < 2 * NCP; ++q) {
+                const int e = tid + q * 256;
+                const int kk = e & 15, c = e >> 4;
+                cp_async8(&Fs[buf][kk][c], fbase + (i64)c * n + k0 + kk);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NCP; ++q) {
+                const int e = tid + q * 256;
+                const int kk = e / HALF, ch = (e % HALF) * 2;
+                cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
+            }
         }
         cp_async_commit();
     };
@@ -186,15 +204,25 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             // prologue multiply (`coeff * v[i]`, curvilinear.py:212): each thread scales the chunks it
             // copied itself (visible to it after wait_group), before the panel is published
             const int k0 = (DESC ? npanel - 1 - pp : pp) * FK;
+            if (LASTAX) {
 #pragma unroll
-            for (int q = 0; q < NCP; ++q) {
-                const int e = tid + q * 256;
-                const int kk = e / HALF, ch = (e % HALF) * 2;
-                Idx4 ix = pre_ix;
-                ix.i[axis] = k0 + kk;
-                const i64 po = coef_off(F.pre, ix);
-                Fs[buf][kk][ch] = __dmul_rn(F.pre.ptr[po], Fs[buf][kk][ch]);
-                Fs[buf][kk][ch + 1] = __dmul_rn(F.pre.ptr[po + F.pre.s[F.vec_axis]], Fs[buf][kk][ch + 1]);
+                for (int q = 0; q < 2 * NCP; ++q) {
+                    const int e = tid + q * 256;
+                    const int kk = e & 15, c = e >> 4;
+                    const Idx4 ix = unravel4((col0 + c) * (i64)n + k0 + kk, F.shape);
+                    Fs[buf][kk][c] = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], Fs[buf][kk][c]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NCP; ++q) {
+                    const int e = tid + q * 256;
+                    const int kk = e / HALF, ch = (e % HALF) * 2;
+                    Idx4 ix = pre_ix;
+                    ix.i[axis] = k0 + kk;
+                    const i64 po = coef_off(F.pre, ix);
+                    Fs[buf][kk][ch] = __dmul_rn(F.pre.ptr[po], Fs[buf][kk][ch]);
+                    Fs[buf][kk][ch + 1] = __dmul_rn(F.pre.ptr[po + F.pre.s[F.vec_axis]], Fs[buf][kk][ch + 1]);
+                }
             }
         }
         __syncthreads();
@@ -222,6 +250,30 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         }
         __syncthreads();
     }
+    if (LASTAX) {
+        // out[(col0 + c)*n + i]: store (i, i+1) pairs of one pencil; one unravel per pencil
+#pragma unroll
+        for (int y = 0; y < 2 * NCP; ++y) {
+            const i64 r = col0 + tx * 2 + (y & 1) + 32 * (y >> 1);
+            Idx4 ix0;
+            if (FUSED) ix0 = unravel4(r * (i64)n, F.shape);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = row0 + ty * 2 + 32 * j;
+                const i64 lin = r * (i64)n + i;
+                double2 v = make_double2(acc[2 * j][y], acc[2 * j + 1][y]);
+                if (FUSED) {
+                    Idx4 ix = ix0;
+                    ix.i[axis] = i;
+                    v.x = fuse_tail(F, v.x, lin, ix);
+                    ix.i[axis] = i + 1;
+                    v.y = fuse_tail(F, v.y, lin + 1, ix);
+                }
+                *reinterpret_cast<double2*>(out + lin) = v;
+            }
+        }
+        return;
+    }
     // ---- epilogue: rows ty*2 + {0,1} + 32*jr, column pairs tx*2 + 32*jc.  One unravel per column
     // pair (the row only changes the coordinate along `axis`).
 #pragma unroll
@@ -246,7 +298,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
-template <bool DESC, bool FMA, int NCP>
+template <bool DESC, bool FMA, int NCP, bool LASTAX>
 int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     constexpr int TFN = 32 * NCP;
     const i64 ncols = p->outer * p->inner;
@@ -256,12 +308,12 @@ int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev&
     do {                                                                                        \
         static bool attr_done = false;                                                          \
         if (!attr_done) {                                                                       \
-            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU, NCP>,              \
+            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX>,              \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                             (int)smem));                                        \
             attr_done = true;                                                                   \
         }                                                                                       \
-        dense_fast_kernel<DESC, FMA, FU, NCP><<<grid, 256, smem, st>>>(                         \
+        dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX><<<grid, 256, smem, st>>>(                         \
             in, out, p->d_Mt, (int)p->n, p->inner, p->axis, F);                                 \
     } while (0)
     if (F.any) NG_DENSE_FAST(true); else NG_DENSE_FAST(false);
@@ -275,15 +327,21 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
     const i64 big_tiles = (p->outer * p->inner / FN) * (p->n / FM);
     const char* e = getenv("NG_DENSE_NCP");
     const int force = e ? atoi(e) : 0;
+    if (p->inner == 1) {                       // contiguous contraction axis
+        const bool wide_l = force ? force == 4 : (big_tiles >= 4 * 148 && p->outer % FN == 0);
+        if (wide_l && p->outer % FN == 0) return launch_fast2<DESC, FMA, 4, true>(p, in, out, F, st);
+        return launch_fast2<DESC, FMA, 1, true>(p, in, out, F, st);
+    }
     const bool wide = force ? force == 4 : (big_tiles >= 4 * 148 && p->inner % FN == 0);
-    if (wide && p->inner % FN == 0) return launch_fast2<DESC, FMA, 4>(p, in, out, F, st);
-    return launch_fast2<DESC, FMA, 1>(p, in, out, F, st);
+    if (wide && p->inner % FN == 0) return launch_fast2<DESC, FMA, 4, false>(p, in, out, F, st);
+    return launch_fast2<DESC, FMA, 1, false>(p, in, out, F, st);
 }
 
 bool fast_ok(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
-    if (p->inner == 1 || p->n % FM != 0 || p->inner % 32 != 0) return false;
+    if (p->n % FM != 0) return false;
+    if (p->inner == 1 ? (p->outer % 32 != 0) : (p->inner % 32 != 0)) return false;
     if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
-    if (F.any && F.shape[F.vec_axis] % 2 != 0) return false;
+    if (F.any && p->inner != 1 && F.shape[F.vec_axis] % 2 != 0) return false;
     const char* e = getenv("NG_DENSE_FAST");
     return !(e && atoi(e) == 0);
 }
