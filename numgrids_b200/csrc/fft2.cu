@@ -347,6 +347,175 @@ fft2pass_pf_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Ring variant (n = 512, 1024) -- the production kernel of cfg3.  Differences from the persistent
+// kernel above, all aimed at the two things ncu showed (profiles/r01_fft_cfg3_ncu_summary.txt):
+// half of the twiddle / multiplier loads missed the ~28 KB of L1 left beside 197 KB of shared
+// memory (long-scoreboard stalls), and 6 warps leave two of the four schedulers with one warp.
+//   * both tables live in shared memory (twiddles transposed to [kr][t]: conflict-free);
+//   * the exchange buffer is XOR-swizzled instead of padded (exactly 16 B per complex sample);
+//   * NW = 8 warps (two per scheduler) share NSTAGE = 4 raw-input stages: the warp that has just
+//     pulled unit j out of a stage refills it with unit j + NSTAGE, which its partner warp
+//     (same scheduler, half a transform out of phase) consumes; one 16 KB cp.async.bulk per unit,
+//     completing on the CONSUMER's own mbarrier so that a fast warp can never observe a stale phase.
+// Shared memory: 2 tables + NW exchange buffers + NSTAGE stages = (2 + 8 + 4) * 16 KB = 224 KB.
+// -------------------------------------------------------------------------------------------------
+template <int RT, int R2, bool FUSED, int NW, int NSTAGE>
+__global__ void __launch_bounds__(32 * NW, 1)
+fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
+                     const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, FuseDev F) {
+    constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
+    constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
+    constexpr int PPU = 2 * TPW;                 // pencils per warp unit
+    constexpr int UNIT = PPU * N;                // doubles per unit (16 KB)
+    constexpr int ROWB = R2 * 16;                // bytes per exchange row
+    static_assert(NW % NSTAGE == 0, "a stage is refilled by the warp that drained it");
+    extern __shared__ __align__(1024) unsigned char rsm[];
+    double2* TWS = reinterpret_cast<double2*>(rsm);                     // [RT][T]  exp(-2 pi i kr t / n)
+    double2* WNS = TWS + N;                                             // [N]      (ik)^order / n
+    unsigned char* Sall = reinterpret_cast<unsigned char*>(WNS + N);    // [NW*TPW][N] double2, swizzled
+    double* rawall = reinterpret_cast<double*>(Sall + (size_t)NW * TPW * N * 16);   // [NSTAGE][UNIT]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rawall + (size_t)NSTAGE * UNIT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tr = lane / T, t = lane - tr * T;
+    unsigned char* Sb = Sall + (size_t)(warp * TPW + tr) * N * 16;
+    const unsigned t16 = (unsigned)t << 4;
+
+    for (int e = threadIdx.x; e < N; e += 32 * NW) {
+        TWS[e] = tw[(e / T) * (e % T)];
+        WNS[e] = Wn[e];
+    }
+    if (threadIdx.x < NW) pf_mbar_init(bars + threadIdx.x, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const i64 nunits = (npencil + PPU - 1) / PPU;
+    const i64 njl = (nunits - (i64)blockIdx.x + gridDim.x - 1) / gridDim.x;   // units of this CTA
+    auto issue = [&](i64 jl) {                   // one lane: unit jl of this CTA -> stage jl % NSTAGE
+        const i64 p0 = (jl * gridDim.x + blockIdx.x) * PPU;
+        const i64 left = npencil - p0;
+        const unsigned bytes = (unsigned)((left < PPU ? left : PPU) * N * 8);
+        unsigned long long* bar = bars + (int)(jl % NW);
+        pf_mbar_expect_tx(bar, bytes);
+        pf_bulk_g2s(rawall + (size_t)(jl % NSTAGE) * UNIT, in + p0 * N, bytes, bar);
+    };
+    if (warp < NSTAGE && lane == 0 && warp < njl) issue(warp);
+    const double* raw = rawall + (size_t)(warp % NSTAGE) * UNIT + (size_t)(2 * tr) * N;
+    unsigned long long* mybar = bars + warp;
+    unsigned phase = 0;
+    for (i64 jl = warp; jl < njl; jl += NW) {
+        const i64 pa = (jl * gridDim.x + blockIdx.x) * PPU + 2 * tr, pb = pa + 1;
+        const bool va = pa < npencil, vb = pb < npencil;
+        Idx4 ia, ib;
+        if (FUSED) {
+            ia = unravel4(va ? pa * N : 0, F.shape);
+            ib = unravel4(vb ? pb * N : 0, F.shape);
+        }
+        pf_mbar_wait(mybar, phase);
+        phase ^= 1;
+        double2 x[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int idx = r * R2 + t;
+            double a = va ? raw[idx] : 0.0, b = vb ? raw[N + idx] : 0.0;
+            if (FUSED && F.pre.ptr) {
+                ia.i[F.vec_axis] = idx;
+                ib.i[F.vec_axis] = idx;
+                if (va) a = __dmul_rn(F.pre.ptr[coef_off(F.pre, ia)], a);
+                if (vb) b = __dmul_rn(F.pre.ptr[coef_off(F.pre, ib)], b);
+            }
+            x[r] = make_double2(a, b);
+        }
+        __syncwarp();                              // the stage is drained
+        if (lane == 0 && jl + NSTAGE < njl) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(jl + NSTAGE);                    // refill it for the partner warp
+        }
+        dif_forward<RT>(x);
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const int kr = bitrev(q, LRT);
+            double2 v = x[q];
+            if (kr != 0) {
+                const double2 w = TWS[kr * T + t];
+                v = cmul(v, w.x, w.y);
+            }
+            *reinterpret_cast<double2*>(Sb + (t16 ^ ((kr & (R2 - 1)) << 4)) + kr * ROWB) = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int kr = t + T * g;
+            unsigned char* row = Sb + (size_t)kr * ROWB;
+            double2* y = x + g * R2;
+#pragma unroll
+            for (int j = 0; j < R2; ++j) y[j] = *reinterpret_cast<const double2*>(row + (t16 ^ (j << 4)));
+            dif_forward<R2>(y);
+#pragma unroll
+            for (int q = 0; q < R2; ++q) {
+                const int k2 = bitrev(q, LR2);
+                const double2 w = WNS[kr + RT * k2];
+                y[q] = cmul(y[q], w.x, w.y);
+            }
+            dit_inverse<R2>(y);
+#pragma unroll
+            for (int j = 0; j < R2; ++j) *reinterpret_cast<double2*>(row + (t16 ^ (j << 4))) = y[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const int kr = bitrev(q, LRT);
+            double2 v = *reinterpret_cast<const double2*>(Sb + (t16 ^ ((kr & (R2 - 1)) << 4)) + kr * ROWB);
+            if (kr != 0) {
+                const double2 w = TWS[kr * T + t];
+                v = cmul(v, w.x, -w.y);
+            }
+            x[q] = v;
+        }
+        dit_inverse<RT>(x);
+        __syncwarp();                              // the exchange buffer is rewritten by the next unit
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int idx = r * R2 + t;
+            double a = x[r].x, b = x[r].y;
+            if (FUSED) {
+                ia.i[F.vec_axis] = idx;
+                ib.i[F.vec_axis] = idx;
+                if (va) a = fuse_tail(F, a, pa * N + idx, ia);
+                if (vb) b = fuse_tail(F, b, pb * N + idx, ib);
+            }
+            if (va) out[pa * N + idx] = a;
+            if (vb) out[pb * N + idx] = b;
+        }
+    }
+}
+
+template <int RT, int R2, int NW, int NSTAGE>
+int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    constexpr int T = R2, TPW = 32 / T, N = RT * R2, PPU = 2 * TPW;
+    const i64 npencil = p->outer;
+    const i64 nunits = (npencil + PPU - 1) / PPU;
+    i64 g = (nunits + NW - 1) / NW;
+    if (g > 148) g = 148;                                // persistent: one CTA per SM
+    const size_t smem = (size_t)2 * N * 16 + (size_t)NW * TPW * N * 16 + (size_t)NSTAGE * PPU * N * 8 + NW * 8;
+#define NG_FFT2_RING(FU)                                                                          \
+    do {                                                                                          \
+        static bool attr_done = false;                                                            \
+        if (!attr_done) {                                                                         \
+            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>,         \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                            (int)smem));                                          \
+            attr_done = true;                                                                     \
+        }                                                                                         \
+        fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE><<<(unsigned)g, 32 * NW, smem, st>>>(         \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
+    } while (0)
+    if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false);
+#undef NG_FFT2_RING
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
 template <int RT, int R2>
 int launch_pf(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     constexpr int T = R2, TPW = 32 / T, N = RT * R2, NSLOT = PF_WARPS * TPW;
@@ -414,9 +583,21 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
     (void)minb;
     const char* pfe = getenv("NG_FFT_PREFETCH");
     const bool pf = !(pfe && atoi(pfe) == 0) && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * PF_WARPS;
+    const char* ve = getenv("NG_FFT_VARIANT");         // tuning: 0 = persistent, 1 = ring 6/6, 2 = ring 8/4
+    const int variant = ve ? atoi(ve) : 2;
     switch (p->n) {
-        case 1024: rc = pf ? launch_pf<32, 32>(p, in, out, F, st) : launch<32, 32, 1>(p, in, out, F, st); break;
-        case 512: rc = pf ? launch_pf<32, 16>(p, in, out, F, st) : launch<32, 16, 1>(p, in, out, F, st); break;
+        case 1024:
+            rc = !pf ? launch<32, 32, 1>(p, in, out, F, st)
+                 : variant == 2 ? launch_ring<32, 32, 8, 4>(p, in, out, F, st)
+                 : variant == 1 ? launch_ring<32, 32, 6, 6>(p, in, out, F, st)
+                                : launch_pf<32, 32>(p, in, out, F, st);
+            break;
+        case 512:
+            rc = !pf ? launch<32, 16, 1>(p, in, out, F, st)
+                 : variant == 2 ? launch_ring<32, 16, 8, 4>(p, in, out, F, st)
+                 : variant == 1 ? launch_ring<32, 16, 6, 6>(p, in, out, F, st)
+                                : launch_pf<32, 16>(p, in, out, F, st);
+            break;
         case 256: rc = launch<16, 16, 1>(p, in, out, F, st); break;
         case 128: rc = launch<16, 8, 1>(p, in, out, F, st); break;
         case 64: rc = launch<8, 8, 1>(p, in, out, F, st); break;

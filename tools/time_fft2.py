@@ -1,4 +1,4 @@
-"""Compare the FFT kernel variants (prefetch on/off) and check them against each other."""
+"""Compare the FFT kernel variants (plain / persistent / ring 6-6 / ring 8-4) and check them against each other."""
 import os
 import sys
 
@@ -16,8 +16,9 @@ f = torch.randn(b0, b1, n, dtype=torch.float64, device="cuda")
 o = torch.empty_like(f)
 op = ng.Diff(g, 1, 2).operator.operator
 ref = None
-for pf in ("0", "1"):
+for pf, var in (("0", "0"), ("1", "0"), ("1", "1"), ("1", "2")):
     os.environ["NG_FFT_PREFETCH"] = pf
+    os.environ["NG_FFT_VARIANT"] = var
     for _ in range(3):
         op.apply_ptr(f.data_ptr(), o.data_ptr())
     torch.cuda.synchronize()
@@ -33,4 +34,4 @@ for pf in ("0", "1"):
         ref = o.clone()
     same = float((o - ref).abs().max() / ref.abs().max())
     ms = float(np.median(ts))
-    print(f"n={n} batch={b0}x{b1} prefetch={pf}: {ms:.4f} ms  {f.numel() / ms / 1e6:.1f} Gpts/s  {16 * f.numel() / ms / 1e6:.0f} GB/s  maxdiff {same:.1e}")
+    print(f"n={n} batch={b0}x{b1} prefetch={pf} variant={var}: {ms:.4f} ms  {f.numel() / ms / 1e6:.1f} Gpts/s  {16 * f.numel() / ms / 1e6:.0f} GB/s  maxdiff {same:.1e}")
