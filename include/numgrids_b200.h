@@ -122,6 +122,33 @@ int ng_fd_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
 int ng_fd_pack_halo(const ng_plan* plan, const double* d_in, double* d_lo_planes,
                     double* d_hi_planes, void* stream);
 int ng_plan_halo_width(const ng_plan* plan);
+/* The same with the elementwise work of ng_fuse (slab form of the curvilinear composites,
+ * numgrids/curvilinear.py:169-317, when the sharded axis is a finite-difference axis).  The
+ * halo planes must already hold `pre * value` (ng_fd_pack_halo_fused on the sending rank, whose
+ * coefficient at a shared point is the same number); all other fuse operands are local. */
+int ng_apply_fused_slab(const ng_plan* plan, const double* d_in, double* d_out, const ng_fuse* fuse,
+                        const double* d_lo_halo, const double* d_hi_halo, void* stream);
+int ng_fd_pack_halo_fused(const ng_plan* plan, const double* d_in, const ng_coef* pre,
+                          double* d_lo_planes, double* d_hi_planes, void* stream);
+
+/* ---- slab <-> pencil redistribution (multi-GPU; no counterpart in the single-process reference)
+ * A Chebyshev / FFT derivative along the sharded last axis needs whole pencils: a rank's slab
+ * [A][B][zl] is redistributed to [A_r][B][Z], the plan applied there, and the result sent back.
+ * Each direction is one launch over <= 16 strided 2-D blocks (rows = contiguous z segments);
+ * src or dst of a block may be peer-GPU memory (NVLink P2P), so copy and exchange are one kernel.
+ * fuse_side 0: plain copy; 1: values are multiplied by fuse->pre as they are read from the local
+ * slab; 2: the tail of ng_fuse (minuend .. finite) is applied as values are written into the local
+ * slab.  local_offset is the linear index, in the rank's own slab array of shape local_shape, of
+ * the block's first element on its LOCAL side (src for side 1, dst for side 2). */
+typedef struct ng_copy_block {
+    const double* src;
+    double* dst;
+    int64_t rows, row_len;
+    int64_t src_stride, dst_stride;   /* in elements */
+    int64_t local_offset;
+} ng_copy_block;
+int ng_slab_block_copy(int nblocks, const ng_copy_block* blocks, int ndim, const int64_t* local_shape,
+                       const ng_fuse* fuse, int fuse_side, void* stream);
 
 /* ---- fused Cartesian Laplacian ----------------------------------------------------------------
  * The reference idiom Diff(g,2,0)(f) + Diff(g,2,1)(f) + ... on equidistant axes (reference

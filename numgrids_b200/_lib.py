@@ -31,6 +31,11 @@ class NgFuse(C.Structure):
                 ("add_zero", C.c_int32), ("divisor", NgCoef), ("finite", C.c_int32)]
 
 
+class NgCopyBlock(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("row_len", C.c_int64),
+                ("src_stride", C.c_int64), ("dst_stride", C.c_int64), ("local_offset", C.c_int64)]
+
+
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
 _D = C.POINTER(C.c_double)
@@ -53,6 +58,9 @@ SIGNATURES = {
     "ng_fd_apply_slab": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ng_fd_pack_halo": (C.c_int, [_P, _P, _P, _P, _P]),
     "ng_plan_halo_width": (C.c_int, [_P]),
+    "ng_apply_fused_slab": (C.c_int, [_P, _P, _P, C.POINTER(NgFuse), _P, _P, _P]),
+    "ng_fd_pack_halo_fused": (C.c_int, [_P, _P, C.POINTER(NgCoef), _P, _P, _P]),
+    "ng_slab_block_copy": (C.c_int, [C.c_int, C.POINTER(NgCopyBlock), C.c_int, _I64, C.POINTER(NgFuse), C.c_int, _P]),
     "ng_fdlap_plan_create": (C.c_int, [C.c_int, _I64, _PP, _PP]),
     "ng_fdlap_apply": (C.c_int, [_P, _P, _P, _P]),
     "ng_fdlap_apply_slab": (C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -400,6 +400,15 @@ int ng_fd_apply_slab(const ng_plan* plan, const double* d_in, double* d_out,
     return ng_fd_launch(plan, d_in, d_out, F, d_lo_halo, d_hi_halo, (cudaStream_t)stream);
 }
 
+int ng_apply_fused_slab(const ng_plan* plan, const double* d_in, double* d_out, const ng_fuse* fuse,
+                        const double* d_lo_halo, const double* d_hi_halo, void* stream) {
+    NG_REQUIRE(plan && plan->kind == PK_FD, "ng_apply_fused_slab: finite-difference plan required");
+    NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_apply_fused_slab: bad buffers");
+    FuseDev F;
+    ng_fuse_to_dev(plan, fuse, &F);
+    return ng_fd_launch(plan, d_in, d_out, F, d_lo_halo, d_hi_halo, (cudaStream_t)stream);
+}
+
 int ng_fdlap_plan_create(int ndim, const int64_t* shape, ng_plan* const* axis_plans,
                          ng_plan** out) {
     NG_REQUIRE(out != nullptr, "out is NULL");

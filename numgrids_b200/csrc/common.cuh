@@ -170,6 +170,12 @@ __device__ __forceinline__ i64 coef_off(const CoefDev& c, const Idx4& ix) {
     return ix.i[0] * c.s[0] + ix.i[1] * c.s[1] + ix.i[2] * c.s[2] + ix.i[3] * c.s[3];
 }
 
+// inf / nan test on the integer pipe (isfinite() would spend FP64-pipe slots in FP64-bound kernels)
+__device__ __forceinline__ bool ng_nonfinite(double v) {
+    return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000;
+}
+__device__ __forceinline__ double ng_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
 // The elementwise tail of ng_fuse (see numgrids_b200.h for the order); `lin` is the linear index
 // of the output element, `ix` its multi-index.
 __device__ __forceinline__ double fuse_tail(const FuseDev& F, double d, i64 lin, const Idx4& ix) {

@@ -94,7 +94,7 @@ fd_apply_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 double x = Vec<VEC>::get(v, j);
-                if (FUSED && F.pre.ptr) {
+                if (FUSED && F.pre.ptr && !(HALO && (ii < 0 || ii >= n))) {   // halo planes arrive pre-multiplied
                     // coefficient at the tap location; the last (contiguous) grid axis advances with j
                     i64 po = pre_base + ii * F.pre.s[axis];
                     if (VEC > 1) po += j * F.pre.s[F.vec_axis];   // c+j stays inside the innermost row
@@ -122,7 +122,7 @@ fd_apply_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
 // first / last nb planes along the axis -> [rows][nb]
 __global__ void fd_pack_halo_kernel(const double* __restrict__ in, double* __restrict__ lo_planes,
                                     double* __restrict__ hi_planes, i64 outer, i64 n, i64 inner,
-                                    int nb) {
+                                    int nb, FuseDev F) {
     const i64 rows = outer * inner;
     const i64 total = rows * nb;
     for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -130,8 +130,14 @@ __global__ void fd_pack_halo_kernel(const double* __restrict__ in, double* __res
         const i64 row = idx / nb;
         const int k = (int)(idx - row * nb);
         const i64 o = row / inner, c = row - o * inner;
-        if (lo_planes) lo_planes[idx] = in[(o * n + k) * inner + c];
-        if (hi_planes) hi_planes[idx] = in[(o * n + (n - nb + k)) * inner + c];
+        const i64 a = (o * n + k) * inner + c, b = (o * n + (n - nb + k)) * inner + c;
+        double va = in[a], vb = in[b];
+        if (F.pre.ptr) {                                  // ng_fd_pack_halo_fused: planes leave as pre * value
+            va = __dmul_rn(F.pre.ptr[coef_off(F.pre, unravel4(a, F.shape))], va);
+            vb = __dmul_rn(F.pre.ptr[coef_off(F.pre, unravel4(b, F.shape))], vb);
+        }
+        if (lo_planes) lo_planes[idx] = va;
+        if (hi_planes) hi_planes[idx] = vb;
     }
 }
 
@@ -182,6 +188,23 @@ int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev&
     return NG_OK;
 }
 
+extern "C" int ng_fd_pack_halo_fused(const ng_plan* p, const double* d_in, const ng_coef* pre,
+                                     double* d_lo_planes, double* d_hi_planes, void* stream) {
+    NG_REQUIRE(p && p->kind == PK_FD, "ng_fd_pack_halo_fused: FD plan required");
+    NG_REQUIRE(d_in, "ng_fd_pack_halo_fused: null input");
+    ng_fuse f;
+    memset(&f, 0, sizeof(f));
+    if (pre) f.pre = *pre;
+    FuseDev F;
+    ng_fuse_to_dev(p, &f, &F);
+    const i64 total = p->outer * p->inner * p->fd.nb;
+    if (total == 0) return NG_OK;
+    fd_pack_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_in, d_lo_planes, d_hi_planes, p->outer, p->n, p->inner, p->fd.nb, F);
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
 extern "C" int ng_fd_pack_halo(const ng_plan* p, const double* d_in, double* d_lo_planes,
                                double* d_hi_planes, void* stream) {
     NG_REQUIRE(p && (p->kind == PK_FD || p->kind == PK_FDLAP), "ng_fd_pack_halo: FD/FDLAP plan required");
@@ -198,8 +221,10 @@ extern "C" int ng_fd_pack_halo(const ng_plan* p, const double* d_in, double* d_l
         NG_LAUNCH_CHECK();
         return NG_OK;
     }
+    FuseDev F;
+    memset(&F, 0, sizeof(F));
     fd_pack_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        d_in, d_lo_planes, d_hi_planes, outer, n, inner, nb);
+        d_in, d_lo_planes, d_hi_planes, outer, n, inner, nb, F);
     NG_LAUNCH_CHECK();
     return NG_OK;
 }

@@ -29,6 +29,12 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
     extern __shared__ double smem[];
     double* sre = smem;                // [P][n]
     double* sim = smem + (i64)P * n;   // [P][n]
+    // A pencil with a non-finite sample (the reference's inf/nan rows on coordinate singularities,
+    // numgrids/curvilinear.py:236-244) must not leak into the pencil it shares a complex transform
+    // with: it is transformed as zeros and its whole output is NaN, as numpy.fft would make it.
+    int* sbad = reinterpret_cast<int*>(smem + (i64)2 * P * n);   // [2P]
+    for (int e = threadIdx.x; e < 2 * P; e += FFT_NT) sbad[e] = 0;
+    __syncthreads();
     const i64 npencil = outer * inner;
     const i64 q0 = (i64)blockIdx.x * 2 * P;   // first pencil of this CTA
     const int tid = threadIdx.x;
@@ -51,6 +57,7 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
                 v = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], v);
             }
         }
+        if (ng_nonfinite(v)) { sbad[pl] = 1; v = 0.0; }
         ((pl & 1) ? sim : sre)[(pl >> 1) * n + k] = v;
     }
     __syncthreads();
@@ -111,6 +118,7 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
         const i64 c = LAST ? 0 : q - o * inner;
         const i64 lin = (o * n + k) * inner + c;
         double d = ((pl & 1) ? sim : sre)[(pl >> 1) * n + k];
+        if (sbad[pl]) d = ng_nan();
         if (FUSED) {
             const Idx4 ix = unravel4(lin, F.shape);
             d = fuse_tail(F, d, lin, ix);
@@ -135,7 +143,7 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
     // pencil pairs per CTA: enough butterflies for 256 threads, bounded by shared memory
     int P = 1;
     while (P * n < 1024 && (i64)(2 * P) * 2 <= npencil) P *= 2;
-    const size_t smem = (size_t)P * n * 2 * sizeof(double);
+    const size_t smem = (size_t)P * n * 2 * sizeof(double) + (size_t)2 * P * sizeof(int);
     const i64 nblk = (npencil + 2 * P - 1) / (2 * P);
     const bool last = p->inner == 1;
 #define NG_FFT_GO(LA, FU)                                                                        \

@@ -94,6 +94,74 @@ __device__ __forceinline__ void dit_inverse(double2* x) {
     }
 }
 
+// Non-finite samples (the reference's inf/nan rows on coordinate singularities before its final
+// isfinite select, numgrids/curvilinear.py:236-244).  Two real pencils share one complex transform,
+// so one bad pencil would poison its partner.  inf/nan survive every +, -, * of the transform and
+// every output depends on every input of both pencils, so ONE test of a finished output per lane
+// detects a poisoned pair at no cost to the clean path; the pair is then redone one pencil at a
+// time by this warp-cooperative radix-2 routine (rare, slow): a pencil with a non-finite sample
+// comes out all-NaN (what numpy.fft makes of it), a clean one gets its derivative.
+template <bool FUSED>
+__device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, double* __restrict__ out, i64 p,
+                                             int N, int log2n, double2* S, const double2* __restrict__ Wn,
+                                             const double2* __restrict__ tw, const FuseDev& F) {
+    const int lane = threadIdx.x & 31;
+    Idx4 ix;
+    if (FUSED) ix = unravel4(p * N, F.shape);
+    bool bad = false;
+    for (int k = lane; k < N; k += 32) {
+        double v = in[p * N + k];
+        if (FUSED && F.pre.ptr) {
+            ix.i[F.vec_axis] = k;
+            v = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], v);
+        }
+        if (ng_nonfinite(v)) { bad = true; v = 0.0; }
+        S[k] = make_double2(v, 0.0);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (!bad) {
+        const int half = N >> 1;
+        for (int st = log2n - 1; st >= 0; --st) {            // forward DIF: natural in, bit-reversed out
+            const int m = 1 << st;
+            for (int e = lane; e < half; e += 32) {
+                const int j = e & (m - 1);
+                const int i0 = ((e >> st) << (st + 1)) + j, i1 = i0 + m;
+                const double2 w = tw[j << (log2n - 1 - st)];
+                const double2 u = S[i0], v = S[i1];
+                S[i0] = make_double2(u.x + v.x, u.y + v.y);
+                S[i1] = cmul(make_double2(u.x - v.x, u.y - v.y), w.x, w.y);
+            }
+            __syncwarp();
+        }
+        for (int k = lane; k < N; k += 32) {
+            const double2 w = Wn[__brev((unsigned)k) >> (32 - log2n)];
+            S[k] = cmul(S[k], w.x, w.y);
+        }
+        __syncwarp();
+        for (int st = 0; st < log2n; ++st) {                 // inverse DIT: bit-reversed in, natural out
+            const int m = 1 << st;
+            for (int e = lane; e < half; e += 32) {
+                const int j = e & (m - 1);
+                const int i0 = ((e >> st) << (st + 1)) + j, i1 = i0 + m;
+                const double2 w = tw[j << (log2n - 1 - st)];
+                const double2 u = S[i0], v = cmul(S[i1], w.x, -w.y);
+                S[i0] = make_double2(u.x + v.x, u.y + v.y);
+                S[i1] = make_double2(u.x - v.x, u.y - v.y);
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = lane; k < N; k += 32) {
+        double d = bad ? ng_nan() : S[k].x;
+        if (FUSED) {
+            ix.i[F.vec_axis] = k;
+            d = fuse_tail(F, d, p * N + k, ix);
+        }
+        out[p * N + k] = d;
+    }
+    __syncwarp();
+}
+
 // RT samples per lane in pass 1, R2 = n / RT = lanes per transform, G = RT / R2 sub-transforms per lane
 template <int RT, int R2, bool FUSED, int MINB>
 __global__ void __launch_bounds__(256, MINB)
@@ -176,6 +244,15 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         x[q] = v;
     }
     dit_inverse<RT>(x);
+    if (__any_sync(0xffffffffu, ng_nonfinite(x[0].x) || ng_nonfinite(x[0].y))) {   // poisoned pair: redo
+        __syncwarp();
+        const i64 p0 = ((i64)blockIdx.x * (blockDim.x >> 5) + warp) * TPW * 2;
+        for (int q = 0; q < 2 * TPW; ++q)
+            if (p0 + q < npencil)
+                fft_slow_pencil<FUSED>(in, out, p0 + q, N, LRT + LR2,
+                                       fsm + (size_t)(warp * TPW + (q >> 1)) * UNITS, Wn, tw, F);
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         const int idx = r * R2 + t;
@@ -191,15 +268,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
-// -------------------------------------------------------------------------------------------------
-// Persistent variant with asynchronous input staging (n >= 512, where 32 samples per lane leave only
-// 8 warps per SM and global-load latency was exposed): every transform slot owns a raw-input
-// buffer filled by cp.async.bulk (one 8 KB copy per pencil, completing on the slot's mbarrier).
-// As soon as a slot has pulled its samples into registers it issues the copy for its NEXT pair,
-// which lands under the three compute passes of the current one.
-// -------------------------------------------------------------------------------------------------
-constexpr int PF_WARPS = 6;
-
+// mbarrier / bulk-copy helpers of the ring kernel
 __device__ __forceinline__ unsigned pf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pf_mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pf_smem_u32(bar)), "r"(count) : "memory");
@@ -224,127 +293,6 @@ __device__ __forceinline__ void pf_bulk_g2s(void* dst, const void* src, unsigned
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(pf_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pf_smem_u32(bar)) : "memory");
-}
-
-template <int RT, int R2, bool FUSED>
-__global__ void __launch_bounds__(32 * PF_WARPS, 1)
-fft2pass_pf_kernel(const double* __restrict__ in, double* __restrict__ out,
-                   const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, FuseDev F) {
-    constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
-    constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
-    constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
-    constexpr int NSLOT = PF_WARPS * TPW;
-    extern __shared__ __align__(128) double2 psm[];
-    double2* Sall = psm;                                            // [NSLOT][UNITS]
-    double* rawall = reinterpret_cast<double*>(psm + (size_t)NSLOT * UNITS);   // [NSLOT][2][N]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rawall + (size_t)NSLOT * 2 * N);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tr = lane / T, t = lane - tr * T;
-    const int slot = warp * TPW + tr;
-    double2* S = Sall + (size_t)slot * UNITS;
-    double* raw = rawall + (size_t)slot * 2 * N;
-    unsigned long long* bar = bars + slot;
-    const i64 npairs = (npencil + 1) / 2;
-    const i64 stride = (i64)gridDim.x * NSLOT;
-
-    if (t == 0) pf_mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    auto issue = [&](i64 pair) {                 // called by lane t == 0 of the slot
-        const i64 pa = 2 * pair, pb = pa + 1;
-        const bool vb = pb < npencil;
-        pf_mbar_expect_tx(bar, (unsigned)(N * 8 * (vb ? 2 : 1)));
-        pf_bulk_g2s(raw, in + pa * N, N * 8, bar);
-        if (vb) pf_bulk_g2s(raw + N, in + pb * N, N * 8, bar);
-    };
-    i64 pair = (i64)blockIdx.x * NSLOT + slot;
-    if (t == 0 && pair < npairs) issue(pair);
-    unsigned phase = 0;
-    for (; pair < npairs; pair += stride) {
-        const i64 pa = 2 * pair, pb = pa + 1;
-        const bool vb = pb < npencil;
-        Idx4 ia, ib;
-        if (FUSED) {
-            ia = unravel4(pa * N, F.shape);
-            ib = unravel4(vb ? pb * N : 0, F.shape);
-        }
-        pf_mbar_wait(bar, phase);
-        phase ^= 1;
-        double2 x[RT];
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const int idx = r * R2 + t;
-            double a = raw[idx], b = vb ? raw[N + idx] : 0.0;
-            if (FUSED && F.pre.ptr) {
-                ia.i[F.vec_axis] = idx;
-                ib.i[F.vec_axis] = idx;
-                a = __dmul_rn(F.pre.ptr[coef_off(F.pre, ia)], a);
-                if (vb) b = __dmul_rn(F.pre.ptr[coef_off(F.pre, ib)], b);
-            }
-            x[r] = make_double2(a, b);
-        }
-        __syncwarp();                              // every lane of the slot has its samples in registers
-        if (t == 0 && pair + stride < npairs) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(pair + stride);                  // next pair streams in under the compute below
-        }
-        dif_forward<RT>(x);
-#pragma unroll
-        for (int q = 0; q < RT; ++q) {
-            const int kr = bitrev(q, LRT);
-            double2 v = x[q];
-            if (kr != 0) {
-                const double2 w = tw[kr * t];
-                v = cmul(v, w.x, w.y);
-            }
-            S[kr * PITCH + t] = v;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int kr = t + T * g;
-            double2* y = x + g * R2;
-#pragma unroll
-            for (int j = 0; j < R2; ++j) y[j] = S[kr * PITCH + j];
-            dif_forward<R2>(y);
-#pragma unroll
-            for (int q = 0; q < R2; ++q) {
-                const int k2 = bitrev(q, LR2);
-                const double2 w = Wn[kr + RT * k2];
-                y[q] = cmul(y[q], w.x, w.y);
-            }
-            dit_inverse<R2>(y);
-#pragma unroll
-            for (int j = 0; j < R2; ++j) S[kr * PITCH + j] = y[j];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < RT; ++q) {
-            const int kr = bitrev(q, LRT);
-            double2 v = S[kr * PITCH + t];
-            if (kr != 0) {
-                const double2 w = tw[kr * t];
-                v = cmul(v, w.x, -w.y);
-            }
-            x[q] = v;
-        }
-        dit_inverse<RT>(x);
-        __syncwarp();                              // S is rewritten by the next transform's pass 1
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const int idx = r * R2 + t;
-            double a = x[r].x, b = x[r].y;
-            if (FUSED) {
-                ia.i[F.vec_axis] = idx;
-                ib.i[F.vec_axis] = idx;
-                a = fuse_tail(F, a, pa * N + idx, ia);
-                if (vb) b = fuse_tail(F, b, pb * N + idx, ib);
-            }
-            out[pa * N + idx] = a;
-            if (vb) out[pb * N + idx] = b;
-        }
-    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -474,6 +422,15 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         }
         dit_inverse<RT>(x);
         __syncwarp();                              // the exchange buffer is rewritten by the next unit
+        if (__any_sync(0xffffffffu, ng_nonfinite(x[0].x) || ng_nonfinite(x[0].y))) {   // poisoned pair: redo
+            const i64 p0 = (jl * gridDim.x + blockIdx.x) * PPU;
+            for (int q = 0; q < PPU; ++q)
+                if (p0 + q < npencil)
+                    fft_slow_pencil<FUSED>(in, out, p0 + q, N, LRT + LR2,
+                                           reinterpret_cast<double2*>(Sall + (size_t)(warp * TPW + (q >> 1)) * N * 16),
+                                           Wn, tw, F);
+            continue;
+        }
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
@@ -496,48 +453,25 @@ int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& 
     const i64 npencil = p->outer;
     const i64 nunits = (npencil + PPU - 1) / PPU;
     i64 g = (nunits + NW - 1) / NW;
-    if (g > 148) g = 148;                                // persistent: one CTA per SM
     const size_t smem = (size_t)2 * N * 16 + (size_t)NW * TPW * N * 16 + (size_t)NSTAGE * PPU * N * 8 + NW * 8;
 #define NG_FFT2_RING(FU)                                                                          \
     do {                                                                                          \
-        static bool attr_done = false;                                                            \
-        if (!attr_done) {                                                                         \
+        static int per_sm = 0;                           /* persistent: resident CTAs per SM */   \
+        if (!per_sm) {                                                                            \
             NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>,         \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                             (int)smem));                                          \
-            attr_done = true;                                                                     \
+            int occ = 0;                                                                          \
+            NG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                             \
+                &occ, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>, 32 * NW, smem));              \
+            per_sm = occ > 0 ? occ : 1;                                                           \
         }                                                                                         \
+        if (g > (i64)148 * per_sm) g = (i64)148 * per_sm;                                         \
         fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE><<<(unsigned)g, 32 * NW, smem, st>>>(         \
             in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
     } while (0)
     if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false);
 #undef NG_FFT2_RING
-    NG_LAUNCH_CHECK();
-    return NG_OK;
-}
-
-template <int RT, int R2>
-int launch_pf(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
-    constexpr int T = R2, TPW = 32 / T, N = RT * R2, NSLOT = PF_WARPS * TPW;
-    const i64 npencil = p->outer;
-    const i64 pairs = (npencil + 1) / 2;
-    i64 g = (pairs + NSLOT - 1) / NSLOT;
-    if (g > 148) g = 148;                                // persistent: one CTA per SM
-    const size_t smem = (size_t)NSLOT * (RT * (R2 + 1) * sizeof(double2) + 2 * N * sizeof(double) + 8) + 128;
-#define NG_FFT2_PF(FU)                                                                            \
-    do {                                                                                          \
-        static bool attr_done = false;                                                            \
-        if (!attr_done) {                                                                         \
-            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_pf_kernel<RT, R2, FU>,                       \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                            (int)smem));                                          \
-            attr_done = true;                                                                     \
-        }                                                                                         \
-        fft2pass_pf_kernel<RT, R2, FU><<<(unsigned)g, 32 * PF_WARPS, smem, st>>>(                 \
-            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
-    } while (0)
-    if (F.any) NG_FFT2_PF(true); else NG_FFT2_PF(false);
-#undef NG_FFT2_PF
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -578,28 +512,32 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
     const char* e = getenv("NG_FFT_TWOPASS");
     if (e && atoi(e) == 0) return NG_OK;
     int rc = NG_OK;
-    const char* mb = getenv("NG_FFT_MINB");
-    const int minb = mb ? atoi(mb) : 0;                 // tuning override: CTAs per SM (register cap)
-    (void)minb;
-    const char* pfe = getenv("NG_FFT_PREFETCH");
-    const bool pf = !(pfe && atoi(pfe) == 0) && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * PF_WARPS;
-    const char* ve = getenv("NG_FFT_VARIANT");         // tuning: 0 = persistent, 1 = ring 6/6, 2 = ring 8/4
-    const int variant = ve ? atoi(ve) : 2;
+    const char* pfe = getenv("NG_FFT_PREFETCH");        // tuning: 0 = one-shot kernel, no input staging
+    // the persistent ring kernel needs enough pencils to fill 148 CTAs and a 16-byte aligned input
+    const bool ring = !(pfe && atoi(pfe) == 0) && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * 6;
+    const char* ve = getenv("NG_FFT_VARIANT");          // tuning: warps / input stages per CTA
+    const int variant = ve ? atoi(ve) : (p->n >= 512 ? 2 : 3);   // measured: profiles/r01_tune_fft.txt
     switch (p->n) {
         case 1024:
-            rc = !pf ? launch<32, 32, 1>(p, in, out, F, st)
-                 : variant == 2 ? launch_ring<32, 32, 8, 4>(p, in, out, F, st)
+            rc = !ring ? launch<32, 32, 1>(p, in, out, F, st)
                  : variant == 1 ? launch_ring<32, 32, 6, 6>(p, in, out, F, st)
-                                : launch_pf<32, 32>(p, in, out, F, st);
+                                : launch_ring<32, 32, 8, 4>(p, in, out, F, st);
             break;
         case 512:
-            rc = !pf ? launch<32, 16, 1>(p, in, out, F, st)
-                 : variant == 2 ? launch_ring<32, 16, 8, 4>(p, in, out, F, st)
+            rc = !ring ? launch<32, 16, 1>(p, in, out, F, st)
                  : variant == 1 ? launch_ring<32, 16, 6, 6>(p, in, out, F, st)
-                                : launch_pf<32, 16>(p, in, out, F, st);
+                                : launch_ring<32, 16, 8, 4>(p, in, out, F, st);
             break;
-        case 256: rc = launch<16, 16, 1>(p, in, out, F, st); break;
-        case 128: rc = launch<16, 8, 1>(p, in, out, F, st); break;
+        case 256:
+            rc = !ring ? launch<16, 16, 1>(p, in, out, F, st)
+                 : variant == 3 ? launch_ring<16, 16, 16, 8>(p, in, out, F, st)
+                                : launch_ring<16, 16, 8, 4>(p, in, out, F, st);
+            break;
+        case 128:
+            rc = !ring ? launch<16, 8, 1>(p, in, out, F, st)
+                 : variant == 3 ? launch_ring<16, 8, 16, 8>(p, in, out, F, st)
+                                : launch_ring<16, 8, 8, 4>(p, in, out, F, st);
+            break;
         case 64: rc = launch<8, 8, 1>(p, in, out, F, st); break;
         default: return NG_OK;
     }

@@ -110,16 +110,19 @@ class _StencilMixin:
         self._x_div = x_div
         self.operator = DeviceOperator(self.grid.shape, self._make_plan)
 
-    def _make_plan(self) -> _lib.Plan:
+    def _make_plan(self, shape=None, x_div=None) -> _lib.Plan:
+        """Plan for the grid's shape, or (slab layer) for an explicit local `shape` whose extent
+        along this axis may be a slab of the axis -- the tables stay those of the global axis."""
         lib = _lib.load()
         oc, wc = self._schemes["center"]
         of, wf = self._schemes["forward"]
         ob, wb = self._schemes["backward"]
         keep = [_lib.as_f64(_tables.snap_unit_weights(w)) for w in (wc, wf, wb)]
         offs = [_lib.as_i32(o) for o in (oc, of, ob)]
-        shp, shp_p = _shape_arg(self.grid)
+        shp, shp_p = _shape_arg(self.grid) if shape is None else _lib.as_i64(list(shape))
         inv_h_pow = 1.0 / self._h ** self.order
-        xd = _lib.as_f64(self._x_div) if self._x_div is not None else (None, None)
+        x_div = self._x_div if x_div is None else x_div
+        xd = _lib.as_f64(x_div) if x_div is not None else (None, None)
         out = C.c_void_p()
         _lib.check(lib.ng_fd_plan_create(
             len(shp), shp_p, self.axis_index, len(oc), keep[0][1], offs[0][1], len(of),
@@ -197,9 +200,9 @@ class FFTDiff(GridDiff):
             self._dense = _tables.fft_dense_matrix(self._W_1d)
         return self._dense
 
-    def _make_plan(self) -> _lib.Plan:
+    def _make_plan(self, shape=None) -> _lib.Plan:
         lib = _lib.load()
-        shp, shp_p = _shape_arg(self.grid)
+        shp, shp_p = _shape_arg(self.grid) if shape is None else _lib.as_i64(list(shape))
         W = np.ascontiguousarray(self._W_1d, dtype=np.complex128).view(np.float64)
         Wk, W_p = _lib.as_f64(W)
         n = len(self.axis)
@@ -233,9 +236,9 @@ class ChebyshevDiff(GridDiff):
         self._sparse = None
         self.operator = DeviceOperator(grid.shape, self._make_plan)
 
-    def _make_plan(self) -> _lib.Plan:
+    def _make_plan(self, shape=None) -> _lib.Plan:
         lib = _lib.load()
-        shp, shp_p = _shape_arg(self.grid)
+        shp, shp_p = _shape_arg(self.grid) if shape is None else _lib.as_i64(list(shape))
         Mk, M_p = _lib.as_f64(self._M)
         out = C.c_void_p()
         _lib.check(lib.ng_cheb_plan_create(len(shp), shp_p, self.axis_index, M_p,

@@ -81,3 +81,44 @@ def test_random_curvilinear_match_oracle(gpu_ready, seed):
     c, cr = ((c,), (cr,)) if nd == 2 else (c, cr)
     for i, (a, b) in enumerate(zip(c, cr)):
         check(a, b, ("curl", i))
+
+
+@pytest.mark.parametrize("nphi,nz", [(16, 11), (64, 7), (256, 5), (512, 3), (12, 9)])
+def test_singular_rows_do_not_leak_through_paired_fft(gpu_ready, nphi, nz):
+    """Cylindrical grid including r = 0 with an ODD z extent: the FFT kernels transform two real
+    pencils as one complex one, and the rows at r = 0 are inf/nan before the final isfinite select
+    (reference numgrids/curvilinear.py:236-244).  A singular pencil must not poison its partner --
+    every kernel family (radix-2, two-pass, ring, dense fallback), phi as a middle and as the last axis."""
+    for order_axes in ("r_phi_z", "z_r_phi"):
+        r = ("chebyshev", 9, 0.0, 1.5)
+        phi = ("periodic", nphi, 0.0, 2 * np.pi)
+        z = ("equidistant", nz + 8, -1.0, 1.0)
+        specs = [r, phi, z] if order_axes == "r_phi_z" else [z, r, phi]
+        ir, iphi = (0, 1) if order_axes == "r_phi_z" else (1, 2)
+        ones = lambda c: np.ones_like(c[0])
+        fns = [ones, ones, ones]
+        fns[iphi] = lambda c: c[ir]                       # h_phi = r, zero on the axis
+        axes = build_axes(ng, specs)
+        g = ng.CurvilinearGrid(*axes, scale_factors=fns)
+        paxes = [pencil.make_axis(*s) for s in specs]
+        D = [pencil.make_diff(paxes, 1, i, 4) for i in range(3)]
+        mesh = np.meshgrid(*[a.coords for a in axes], indexing="ij")
+        h = tuple(fn(mesh) for fn in fns)
+        rng = np.random.default_rng(nphi + nz)
+        f = rng.standard_normal(g.shape)
+        v = [rng.standard_normal(g.shape) for _ in range(3)]
+        with np.errstate(all="ignore"):
+            refs = {"lap": pencil.laplacian(f, h, D), "div": pencil.divergence(v, h, D)}
+            for i, x in enumerate(pencil.gradient(f, h, D)):
+                refs["grad%d" % i] = x
+            for i, x in enumerate(pencil.curl(v, h, D)):
+                refs["curl%d" % i] = x
+        got = {"lap": g.laplacian(f), "div": g.divergence(*v)}
+        for i, x in enumerate(g.gradient(f)):
+            got["grad%d" % i] = x
+        for i, x in enumerate(g.curl(*v)):
+            got["curl%d" % i] = x
+        for k in refs:
+            assert np.all(np.isfinite(got[k])), (order_axes, k)
+            assert np.array_equal(got[k] == 0.0, refs[k] == 0.0) or rel_linf(got[k], refs[k]) <= 1e-10, (order_axes, k)
+            assert rel_linf(got[k], refs[k]) <= 1e-10, (order_axes, k, rel_linf(got[k], refs[k]))

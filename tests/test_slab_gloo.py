@@ -1,5 +1,6 @@
 """CPU, world_size 2 and 3 over gloo: the slab layer's host logic (partition, neighbour pattern,
-halo exchange) reproduces the single-process oracle slab by slab.
+halo exchange, slab <-> pencil redistribution with its all-to-all splits and block descriptors)
+reproduces the single-process oracle slab by slab.
 
 The CUDA pack/stencil kernels are replaced by torch slicing and the oracle stencil here (no GPU in
 this tier); the GPU tier checks the same decomposition with the real kernels
@@ -94,3 +95,93 @@ def test_partition_and_neighbours():
     assert s.local_shape == (64, 64, 16) and s.nb == 2 and s.rows == 4096
     with pytest.raises(ValueError):
         slab.SlabLaplacian((64, 64, 16), (0.1, 0.1, 0.1), rank=0, nranks=4)
+
+
+# ---------------------------------------------------------------------------------------------
+# slab <-> pencil redistribution (Chebyshev / FFT along the sharded axis)
+# ---------------------------------------------------------------------------------------------
+RSHAPE = (7, 5, 11)            # uneven in both partitioned axes for world = 2 and 3
+
+
+def _exec_blocks(blocks):
+    """CPU stand-in of ng_slab_block_copy (plain copy): run the descriptors with memmove."""
+    import ctypes as C
+    for b in blocks:
+        for r in range(b.rows):
+            C.memmove(b.dst + 8 * r * b.dst_stride, b.src + 8 * r * b.src_stride, 8 * b.row_len)
+
+
+def _rfield():
+    return np.arange(np.prod(RSHAPE), dtype=np.float64).reshape(RSHAPE) * 0.25 + 1.0
+
+
+def _redist_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        f = _rfield()
+        n = RSHAPE[-1]
+        M = pencil.chebyshev_matrix(n, 0.0, 1.0, 2, True)
+        ref = pencil.chebyshev_apply(f, 2, M, False)
+        rd = slab.Redistribution(RSHAPE, rank, world)
+        z0, z1 = rd.z[rank]
+        a0, a1 = rd.a[rank]
+        local = np.ascontiguousarray(f[..., z0:z1])
+        assert local.shape == rd.slab_shape
+        # forward all-to-all: slab-side chunks are contiguous row ranges of the slab itself
+        chunks = torch.empty(int(np.prod(rd.pencil_shape)), dtype=torch.float64)
+        dist.all_to_all_single(chunks, torch.from_numpy(local).reshape(-1), rd.pencil_splits(), rd.slab_splits())
+        pin = np.full(rd.pencil_shape, np.nan)
+        _exec_blocks(rd.unpack_blocks(chunks.data_ptr(), pin.ctypes.data))
+        ok_fwd = bool(np.array_equal(pin, f[a0:a1]))
+        pout = np.ascontiguousarray(pencil.chebyshev_apply(pin, 2, M, False))
+        _exec_blocks(rd.pack_blocks(pout.ctypes.data, chunks.data_ptr()))
+        out = torch.full((int(np.prod(rd.slab_shape)),), float("nan"), dtype=torch.float64)
+        dist.all_to_all_single(out, chunks, rd.slab_splits(), rd.pencil_splits())
+        ok_bwd = bool(np.array_equal(out.numpy().reshape(rd.slab_shape), ref[..., z0:z1]))
+        q.put((rank, ok_fwd and ok_bwd))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pencil_redistribution_matches_single_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_redist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=5) for _ in range(world))
+    assert got == {r: True for r in range(world)}
+
+
+def test_push_pull_descriptors_cover_everything_once():
+    """Peer-memory form (push into the peers' pencil buffers, pull out of their results), all ranks
+    emulated in one process with NumPy buffers."""
+    for world in (1, 2, 3, 4):
+        f = _rfield()
+        rds = [slab.Redistribution(RSHAPE, r, world) for r in range(world)]
+        slabs = [np.ascontiguousarray(f[..., rd.z[rd.rank][0]:rd.z[rd.rank][1]]) for rd in rds]
+        pens = [np.full(rd.pencil_elems_max, np.nan) for rd in rds]
+        for rd, s in zip(rds, slabs):
+            _exec_blocks(rd.push_blocks(s.ctypes.data, [p.ctypes.data for p in pens]))
+        for rd, p in zip(rds, pens):
+            a0, a1 = rd.a[rd.rank]
+            n = int(np.prod(rd.pencil_shape))
+            assert np.array_equal(p[:n].reshape(rd.pencil_shape), f[a0:a1])
+        outs = [np.full(rd.slab_shape, np.nan) for rd in rds]
+        for rd, o in zip(rds, outs):
+            _exec_blocks(rd.pull_blocks([p.ctypes.data for p in pens], o.ctypes.data))
+        for s, o in zip(slabs, outs):
+            assert np.array_equal(s, o)
+        offs = [b.local_offset for b in rds[0].push_blocks(0, [0] * world)]
+        assert offs == [a0 * rds[0].B * rds[0].zl for a0, _ in rds[0].a]
+    with pytest.raises(ValueError):
+        slab.Redistribution((2, 5, 11), 0, 3)
+    with pytest.raises(ValueError):
+        slab.Redistribution((11,), 0, 2)

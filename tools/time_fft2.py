@@ -1,4 +1,4 @@
-"""Compare the FFT kernel variants (plain / persistent / ring 6-6 / ring 8-4) and check them against each other."""
+"""Compare the FFT kernel variants (one-shot / ring 6-6 / ring 8-4 / ring 16-8 where built) and check them against each other."""
 import os
 import sys
 
@@ -16,7 +16,7 @@ f = torch.randn(b0, b1, n, dtype=torch.float64, device="cuda")
 o = torch.empty_like(f)
 op = ng.Diff(g, 1, 2).operator.operator
 ref = None
-for pf, var in (("0", "0"), ("1", "0"), ("1", "1"), ("1", "2")):
+for pf, var in (("0", "0"), ("1", "1"), ("1", "2"), ("1", "3")):
     os.environ["NG_FFT_PREFETCH"] = pf
     os.environ["NG_FFT_VARIANT"] = var
     for _ in range(3):
