@@ -50,3 +50,37 @@ for _ in range(10):
 b.record()
 torch.cuda.synchronize()
 print(f"pack kernel: {a.elapsed_time(b) / 10:7.3f} ms")
+
+
+def run_parts(steps=10, warm=3):
+    def once():
+        lap.apply_part(f, out, 1, lo, hi)
+        lap.apply_part(f, out, 2, lo, hi)
+    for _ in range(warm):
+        once()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        once()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def run_one_part(part, steps=10, warm=3):
+    for _ in range(warm):
+        lap.apply_part(f, out, part, lo, hi)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        lap.apply_part(f, out, part, lo, hi)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+ms = run_parts()
+print(f"part 1 + part 2 (both halos): {ms:7.3f} ms  {16 * pts / ms / 1e6:8.1f} GB/s")
+print(f"part 1 alone: {run_one_part(1):7.3f} ms   part 2 alone: {run_one_part(2):7.3f} ms")
