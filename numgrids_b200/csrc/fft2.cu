@@ -162,6 +162,48 @@ __device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, doub
     __syncwarp();
 }
 
+// ng_fuse along a contiguous pencil: the coefficient offsets of sample 0 and the strides along the
+// pencil are found once per pencil (one unravel), and a coefficient that does not vary along the
+// pencil (spherical J/h^2 tables depend on (r, theta) only) is loaded once -- instead of an
+// unravel + 4-term offset per sample, which cost more instructions than the transform itself.
+struct PencilCoef {
+    const double* p;      // table + offset of sample 0 (nullptr = absent)
+    i64 s;                // element stride along the pencil
+    double c;             // the value when s == 0
+    __device__ __forceinline__ void init(const CoefDev& C, const Idx4& ix0, int vec_axis) {
+        p = C.ptr ? C.ptr + coef_off(C, ix0) : nullptr;
+        s = C.s[vec_axis];
+        c = (p && s == 0) ? *p : 0.0;
+    }
+    __device__ __forceinline__ double at(int idx) const { return s == 0 ? c : p[(i64)idx * s]; }
+};
+struct PencilTail {
+    PencilCoef post, div;
+    __device__ __forceinline__ void init(const FuseDev& F, i64 lin0) {
+        Idx4 ix = unravel4(lin0, F.shape);
+        ix.i[F.vec_axis] = 0;
+        post.init(F.post, ix, F.vec_axis);
+        div.init(F.div, ix, F.vec_axis);
+    }
+    // same steps and order as fuse_tail (common.cuh)
+    __device__ __forceinline__ double apply(const FuseDev& F, double d, i64 lin, int idx) const {
+        if (F.minuend) d = __dsub_rn(F.minuend[lin], d);
+        if (post.p) d = __dmul_rn(post.at(idx), d);
+        if (F.addend) d = __dadd_rn(F.addend[lin], d);
+        else if (F.add_zero) d = __dadd_rn(0.0, d);
+        if (div.p) d = __ddiv_rn(d, div.at(idx));
+        if (F.finite) d = ng_nonfinite(d) ? 0.0 : d;
+        return d;
+    }
+};
+__device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0) {
+    PencilCoef c;
+    Idx4 ix = unravel4(lin0, F.shape);
+    ix.i[F.vec_axis] = 0;
+    c.init(F.pre, ix, F.vec_axis);
+    return c;
+}
+
 // RT samples per lane in pass 1, R2 = n / RT = lanes per transform, G = RT / R2 sub-transforms per lane
 template <int RT, int R2, bool FUSED, int MINB>
 __global__ void __launch_bounds__(256, MINB)
@@ -180,26 +222,24 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
 
     // multi-index of sample 0 of each pencil (one unravel per pencil; the FFT axis is the innermost
     // non-unit axis, so sample idx only changes that coordinate)
-    Idx4 ia, ib;
-    if (FUSED) {
-        ia = unravel4(va ? pa * N : 0, F.shape);
-        ib = unravel4(vb ? pb * N : 0, F.shape);
-    }
     double2 x[RT];
     // ---- pass 1: strided samples r*R2 + t of both pencils
+    {
+        PencilCoef ca, cb;
+        const bool pre = FUSED && F.pre.ptr;
+        if (pre) { ca = pencil_pre(F, va ? pa * N : 0); cb = pencil_pre(F, vb ? pb * N : 0); }
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-        const int idx = r * R2 + t;
-        double a = 0.0, b = 0.0;
-        if (va) a = in[pa * N + idx];
-        if (vb) b = in[pb * N + idx];
-        if (FUSED && F.pre.ptr) {
-            ia.i[F.vec_axis] = idx;
-            ib.i[F.vec_axis] = idx;
-            if (va) a = __dmul_rn(F.pre.ptr[coef_off(F.pre, ia)], a);
-            if (vb) b = __dmul_rn(F.pre.ptr[coef_off(F.pre, ib)], b);
+        for (int r = 0; r < RT; ++r) {
+            const int idx = r * R2 + t;
+            double a = 0.0, b = 0.0;
+            if (va) a = in[pa * N + idx];
+            if (vb) b = in[pb * N + idx];
+            if (pre) {                               // (an absent pencil must stay exactly zero)
+                if (va) a = __dmul_rn(ca.at(idx), a);
+                if (vb) b = __dmul_rn(cb.at(idx), b);
+            }
+            x[r] = make_double2(a, b);
         }
-        x[r] = make_double2(a, b);
     }
     dif_forward<RT>(x);
 #pragma unroll
@@ -253,15 +293,15 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
                                        fsm + (size_t)(warp * TPW + (q >> 1)) * UNITS, Wn, tw, F);
         return;
     }
+    PencilTail ta, tb;
+    if (FUSED) { ta.init(F, va ? pa * N : 0); tb.init(F, vb ? pb * N : 0); }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         const int idx = r * R2 + t;
         double a = x[r].x, b = x[r].y;
         if (FUSED) {
-            ia.i[F.vec_axis] = idx;
-            ib.i[F.vec_axis] = idx;
-            if (va) a = fuse_tail(F, a, pa * N + idx, ia);
-            if (vb) b = fuse_tail(F, b, pb * N + idx, ib);
+            if (va) a = ta.apply(F, a, pa * N + idx, idx);
+            if (vb) b = tb.apply(F, b, pb * N + idx, idx);
         }
         if (va) out[pa * N + idx] = a;
         if (vb) out[pb * N + idx] = b;
@@ -354,11 +394,9 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
     for (i64 jl = warp; jl < njl; jl += NW) {
         const i64 pa = (jl * gridDim.x + blockIdx.x) * PPU + 2 * tr, pb = pa + 1;
         const bool va = pa < npencil, vb = pb < npencil;
-        Idx4 ia, ib;
-        if (FUSED) {
-            ia = unravel4(va ? pa * N : 0, F.shape);
-            ib = unravel4(vb ? pb * N : 0, F.shape);
-        }
+        PencilCoef ca, cb;
+        const bool pre = FUSED && F.pre.ptr;
+        if (pre) { ca = pencil_pre(F, va ? pa * N : 0); cb = pencil_pre(F, vb ? pb * N : 0); }
         pf_mbar_wait(mybar, phase);
         phase ^= 1;
         double2 x[RT];
@@ -366,11 +404,9 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
             double a = va ? raw[idx] : 0.0, b = vb ? raw[N + idx] : 0.0;
-            if (FUSED && F.pre.ptr) {
-                ia.i[F.vec_axis] = idx;
-                ib.i[F.vec_axis] = idx;
-                if (va) a = __dmul_rn(F.pre.ptr[coef_off(F.pre, ia)], a);
-                if (vb) b = __dmul_rn(F.pre.ptr[coef_off(F.pre, ib)], b);
+            if (pre) {                               // (an absent pencil must stay exactly zero)
+                if (va) a = __dmul_rn(ca.at(idx), a);
+                if (vb) b = __dmul_rn(cb.at(idx), b);
             }
             x[r] = make_double2(a, b);
         }
@@ -431,15 +467,15 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
                                            Wn, tw, F);
             continue;
         }
+        PencilTail ta, tb;
+        if (FUSED) { ta.init(F, va ? pa * N : 0); tb.init(F, vb ? pb * N : 0); }
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
             double a = x[r].x, b = x[r].y;
             if (FUSED) {
-                ia.i[F.vec_axis] = idx;
-                ib.i[F.vec_axis] = idx;
-                if (va) a = fuse_tail(F, a, pa * N + idx, ia);
-                if (vb) b = fuse_tail(F, b, pb * N + idx, ib);
+                if (va) a = ta.apply(F, a, pa * N + idx, idx);
+                if (vb) b = tb.apply(F, b, pb * N + idx, idx);
             }
             if (va) out[pa * N + idx] = a;
             if (vb) out[pb * N + idx] = b;
