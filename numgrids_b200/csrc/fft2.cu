@@ -162,45 +162,51 @@ __device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, doub
     __syncwarp();
 }
 
-// ng_fuse along a contiguous pencil: the coefficient offsets of sample 0 and the strides along the
-// pencil are found once per pencil (one unravel), and a coefficient that does not vary along the
-// pencil (spherical J/h^2 tables depend on (r, theta) only) is loaded once -- instead of an
-// unravel + 4-term offset per sample, which cost more instructions than the transform itself.
+// ng_fuse along a contiguous pencil, for a lane that owns samples idx = t + r*R2 (r compile-time):
+// the coefficient offsets of the pencil are found once (one unravel per pencil), every operand
+// becomes a per-lane base pointer plus r times a per-pencil step, and a coefficient that does
+// not vary along the pencil (spherical J/h^2 tables depend on (r, theta) only) is loaded once --
+// instead of an unravel + 4-term 64-bit offset per sample, which cost more instructions than the
+// transform itself.
 struct PencilCoef {
-    const double* p;      // table + offset of sample 0 (nullptr = absent)
-    i64 s;                // element stride along the pencil
-    double c;             // the value when s == 0
-    __device__ __forceinline__ void init(const CoefDev& C, const Idx4& ix0, int vec_axis) {
-        p = C.ptr ? C.ptr + coef_off(C, ix0) : nullptr;
-        s = C.s[vec_axis];
-        c = (p && s == 0) ? *p : 0.0;
+    const double* p;      // table entry of this lane's sample r = 0 (nullptr = absent)
+    i64 step;             // elements between this lane's consecutive samples (0: constant along the pencil)
+    double c;             // the value when step == 0
+    __device__ __forceinline__ void init(const CoefDev& C, const Idx4& ix0, int vec_axis, int t, int R2) {
+        const i64 s = C.s[vec_axis];
+        p = C.ptr ? C.ptr + coef_off(C, ix0) + t * s : nullptr;
+        step = s * R2;
+        c = (p && step == 0) ? *p : 0.0;
     }
-    __device__ __forceinline__ double at(int idx) const { return s == 0 ? c : p[(i64)idx * s]; }
+    __device__ __forceinline__ double at(int r) const { return step == 0 ? c : p[r * step]; }
 };
 struct PencilTail {
     PencilCoef post, div;
-    __device__ __forceinline__ void init(const FuseDev& F, i64 lin0) {
+    const double *minuend, *addend;
+    __device__ __forceinline__ void init(const FuseDev& F, i64 lin0, int t, int R2) {
         Idx4 ix = unravel4(lin0, F.shape);
         ix.i[F.vec_axis] = 0;
-        post.init(F.post, ix, F.vec_axis);
-        div.init(F.div, ix, F.vec_axis);
+        post.init(F.post, ix, F.vec_axis, t, R2);
+        div.init(F.div, ix, F.vec_axis, t, R2);
+        minuend = F.minuend ? F.minuend + lin0 + t : nullptr;
+        addend = F.addend ? F.addend + lin0 + t : nullptr;
     }
-    // same steps and order as fuse_tail (common.cuh)
-    __device__ __forceinline__ double apply(const FuseDev& F, double d, i64 lin, int idx) const {
-        if (F.minuend) d = __dsub_rn(F.minuend[lin], d);
-        if (post.p) d = __dmul_rn(post.at(idx), d);
-        if (F.addend) d = __dadd_rn(F.addend[lin], d);
+    // same steps and order as fuse_tail (common.cuh); sample r of this lane sits at offset r*R2
+    __device__ __forceinline__ double apply(const FuseDev& F, double d, int r, int R2) const {
+        if (minuend) d = __dsub_rn(minuend[r * R2], d);
+        if (post.p) d = __dmul_rn(post.at(r), d);
+        if (addend) d = __dadd_rn(addend[r * R2], d);
         else if (F.add_zero) d = __dadd_rn(0.0, d);
-        if (div.p) d = __ddiv_rn(d, div.at(idx));
+        if (div.p) d = __ddiv_rn(d, div.at(r));
         if (F.finite) d = ng_nonfinite(d) ? 0.0 : d;
         return d;
     }
 };
-__device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0) {
+__device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0, int t, int R2) {
     PencilCoef c;
     Idx4 ix = unravel4(lin0, F.shape);
     ix.i[F.vec_axis] = 0;
-    c.init(F.pre, ix, F.vec_axis);
+    c.init(F.pre, ix, F.vec_axis, t, R2);
     return c;
 }
 
@@ -208,7 +214,8 @@ __device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0) {
 template <int RT, int R2, bool FUSED, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
-                const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, FuseDev F) {
+                const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil,
+                     const __grid_constant__ FuseDev F) {   // (address taken for the rare slow path: no local copy)
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
     constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
     constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
@@ -227,7 +234,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     {
         PencilCoef ca, cb;
         const bool pre = FUSED && F.pre.ptr;
-        if (pre) { ca = pencil_pre(F, va ? pa * N : 0); cb = pencil_pre(F, vb ? pb * N : 0); }
+        if (pre) { ca = pencil_pre(F, va ? pa * N : 0, t, R2); cb = pencil_pre(F, vb ? pb * N : 0, t, R2); }
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
@@ -235,8 +242,8 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
             if (va) a = in[pa * N + idx];
             if (vb) b = in[pb * N + idx];
             if (pre) {                               // (an absent pencil must stay exactly zero)
-                if (va) a = __dmul_rn(ca.at(idx), a);
-                if (vb) b = __dmul_rn(cb.at(idx), b);
+                if (va) a = __dmul_rn(ca.at(r), a);
+                if (vb) b = __dmul_rn(cb.at(r), b);
             }
             x[r] = make_double2(a, b);
         }
@@ -294,14 +301,14 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         return;
     }
     PencilTail ta, tb;
-    if (FUSED) { ta.init(F, va ? pa * N : 0); tb.init(F, vb ? pb * N : 0); }
+    if (FUSED) { ta.init(F, va ? pa * N : 0, t, R2); tb.init(F, vb ? pb * N : 0, t, R2); }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         const int idx = r * R2 + t;
         double a = x[r].x, b = x[r].y;
         if (FUSED) {
-            if (va) a = ta.apply(F, a, pa * N + idx, idx);
-            if (vb) b = tb.apply(F, b, pb * N + idx, idx);
+            if (va) a = ta.apply(F, a, r, R2);
+            if (vb) b = tb.apply(F, b, r, R2);
         }
         if (va) out[pa * N + idx] = a;
         if (vb) out[pb * N + idx] = b;
@@ -351,7 +358,8 @@ __device__ __forceinline__ void pf_bulk_g2s(void* dst, const void* src, unsigned
 template <int RT, int R2, bool FUSED, int NW, int NSTAGE>
 __global__ void __launch_bounds__(32 * NW, 1)
 fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
-                     const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, FuseDev F) {
+                     const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil,
+                     const __grid_constant__ FuseDev F) {   // (address taken for the rare slow path: no local copy)
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
     constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
     constexpr int PPU = 2 * TPW;                 // pencils per warp unit
@@ -396,7 +404,7 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         const bool va = pa < npencil, vb = pb < npencil;
         PencilCoef ca, cb;
         const bool pre = FUSED && F.pre.ptr;
-        if (pre) { ca = pencil_pre(F, va ? pa * N : 0); cb = pencil_pre(F, vb ? pb * N : 0); }
+        if (pre) { ca = pencil_pre(F, va ? pa * N : 0, t, R2); cb = pencil_pre(F, vb ? pb * N : 0, t, R2); }
         pf_mbar_wait(mybar, phase);
         phase ^= 1;
         double2 x[RT];
@@ -405,8 +413,8 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             const int idx = r * R2 + t;
             double a = va ? raw[idx] : 0.0, b = vb ? raw[N + idx] : 0.0;
             if (pre) {                               // (an absent pencil must stay exactly zero)
-                if (va) a = __dmul_rn(ca.at(idx), a);
-                if (vb) b = __dmul_rn(cb.at(idx), b);
+                if (va) a = __dmul_rn(ca.at(r), a);
+                if (vb) b = __dmul_rn(cb.at(r), b);
             }
             x[r] = make_double2(a, b);
         }
@@ -468,17 +476,19 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             continue;
         }
         PencilTail ta, tb;
-        if (FUSED) { ta.init(F, va ? pa * N : 0); tb.init(F, vb ? pb * N : 0); }
+        if (FUSED) { ta.init(F, va ? pa * N : 0, t, R2); tb.init(F, vb ? pb * N : 0, t, R2); }
+        double* const oa = out + pa * N;
+        double* const ob = oa + N;
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
             double a = x[r].x, b = x[r].y;
             if (FUSED) {
-                if (va) a = ta.apply(F, a, pa * N + idx, idx);
-                if (vb) b = tb.apply(F, b, pb * N + idx, idx);
+                if (va) a = ta.apply(F, a, r, R2);
+                if (vb) b = tb.apply(F, b, r, R2);
             }
-            if (va) out[pa * N + idx] = a;
-            if (vb) out[pb * N + idx] = b;
+            if (va) oa[idx] = a;
+            if (vb) ob[idx] = b;
         }
     }
 }
