@@ -170,6 +170,18 @@ __device__ __forceinline__ i64 coef_off(const CoefDev& c, const Idx4& ix) {
     return ix.i[0] * c.s[0] + ix.i[1] * c.s[1] + ix.i[2] * c.s[2] + ix.i[3] * c.s[3];
 }
 
+// fuse_tail with the coefficient offsets already resolved (kernels that walk one axis resolve the
+// other coordinates once and step the offset); same steps and order as fuse_tail below.
+__device__ __forceinline__ double fuse_tail_off(const FuseDev& F, double d, i64 lin, i64 post_off, i64 div_off) {
+    if (F.minuend) d = __dsub_rn(F.minuend[lin], d);
+    if (F.post.ptr) d = __dmul_rn(F.post.ptr[post_off], d);
+    if (F.addend) d = __dadd_rn(F.addend[lin], d);
+    else if (F.add_zero) d = __dadd_rn(0.0, d);
+    if (F.div.ptr) d = __ddiv_rn(d, F.div.ptr[div_off]);
+    if (F.finite) d = isfinite(d) ? d : 0.0;
+    return d;
+}
+
 // inf / nan test on the integer pipe (isfinite() would spend FP64-pipe slots in FP64-bound kernels)
 __device__ __forceinline__ bool ng_nonfinite(double v) {
     return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000;

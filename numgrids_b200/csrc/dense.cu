@@ -255,19 +255,20 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
         for (int y = 0; y < 2 * NCP; ++y) {
             const i64 r = col0 + tx * 2 + (y & 1) + 32 * (y >> 1);
-            Idx4 ix0;
-            if (FUSED) ix0 = unravel4(r * (i64)n, F.shape);
+            i64 po = 0, dv = 0, pa = 0, da = 0;             // offsets of (pencil r, i = 0), strides along i
+            if (FUSED) {
+                const Idx4 ix0 = unravel4(r * (i64)n, F.shape);
+                if (F.post.ptr) { po = coef_off(F.post, ix0); pa = F.post.s[axis]; }
+                if (F.div.ptr) { dv = coef_off(F.div, ix0); da = F.div.s[axis]; }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = row0 + ty * 2 + 32 * j;
                 const i64 lin = r * (i64)n + i;
                 double2 v = make_double2(acc[2 * j][y], acc[2 * j + 1][y]);
                 if (FUSED) {
-                    Idx4 ix = ix0;
-                    ix.i[axis] = i;
-                    v.x = fuse_tail(F, v.x, lin, ix);
-                    ix.i[axis] = i + 1;
-                    v.y = fuse_tail(F, v.y, lin + 1, ix);
+                    v.x = fuse_tail_off(F, v.x, lin, po + i * pa, dv + i * da);
+                    v.y = fuse_tail_off(F, v.y, lin + 1, po + (i + 1) * pa, dv + (i + 1) * da);
                 }
                 *reinterpret_cast<double2*>(out + lin) = v;
             }
@@ -279,19 +280,20 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
     for (int jc = 0; jc < NCP; ++jc) {
         const i64 lin0 = (o * n) * inner + c0 + tx * 2 + 32 * jc;       // row 0 of this column pair
-        Idx4 ix0;
-        if (FUSED) ix0 = unravel4(lin0, F.shape);
+        i64 po = 0, dv = 0, pa = 0, da = 0, pv = 0, dvv = 0;   // offsets of row 0, strides along i / the pair
+        if (FUSED) {
+            const Idx4 ix0 = unravel4(lin0, F.shape);          // (row 0: the coordinate along `axis` is 0)
+            if (F.post.ptr) { po = coef_off(F.post, ix0); pa = F.post.s[axis]; pv = F.post.s[F.vec_axis]; }
+            if (F.div.ptr) { dv = coef_off(F.div, ix0); da = F.div.s[axis]; dvv = F.div.s[F.vec_axis]; }
+        }
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
             const int i = row0 + ty * 2 + (x & 1) + 32 * (x >> 1);
             const i64 lin = lin0 + (i64)i * inner;
             double2 v = make_double2(acc[x][2 * jc], acc[x][2 * jc + 1]);
             if (FUSED) {
-                Idx4 ix = ix0;
-                ix.i[axis] = i;
-                v.x = fuse_tail(F, v.x, lin, ix);
-                ix.i[F.vec_axis] += 1;                  // the pair stays inside the innermost row
-                v.y = fuse_tail(F, v.y, lin + 1, ix);
+                v.x = fuse_tail_off(F, v.x, lin, po + i * pa, dv + i * da);
+                v.y = fuse_tail_off(F, v.y, lin + 1, po + i * pa + pv, dv + i * da + dvv);   // the pair stays inside the innermost row
             }
             *reinterpret_cast<double2*>(out + lin) = v;
         }

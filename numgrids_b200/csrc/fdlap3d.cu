@@ -660,7 +660,7 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
                                               const Lap3U& W, const Lap3Side* side,
                                               const double* __restrict__ in, double* __restrict__ out,
                                               unsigned a_hlo, unsigned a_hhi,
-                                              unsigned a_cen, bool rowfix, bool ztile, int zfix,
+                                              unsigned a_cen, bool rowfix, int ztile, int zfix,
                                               const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
                                               const Rows<R>& D, const Rows<R>& E) {
     constexpr unsigned PB = RING_PITCH * 8;
@@ -672,6 +672,21 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
 #pragma unroll
     for (int r = 0; r < R; ++r) colv[r + 2] = C.v[r];
     const bool fix = rowfix || (x < 2) || (x >= nx - 2);        // warp-uniform
+    // Global z boundary (first / last z tile without a slab halo): the boundary lane needs 2R
+    // one-sided 6-tap sums (2 z points x R rows).  Each sum is sequential (reference order), but
+    // the 2R sums are independent: lanes 0..2R-1 each compute ONE of them from the ring and the
+    // boundary lane collects them by shuffle -- one sum's latency per step instead of 2R (the
+    // single-lane version cost +35 % FP64 issue on every boundary tile, i.e. on half of the
+    // tiles of a 256-wide slab).  ztile: 1 = first tile, 2 = last tile, 3 = both (nz == 64).
+    const int lane_ = threadIdx.x & 31;
+    double zsum = 0.0;
+    if (ztile == 1 || ztile == 2) {                             // warp-uniform
+        if (lane_ < 2 * R) {
+            const int rr = lane_ >> 1, cc_ = lane_ & 1;
+            const unsigned edge = ztile == 1 ? a_cen - 16u * lane_ : a_cen + 16u * (31 - lane_);   // the boundary lane's pair
+            zsum = onesided6_z_smem(ztile == 1 ? W.wfz : W.wbz, edge + rr * PB + cc_ * 8, ztile == 1 ? 8 : -8, W.ih[2]);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         if (y0 + r >= ny) break;                                // ragged last tile (warp-uniform)
@@ -699,7 +714,7 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
         }
         // global z boundary (first / last z tile without a slab halo): the owning lane replaces its
         // two z sums by the one-sided schemes, all 7 points come from the ring (warp-uniform test)
-        if (ztile) {
+        if (ztile == 3) {
             if (zfix == 1) {
                 dz.x = onesided6_z_smem(W.wfz, a_cen + r * PB, 8, W.ih[2]);
                 dz.y = onesided6_z_smem(W.wfz, a_cen + r * PB + 8, 8, W.ih[2]);
@@ -707,6 +722,9 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
                 dz.x = onesided6_z_smem(W.wbz, a_cen + r * PB, -8, W.ih[2]);
                 dz.y = onesided6_z_smem(W.wbz, a_cen + r * PB + 8, -8, W.ih[2]);
             }
+        } else if (ztile) {
+            const double v0 = __shfl_sync(0xffffffffu, zsum, 2 * r), v1 = __shfl_sync(0xffffffffu, zsum, 2 * r + 1);
+            if (zfix) { dz.x = v0; dz.y = v1; }
         }
         double2 o;
         if (fix) {
@@ -830,7 +848,7 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     const int z = z0 + 2 * lane;
     const bool zfix_lo = (z0 == 0) && (lo == nullptr), zfix_hi = (z0 + RING_TZ == nz) && (hi == nullptr);
     const bool rowfix = (y0 < 2) || (y0 + R > ny - 2);                            // warp-uniform, rare
-    const bool ztile = zfix_lo || zfix_hi;                                        // warp-uniform
+    const int ztile = (zfix_lo ? 1 : 0) | (zfix_hi ? 2 : 0);                      // warp-uniform
     const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
     // this lane's halo pair address in slot 0 (0 = not an edge lane of an edge tile)
     unsigned a_hlo = (lo_tile && lane == 0) ? smem_u32(hlo) + (unsigned)(j0 + 2) * 16u : 0u;
