@@ -339,10 +339,17 @@ def per_config_extras(torch, ng, peak_gbs, quick):
         v = (R.contiguous(), torch.sin(T).contiguous(), torch.cos(P).contiguous())
         pts = 128 * 128 * 256
         res = {}
+        # FP64-pipe-bound: a Chebyshev apply issues 2*128 DMUL/DADD per point, the n = 256
+        # FFT apply ~28 FP64 instructions per point; laplacian and curl = 4 Chebyshev + 2 FFT applies,
+        # gradient and divergence = 2 + 1
+        cheb, fft = 2.0 * 128, 28.0
+        work = {"laplacian": 4 * cheb + 2 * fft, "gradient": 2 * cheb + fft,
+                "divergence": 2 * cheb + fft, "curl": 4 * cheb + 2 * fft}
         for name, fn in (("laplacian", lambda: g.laplacian(f)), ("gradient", lambda: g.gradient(f)),
                          ("divergence", lambda: g.divergence(*v)), ("curl", lambda: g.curl(*v))):
             ms = timed(fn, 10, 3, True)
-            res[name] = {"gpts": pts / ms / 1e6, "ms": ms}
+            res[name] = {"gpts": pts / ms / 1e6, "ms": ms, "fp64_instr_per_point": work[name],
+                         "fp64_pipe_frac_at_1965MHz": work[name] * pts / ms / 1e9 / (148 * 64 * 1.965e-3)}
         out["cfg4_spherical_128x128x256"] = res
     except Exception as e:  # pragma: no cover
         out["cfg4_spherical"] = {"error": repr(e)}

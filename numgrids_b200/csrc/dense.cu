@@ -145,9 +145,13 @@ __global__ void __launch_bounds__(256, NCP == 4 ? 1 : 2)
 dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                   const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F) {
     constexpr int TFN = 32 * NCP, HALF = TFN / 2;
+    // LASTAX stages F by 8-byte copies with consecutive threads walking k: rows one pitch apart.  A
+    // pitch of TFN doubles puts all 16 k of a column in one bank (16-way conflict on every copy);
+    // two doubles of padding spread them over 8 banks and keep rows 16-byte aligned for the LDS.128.
+    constexpr int TFP = TFN + (LASTAX ? 2 : 0);
     extern __shared__ __align__(16) double dsm[];
     double (*Ms)[FK][FM] = reinterpret_cast<double (*)[FK][FM]>(dsm);                  // [2][FK][FM]
-    double (*Fs)[FK][TFN] = reinterpret_cast<double (*)[FK][TFN]>(dsm + 2 * FK * FM);  // [2][FK][TFN]
+    double (*Fs)[FK][TFP] = reinterpret_cast<double (*)[FK][TFP]>(dsm + 2 * FK * FM);  // [2][FK][TFP]
     const i64 col0 = (i64)blockIdx.x * TFN;         // flattened (o, c) column; tiles never straddle o
     const int row0 = blockIdx.y * FM;
     const i64 o = LASTAX ? 0 : col0 / inner, c0 = LASTAX ? 0 : col0 - o * inner;
@@ -305,7 +309,7 @@ int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev&
     constexpr int TFN = 32 * NCP;
     const i64 ncols = p->outer * p->inner;
     dim3 grid((unsigned)(ncols / TFN), (unsigned)(p->n / FM));
-    const size_t smem = (size_t)2 * FK * (FM + TFN) * sizeof(double);
+    const size_t smem = (size_t)2 * FK * (FM + TFN + (LASTAX ? 2 : 0)) * sizeof(double);
 #define NG_DENSE_FAST(FU)                                                                       \
     do {                                                                                        \
         static bool attr_done = false;                                                          \
