@@ -168,8 +168,24 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     const int npanel = n / FK;
     Idx4 pre_ix;                                   // multi-index of (row 0, this thread's chunk column)
     if (FUSED && F.pre.ptr && !LASTAX) pre_ix = unravel4((o * n) * inner + c0 + (tid % HALF) * 2, F.shape);
+    // prologue coefficients (`coeff * v[i]`) of the panel in flight, fetched with the panel so that
+    // their global-load latency hides under the previous panel's arithmetic
+    double pcn[2 * NCP];
+#pragma unroll
+    for (int q = 0; q < 2 * NCP; ++q) pcn[q] = 0.0;
     auto stage = [&](int p, int buf) {
         const int k0 = p * FK;
+        if (FUSED && !LASTAX && F.pre.ptr) {
+#pragma unroll
+            for (int q = 0; q < NCP; ++q) {
+                const int kk = (tid + q * 256) / HALF;
+                Idx4 ix = pre_ix;
+                ix.i[axis] = k0 + kk;
+                const i64 po = coef_off(F.pre, ix);
+                pcn[2 * q] = F.pre.ptr[po];
+                pcn[2 * q + 1] = F.pre.ptr[po + F.pre.s[F.vec_axis]];
+            }
+        }
         // M panel: 16 x 128 doubles = 1024 16-byte chunks (4 per thread); F panel: 16 x TFN (NCP per thread)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -198,6 +214,9 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     stage(DESC ? npanel - 1 : 0, 0);
     for (int pp = 0; pp < npanel; ++pp) {
         const int buf = pp & 1;
+        double pcc[2 * NCP];                        // this panel's prologue coefficients
+#pragma unroll
+        for (int q = 0; q < 2 * NCP; ++q) pcc[q] = pcn[q];
         if (pp + 1 < npanel) {
             stage(DESC ? npanel - 2 - pp : pp + 1, buf ^ 1);
             cp_async_wait<1>();
@@ -221,11 +240,8 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                 for (int q = 0; q < NCP; ++q) {
                     const int e = tid + q * 256;
                     const int kk = e / HALF, ch = (e % HALF) * 2;
-                    Idx4 ix = pre_ix;
-                    ix.i[axis] = k0 + kk;
-                    const i64 po = coef_off(F.pre, ix);
-                    Fs[buf][kk][ch] = __dmul_rn(F.pre.ptr[po], Fs[buf][kk][ch]);
-                    Fs[buf][kk][ch + 1] = __dmul_rn(F.pre.ptr[po + F.pre.s[F.vec_axis]], Fs[buf][kk][ch + 1]);
+                    Fs[buf][kk][ch] = __dmul_rn(pcc[2 * q], Fs[buf][kk][ch]);
+                    Fs[buf][kk][ch + 1] = __dmul_rn(pcc[2 * q + 1], Fs[buf][kk][ch + 1]);
                 }
             }
         }
