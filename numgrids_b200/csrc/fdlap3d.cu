@@ -749,6 +749,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* t
         ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
 // TMAP: the producer issues ONE 3-D tensor-map TMA per plane (box 68 x (TY+4) x 1, out-of-bounds
 // elements zero-filled by the hardware) instead of TY+4 row copies.
 template <int R, int WY, int S, int MINB, bool SLAB, bool TMAP>
@@ -776,6 +784,9 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // zmode 0: every z tile; 1: interior tiles only (no halo dependence); 2: the first and last tile
+    // (bits 4, 5: A/B switches of tools/ab_fdlap.py -- single-lane z sums, 3-D halo boxes)
+    const bool ab_zsingle = (zmode & 16) != 0, ab_halo3d = (zmode & 32) != 0;
+    zmode &= 3;
     const int zt_idx = zmode == 1 ? (int)blockIdx.x + 1
                                   : (zmode == 2 ? (blockIdx.x == 0 ? 0 : nz / RING_TZ - 1) : (int)blockIdx.x);
     const int z0 = zt_idx * RING_TZ;
@@ -809,8 +820,16 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
                     if (q >= S) mbar_wait(&empty[s], eph ^ 1);
                     mbar_arrive_expect_tx(&full[s], PLANE_B + (lo_tile ? ROWS * 16u : 0u) + (hi_tile ? ROWS * 16u : 0u));   // bytes the TMAs deliver (slots are padded to 128 B)
                     tma_load_3d(ring + (size_t)s * PLANE, &tmap, z0 - 2, yb - 2, p_first + q, &full[s]);
-                    if (lo_tile) tma_load_3d(hlo + (size_t)s * HALO, &tmap_lo, 0, yb - 2, p_first + q, &full[s]);
-                    if (hi_tile) tma_load_3d(hhi + (size_t)s * HALO, &tmap_hi, 0, yb - 2, p_first + q, &full[s]);
+                    // halo planes are [nx][ny][2]: the tile's ROWS x 2 values of one plane are ONE contiguous
+                    // 16*ROWS-byte run, fetched as a single-row 2-D box (a {2, ROWS, 1} box would cost ROWS
+                    // 16-byte row requests -- as many TMA row operations as the main box)
+                    if (ab_halo3d) {
+                        if (lo_tile) tma_load_3d(hlo + (size_t)s * HALO, &tmap_lo, 0, yb - 2, p_first + q, &full[s]);
+                        if (hi_tile) tma_load_3d(hhi + (size_t)s * HALO, &tmap_hi, 0, yb - 2, p_first + q, &full[s]);
+                    } else {
+                        if (lo_tile) tma_load_2d(hlo + (size_t)s * HALO, &tmap_lo, 2 * (yb - 2), p_first + q, &full[s]);
+                        if (hi_tile) tma_load_2d(hhi + (size_t)s * HALO, &tmap_hi, 2 * (yb - 2), p_first + q, &full[s]);
+                    }
                     if (++s == S) { s = 0; if (q >= S) eph ^= 1; }
                 }
             }
@@ -848,7 +867,8 @@ fdlap3d_ring2_kernel(const double* __restrict__ in, double* __restrict__ out, in
     const int z = z0 + 2 * lane;
     const bool zfix_lo = (z0 == 0) && (lo == nullptr), zfix_hi = (z0 + RING_TZ == nz) && (hi == nullptr);
     const bool rowfix = (y0 < 2) || (y0 + R > ny - 2);                            // warp-uniform, rare
-    const int ztile = (zfix_lo ? 1 : 0) | (zfix_hi ? 2 : 0);                      // warp-uniform
+    const int ztile = ab_zsingle ? ((zfix_lo || zfix_hi) ? 3 : 0)
+                                 : ((zfix_lo ? 1 : 0) | (zfix_hi ? 2 : 0));      // warp-uniform
     const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
     // this lane's halo pair address in slot 0 (0 = not an edge lane of an edge tile)
     unsigned a_hlo = (lo_tile && lane == 0) ? smem_u32(hlo) + (unsigned)(j0 + 2) * 16u : 0u;
@@ -958,6 +978,33 @@ static int env_int(const char* name, int dflt) {
     return s ? atoi(s) : dflt;
 }
 
+// 2-D tensor map over a halo array [nx][ny][2] viewed as nx rows of 2*ny doubles: box = 2*rows x 1.
+static int make_tmap_halo(CUtensorMap* tm, const double* halo, i64 nx, i64 ny, int rows) {
+    ng_encode_fn encode = nullptr;
+    {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NG_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
+        if (!fp || qres != cudaDriverEntryPointSuccess) {
+            ng_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return NG_ECUDA;
+        }
+        encode = (ng_encode_fn)fp;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * ny), (cuuint64_t)nx};
+    const cuuint64_t gstr[1] = {(cuuint64_t)(2 * ny) * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * rows), 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)halo, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ng_set_error("cuTensorMapEncodeTiled (halo) failed with CUresult %d", (int)r);
+        return NG_ECUDA;
+    }
+    return NG_OK;
+}
+
 int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const double* lo,
                           const double* hi, int xbeg, int xend, int zmode, cudaStream_t st, bool* handled) {
     *handled = false;
@@ -1003,6 +1050,8 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         const int cfg_s = env_int("NG_FDLAP_S", 8);
         const bool slab = (lo != nullptr) || (hi != nullptr);
         const bool use_tmap = env_int("NG_FDLAP_TMAP", 1) != 0;
+        const bool ab_halo3d = env_int("NG_FDLAP_HALO3D", 0) != 0;          // A/B switches (tools/ab_fdlap.py)
+        const int ab_flags = (env_int("NG_FDLAP_ZSINGLE", 0) ? 16 : 0) | (ab_halo3d ? 32 : 0);
         bool launched = false, skip_count = false;
 #define NG_RING2_GO1(RR, WW, SS, MB, SL, TM)                                                         \
     {                                                                                              \
@@ -1023,12 +1072,12 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         memset(&tm, 0, sizeof(tm)); memset(&tm_lo, 0, sizeof(tm)); memset(&tm_hi, 0, sizeof(tm));  \
         if (TM) {                                                                                  \
             int trc = make_tmap(&tm, in, nx, ny, nz, RING_PITCH, RR * WW + 4);                     \
-            if (!trc && SL && lo) trc = make_tmap(&tm_lo, lo, nx, ny, 2, 2, RR * WW + 4);          \
-            if (!trc && SL && hi) trc = make_tmap(&tm_hi, hi, nx, ny, 2, 2, RR * WW + 4);          \
+            if (!trc && SL && lo) trc = ab_halo3d ? make_tmap(&tm_lo, lo, nx, ny, 2, 2, RR * WW + 4) : make_tmap_halo(&tm_lo, lo, nx, ny, RR * WW + 4); \
+            if (!trc && SL && hi) trc = ab_halo3d ? make_tmap(&tm_hi, hi, nx, ny, 2, 2, RR * WW + 4) : make_tmap_halo(&tm_hi, hi, nx, ny, RR * WW + 4); \
             if (trc) return trc;                                                                   \
         }                                                                                          \
         fdlap3d_ring2_kernel<RR, WW, SS, MB, SL, TM><<<grid, 32 * (WW + 1), smem + 128, st>>>(     \
-            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, zmode, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
+            in, out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, zmode | ab_flags, WU, (const Lap3Side*)p->d_Mt, lo, hi, tm,  \
             tm_lo, tm_hi);                                                                         \
         launched = true; }                                                                         \
     }
