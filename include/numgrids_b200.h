@@ -194,6 +194,17 @@ int ng_curv_gradient(ng_plan* plan, const double* d_f, double* const* d_out, voi
 int ng_curv_divergence(ng_plan* plan, const double* const* d_v, double* d_out, void* stream);
 int ng_curv_curl(ng_plan* plan, const double* const* d_v, double* const* d_out, void* stream);
 
+/* ---- array-level boundary conditions (numgrids/boundary.py:157-166, :216-245) ------------------
+ * In place on a device array of the given shape, so that a time-stepping loop keeps its field on
+ * the device between derivative applies.  The face is the array with `axis` removed (C order).
+ *   NG_BC_DIRICHLET  u[face] = g
+ *   NG_BC_NEUMANN    u[face] = u[adjacent layer] + hs * g,  hs = h * normal_sign from the host
+ *                    (the reference's first-order form: h = |x[1]-x[0]| at the face, sign -1 low / +1 high)
+ * d_g: device array of face values, or NULL to use g_scalar everywhere. */
+enum ng_bc_kind { NG_BC_DIRICHLET = 0, NG_BC_NEUMANN = 1 };
+int ng_bc_apply(int ndim, const int64_t* shape, int axis, int side /* 0 low, 1 high */, int kind,
+                double hs, const double* d_g, double g_scalar, double* d_u, void* stream);
+
 /* ---- lifetime ---------------------------------------------------------------------------------*/
 int ng_plan_destroy(ng_plan* plan);
 /* bytes of device memory owned by the plan (tables + workspace + host-call staging) */

@@ -1,11 +1,13 @@
 """numgrids_b200 -- B200-native (sm_100a) implementation of the numgrids differentiation hot path.
 
 Drop-in for the reference's hot-path API: ``Grid``, ``CurvilinearGrid``, ``SphericalGrid``,
-``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` / ``Axis``, ``Diff``, ``diff``.
+``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` / ``Axis``, ``Diff``, ``diff``,
+plus the step that follows a derivative apply in a PDE loop: ``BoundaryFace``, ``DirichletBC``,
+``NeumannBC``, ``RobinBC``, ``apply_bcs`` (in place on device arrays).
 ``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` run hand-written CUDA kernels
 through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.
 
-Reference components outside the hot path (boundary conditions, integration, interpolation, AMR,
+Reference components outside the hot path (integration, interpolation, AMR,
 I/O, plotting, MultiGrid -- SURVEY.md section 2) are intentionally not provided; accessing their
 names raises ``NotImplementedError`` that says so.
 """
@@ -17,14 +19,14 @@ from .grids import Grid
 from .curvilinear import CurvilinearGrid
 from .api import (Diff, AxisType, create_axis, SphericalGrid, CylindricalGrid, PolarGrid, diff,
                   CartesianLaplacian, cartesian_laplacian)
+from .boundary import BoundaryFace, DirichletBC, NeumannBC, RobinBC, apply_bcs
 from ._lib import NumgridsB200Error
 
 # Backward compatibility alias kept by the reference (numgrids/__init__.py:13)
 Axis = create_axis
 
 _OUT_OF_SCOPE = {
-    "MultiGrid", "Interpolator", "Integral", "BoundaryFace", "DirichletBC", "NeumannBC", "RobinBC",
-    "apply_bcs", "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
+    "MultiGrid", "Interpolator", "Integral", "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
     "estimate_error", "interpolate", "integrate",
 }
 

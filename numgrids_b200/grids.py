@@ -67,6 +67,19 @@ class Grid:
         return self._boundary
 
     @property
+    def faces(self):
+        """All boundary faces keyed '{axis_index}_{side}'; periodic axes are skipped (numgrids/grids.py:124-139)."""
+        if self.cache["faces"] is None:
+            from .boundary import BoundaryFace
+            result = {}
+            for i, axis in enumerate(self.axes):
+                if not axis.periodic:
+                    result[f"{i}_low"] = BoundaryFace(self, i, "low")
+                    result[f"{i}_high"] = BoundaryFace(self, i, "high")
+            self.cache["faces"] = result
+        return self.cache["faces"]
+
+    @property
     def meshed_indices(self):
         return np.meshgrid(*(np.arange(len(a)) for a in self.axes), indexing="ij")
 
