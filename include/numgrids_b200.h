@@ -205,6 +205,16 @@ enum ng_bc_kind { NG_BC_DIRICHLET = 0, NG_BC_NEUMANN = 1 };
 int ng_bc_apply(int ndim, const int64_t* shape, int axis, int side /* 0 low, 1 high */, int kind,
                 double hs, const double* d_g, double g_scalar, double* d_u, void* stream);
 
+/* ---- quadrature over the whole grid (numgrids/integration.py:44-72, Integral.__call__) ----------
+ * out[0] = sum_{i0,i1,..} w_0[i0] w_1[i1] ... f[i0,i1,..]: one streaming pass (8 B/point).  d_w[a] is
+ * the device table of shape[a] weights the host derives exactly as the reference does (periodic axis:
+ * the spacing everywhere, integration.py:61-63; otherwise 0 followed by the last row of
+ * inv(D[1:,1:]), integration.py:33-40, :65-70).  d_work: >= ng_quad_workspace_doubles() doubles of
+ * device scratch; d_out: one device double.  Deterministic for a given shape (no atomics). */
+int64_t ng_quad_workspace_doubles(void);
+int ng_quad_apply(int ndim, const int64_t* shape, const double* const* d_w, const double* d_f,
+                  double* d_work, double* d_out, void* stream);
+
 /* ---- lifetime ---------------------------------------------------------------------------------*/
 int ng_plan_destroy(ng_plan* plan);
 /* bytes of device memory owned by the plan (tables + workspace + host-call staging) */

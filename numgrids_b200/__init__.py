@@ -3,11 +3,12 @@
 Drop-in for the reference's hot-path API: ``Grid``, ``CurvilinearGrid``, ``SphericalGrid``,
 ``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` / ``Axis``, ``Diff``, ``diff``,
 plus the step that follows a derivative apply in a PDE loop: ``BoundaryFace``, ``DirichletBC``,
-``NeumannBC``, ``RobinBC``, ``apply_bcs`` (in place on device arrays).
+``NeumannBC``, ``RobinBC``, ``apply_bcs`` (in place on device arrays) and
+``Integral`` / ``integrate`` (one streaming quadrature pass, N3).
 ``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` run hand-written CUDA kernels
 through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.
 
-Reference components outside the hot path (integration, interpolation, AMR,
+Reference components outside the hot path (interpolation, AMR,
 I/O, plotting, MultiGrid -- SURVEY.md section 2) are intentionally not provided; accessing their
 names raises ``NotImplementedError`` that says so.
 """
@@ -18,7 +19,8 @@ from . import diff as _diff_module   # load the submodule first so that the `dif
 from .grids import Grid
 from .curvilinear import CurvilinearGrid
 from .api import (Diff, AxisType, create_axis, SphericalGrid, CylindricalGrid, PolarGrid, diff,
-                  CartesianLaplacian, cartesian_laplacian)
+                  CartesianLaplacian, cartesian_laplacian, integrate)
+from .integration import Integral
 from .boundary import BoundaryFace, DirichletBC, NeumannBC, RobinBC, apply_bcs
 from ._lib import NumgridsB200Error
 
@@ -26,8 +28,8 @@ from ._lib import NumgridsB200Error
 Axis = create_axis
 
 _OUT_OF_SCOPE = {
-    "MultiGrid", "Interpolator", "Integral", "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
-    "estimate_error", "interpolate", "integrate",
+    "MultiGrid", "Interpolator", "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
+    "estimate_error", "interpolate",
 }
 
 

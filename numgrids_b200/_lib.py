@@ -74,6 +74,8 @@ SIGNATURES = {
     "ng_curv_divergence": (C.c_int, [_P, _PP, _P, _P]),
     "ng_curv_curl": (C.c_int, [_P, _PP, _PP, _P]),
     "ng_bc_apply": (C.c_int, [C.c_int, _I64, C.c_int, C.c_int, C.c_int, C.c_double, _P, C.c_double, _P, _P]),
+    "ng_quad_workspace_doubles": (C.c_int64, []),
+    "ng_quad_apply": (C.c_int, [C.c_int, _I64, _PP, _P, _P, _P, _P]),
     "ng_plan_destroy": (C.c_int, [_P]),
     "ng_plan_device_bytes": (C.c_int64, [_P]),
 }

@@ -91,6 +91,18 @@ def diff(grid, f, order=1, axis_index=0, acc=4):
     return ops[key](f)
 
 
+def integrate(grid, f):
+    """Integrate a meshed function over the whole grid; the operator is cached on the grid
+    under the reference's key (numgrids/api.py:309-335)."""
+    from .integration import Integral
+    if grid.cache.get("integral"):
+        I = grid.cache["integral"]
+    else:
+        I = Integral(grid)
+        grid.cache["integral"] = I
+    return I(f)
+
+
 class CartesianLaplacian:
     """Fused ``Diff(g,2,0)(f) + Diff(g,2,1)(f) + ...`` on equidistant non-periodic axes.
 
