@@ -120,7 +120,13 @@ dense_apply_kernel(const double* __restrict__ in, double* __restrict__ out,
 // k panels of 16 double-buffered in shared memory with cp.async (LDGSTS) so the next panel streams
 // in under the 2048 FP64 instructions of the current one.  Same arithmetic contract as above.
 // -------------------------------------------------------------------------------------------------
-constexpr int FM = 128, FN = 128, FK = 16;
+#ifndef NG_DENSE_FK
+#define NG_DENSE_FK 16
+#endif
+#ifndef NG_DENSE_MINB
+#define NG_DENSE_MINB 2
+#endif
+constexpr int FM = 128, FN = 128, FK = NG_DENSE_FK, FKS = FK / 16;   // FKS: staging copies scale with the panel depth
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -141,7 +147,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // the F panel is transposed on the fly by 8-byte cp.async (source coalesced along k), outputs are
 // stored as (i, i+1) pairs of one pencil.
 template <bool DESC, bool FMA, bool FUSED, int NCP, bool LASTAX>
-__global__ void __launch_bounds__(256, NCP == 4 ? 1 : 2)
+__global__ void __launch_bounds__(256, NCP == 4 ? 1 : NG_DENSE_MINB)
 dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                   const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F) {
     constexpr int TFN = 32 * NCP, HALF = TFN / 2;
@@ -170,14 +176,14 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     if (FUSED && F.pre.ptr && !LASTAX) pre_ix = unravel4((o * n) * inner + c0 + (tid % HALF) * 2, F.shape);
     // prologue coefficients (`coeff * v[i]`) of the panel in flight, fetched with the panel so that
     // their global-load latency hides under the previous panel's arithmetic
-    double pcn[2 * NCP];
+    double pcn[2 * NCP * FKS];
 #pragma unroll
-    for (int q = 0; q < 2 * NCP; ++q) pcn[q] = 0.0;
+    for (int q = 0; q < 2 * NCP * FKS; ++q) pcn[q] = 0.0;
     auto stage = [&](int p, int buf) {
         const int k0 = p * FK;
         if (FUSED && !LASTAX && F.pre.ptr) {
 #pragma unroll
-            for (int q = 0; q < NCP; ++q) {
+            for (int q = 0; q < NCP * FKS; ++q) {
                 const int kk = (tid + q * 256) / HALF;
                 Idx4 ix = pre_ix;
                 ix.i[axis] = k0 + kk;
@@ -188,7 +194,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         }
         // M panel: 16 x 128 doubles = 1024 16-byte chunks (4 per thread); F panel: 16 x TFN (NCP per thread)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4 * FKS; ++q) {
             const int e = tid + q * 256;
             const int kk = e >> 6, ch = (e & 63) * 2;
             cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * n + row0 + ch);
@@ -196,14 +202,14 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         if (LASTAX) {
             // 16 x TFN doubles as 8-byte copies: consecutive threads walk k (128 B contiguous per pencil)
 #pragma unroll
-            for (int q = 0; q < 2 * NCP; ++q) {
+            for (int q = 0; q < 2 * NCP * FKS; ++q) {
                 const int e = tid + q * 256;
-                const int kk = e & 15, c = e >> 4;
+                const int kk = e % FK, c = e / FK;
                 cp_async8(&Fs[buf][kk][c], fbase + (i64)c * n + k0 + kk);
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < NCP; ++q) {
+            for (int q = 0; q < NCP * FKS; ++q) {
                 const int e = tid + q * 256;
                 const int kk = e / HALF, ch = (e % HALF) * 2;
                 cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
@@ -214,9 +220,9 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     stage(DESC ? npanel - 1 : 0, 0);
     for (int pp = 0; pp < npanel; ++pp) {
         const int buf = pp & 1;
-        double pcc[2 * NCP];                        // this panel's prologue coefficients
+        double pcc[2 * NCP * FKS];                  // this panel's prologue coefficients
 #pragma unroll
-        for (int q = 0; q < 2 * NCP; ++q) pcc[q] = pcn[q];
+        for (int q = 0; q < 2 * NCP * FKS; ++q) pcc[q] = pcn[q];
         if (pp + 1 < npanel) {
             stage(DESC ? npanel - 2 - pp : pp + 1, buf ^ 1);
             cp_async_wait<1>();
@@ -229,15 +235,15 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             const int k0 = (DESC ? npanel - 1 - pp : pp) * FK;
             if (LASTAX) {
 #pragma unroll
-                for (int q = 0; q < 2 * NCP; ++q) {
+                for (int q = 0; q < 2 * NCP * FKS; ++q) {
                     const int e = tid + q * 256;
-                    const int kk = e & 15, c = e >> 4;
+                    const int kk = e % FK, c = e / FK;
                     const Idx4 ix = unravel4((col0 + c) * (i64)n + k0 + kk, F.shape);
                     Fs[buf][kk][c] = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], Fs[buf][kk][c]);
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < NCP; ++q) {
+                for (int q = 0; q < NCP * FKS; ++q) {
                     const int e = tid + q * 256;
                     const int kk = e / HALF, ch = (e % HALF) * 2;
                     Fs[buf][kk][ch] = __dmul_rn(pcc[2 * q], Fs[buf][kk][ch]);
@@ -352,10 +358,12 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
     if (p->inner == 1) {                       // contiguous contraction axis
         const bool wide_l = force ? force == 4 : (big_tiles >= 4 * 148 && p->outer % FN == 0);
         if (wide_l && p->outer % FN == 0) return launch_fast2<DESC, FMA, 4, true>(p, in, out, F, st);
+        if (force == 2 && p->outer % 64 == 0) return launch_fast2<DESC, FMA, 2, true>(p, in, out, F, st);
         return launch_fast2<DESC, FMA, 1, true>(p, in, out, F, st);
     }
     const bool wide = force ? force == 4 : (big_tiles >= 4 * 148 && p->inner % FN == 0);
     if (wide && p->inner % FN == 0) return launch_fast2<DESC, FMA, 4, false>(p, in, out, F, st);
+    if (force == 2 && p->inner % 64 == 0) return launch_fast2<DESC, FMA, 2, false>(p, in, out, F, st);
     return launch_fast2<DESC, FMA, 1, false>(p, in, out, F, st);
 }
 

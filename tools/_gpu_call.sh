@@ -1,4 +1,7 @@
-set -x
-python -m pytest tests/test_boundary.py tests/test_integral.py -x -q -m gpu > gpurun_out/pytest_n2n3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_n2n3.log
-python tools/time_quad_bc.py > gpurun_out/time_quad_bc.log 2>&1
-tail -5 gpurun_out/pytest_n2n3.log; cat gpurun_out/time_quad_bc.log
+V=numgrids_b200/lib/variants
+L=gpurun_out/dense_variants.log
+: > $L
+python tools/time_cfg4_variants.py >> $L 2>&1
+for v in minb3 fk32b fk32minb3; do NUMGRIDS_B200_LIB=$PWD/$V/libng_$v.so python tools/time_cfg4_variants.py >> $L 2>&1; done
+for v in ncp2 ncp2minb1; do NG_DENSE_NCP=2 NUMGRIDS_B200_LIB=$PWD/$V/libng_$v.so python tools/time_cfg4_variants.py >> $L 2>&1; done
+cat $L

@@ -1,11 +1,12 @@
-"""Dynamic opcode mix + top stall lines from an .ncu-rep source page: python tools/ncu_opmix.py rep points"""
+"""Dynamic opcode mix + top stall lines from an .ncu-rep source page: python tools/ncu_opmix.py rep points [ncu launch filters]"""
 import collections
 import csv
 import subprocess
 import sys
 
 rep, pts = sys.argv[1], float(sys.argv[2])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+extra = sys.argv[3:]          # e.g. -s 2 -c 1 to pick one launch of the report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 ci, ei, si = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")

@@ -1,4 +1,4 @@
-"""cfg4 (SphericalGrid 128x128x256) composite timings on device tensors, sweeping NG_DENSE_STAGGER_NS."""
+"""Time cfg4-size Chebyshev applies / the spherical Laplacian with one library variant (NUMGRIDS_B200_LIB)."""
 import os
 import sys
 import statistics
@@ -19,6 +19,12 @@ o = torch.empty_like(f)
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float64, device="cuda")
 d0 = ng.Diff(g, 1, 0).operator.operator
 d1 = ng.Diff(g, 1, 1).operator.operator
+ax = ng.create_axis(A.CHEBYSHEV, 256, 0.0, 1.0)
+g2 = ng.Grid(ax, ax, ax)
+f2 = torch.randn(256, 256, 256, dtype=torch.float64, device="cuda")
+o2 = torch.empty_like(f2)
+c0 = ng.Diff(g2, 2, 0).operator.operator
+c2 = ng.Diff(g2, 2, 2).operator.operator
 
 
 def timed(fn, steps=15, warm=3):
@@ -36,17 +42,11 @@ def timed(fn, steps=15, warm=3):
     return statistics.median(ts)
 
 
-ref = None
-for ns in sys.argv[1:] or ["0", "4000", "8000", "12000", "16000"]:
-    os.environ["NG_DENSE_STAGGER_NS"] = ns
-    a0 = timed(lambda: d0.apply_ptr(f.data_ptr(), o.data_ptr()))
-    a1 = timed(lambda: d1.apply_ptr(f.data_ptr(), o.data_ptr()))
-    lap = timed(lambda: g.laplacian(f))
-    grad = timed(lambda: g.gradient(f))
-    div = timed(lambda: g.divergence(f, f, f))
-    curl = timed(lambda: g.curl(f, f, f))
-    out = g.laplacian(f)
-    if ref is None:
-        ref = out.clone()
-    print(f"stagger={ns:>6s} ns: Diff axis0 {a0 * 1e3:.1f} us  axis1 {a1 * 1e3:.1f} us  laplacian {lap:.3f} ms  gradient {grad:.3f}  "
-          f"divergence {div:.3f}  curl {curl:.3f}  bit-equal={torch.equal(out, ref)}", flush=True)
+a0 = timed(lambda: d0.apply_ptr(f.data_ptr(), o.data_ptr()))
+a1 = timed(lambda: d1.apply_ptr(f.data_ptr(), o.data_ptr()))
+lap = timed(lambda: g.laplacian(f))
+b0 = timed(lambda: c0.apply_ptr(f2.data_ptr(), o2.data_ptr()))
+b2 = timed(lambda: c2.apply_ptr(f2.data_ptr(), o2.data_ptr()))
+chk = float(g.laplacian(f).double().sum().item())
+print(f"{os.environ.get('NUMGRIDS_B200_LIB', 'default')[-24:]:>24s} NCP={os.environ.get('NG_DENSE_NCP', '-')}: cfg4 Diff axis0 {a0 * 1e3:.1f} us  axis1 {a1 * 1e3:.1f} us  "
+      f"laplacian {lap:.3f} ms | cfg2 axis0 {b0:.3f} ms axis2 {b2:.3f} ms | checksum {chk!r}", flush=True)
