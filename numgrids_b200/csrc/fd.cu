@@ -119,6 +119,256 @@ fd_apply_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Streaming kernels for the central scheme with offsets -P..P (every findiff central stencil), P <= 4.
+// Each input element is loaded from global memory exactly once (plus a (2P)-element window refill
+// per segment) and every access is 128 bits wide, so the kernels run at the HBM roofline (16 B/pt);
+// the gather kernel above re-reads every tap through L1/L2 and stays the any-shape fallback.
+// Same arithmetic as the gather kernel, bit for bit: acc = 0.0; acc = acc + w_k * x_k in stored order.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg128(const double* p) {
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// (a) derivative axis is NOT the contiguous one: thread = one pair of adjacent columns of the
+// [outer][n][inner] view, marching along n with a (2P+1)-deep window of double2 in registers (the loop
+// is unrolled by the window depth, so the rotation costs no moves).  Consecutive threads own
+// consecutive column pairs: every load/store of a warp is one contiguous 512-byte row piece.  n is cut
+// into `nseg` segments when there are too few columns to fill the machine.
+#ifndef NG_FD_MINB
+#define NG_FD_MINB 1
+#endif
+template <int P, bool FUSED>
+__global__ void __launch_bounds__(256, NG_FD_MINB)
+fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 outer, int n, i64 inner,
+                int axis, FdTables T, const double* __restrict__ xdiv, FuseDev F, int seg_len, int nseg) {
+    constexpr int W = 2 * P + 1;
+    const i64 inner2 = inner >> 1, ncol = outer * inner2;
+    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= ncol * nseg) return;
+    const int seg = (int)(idx / ncol);
+    const i64 col = idx - (i64)seg * ncol;
+    const i64 o = col / inner2, c = (col - o * inner2) * 2;
+    const int i0 = seg * seg_len, i1 = min(n, i0 + seg_len);
+    const i64 base = o * (i64)n * inner + c;                 // element i of this column pair: base + i*inner
+    const double* __restrict__ src = in + base;
+    double* __restrict__ dst = out + base;
+
+    i64 pre0 = 0, pre_a = 0, pre_v = 0, post0 = 0, post_a = 0, post_v = 0, div0 = 0, div_a = 0, div_v = 0;
+    if (FUSED) {
+        const Idx4 ix = unravel4(base, F.shape);             // coordinate along `axis` is 0 here
+        if (F.pre.ptr) { pre0 = coef_off(F.pre, ix); pre_a = F.pre.s[axis]; pre_v = F.pre.s[F.vec_axis]; }
+        if (F.post.ptr) { post0 = coef_off(F.post, ix); post_a = F.post.s[axis]; post_v = F.post.s[F.vec_axis]; }
+        if (F.div.ptr) { div0 = coef_off(F.div, ix); div_a = F.div.s[axis]; div_v = F.div.s[F.vec_axis]; }
+    }
+    auto ld = [&](int i) -> double2 {
+        double2 v = ldg128(src + (i64)i * inner);
+        if (FUSED && F.pre.ptr) {                            // `coeff * v[i]` once, as the value enters the window
+            const i64 po = pre0 + i * pre_a;
+            v.x = __dmul_rn(F.pre.ptr[po], v.x);
+            v.y = __dmul_rn(F.pre.ptr[po + pre_v], v.y);
+        }
+        return v;
+    };
+    auto finish = [&](int i, double ax, double ay) {
+        double2 r;
+        r.x = __dmul_rn(ax, T.inv_h_pow);
+        r.y = __dmul_rn(ay, T.inv_h_pow);
+        if (xdiv) { const double xd = xdiv[i]; r.x = __ddiv_rn(r.x, xd); r.y = __ddiv_rn(r.y, xd); }
+        const i64 lin = base + (i64)i * inner;
+        if (FUSED) {
+            r.x = fuse_tail_off(F, r.x, lin, post0 + i * post_a, div0 + i * div_a);
+            r.y = fuse_tail_off(F, r.y, lin + 1, post0 + i * post_a + post_v, div0 + i * div_a + div_v);
+        }
+        *reinterpret_cast<double2*>(dst + (i64)i * inner) = r;
+    };
+    auto one_sided = [&](int i, const double* w, const int* off) {
+        double ax = 0.0, ay = 0.0;
+        for (int k = 0; k < T.n_side; ++k) {
+            const double2 v = ld(i + off[k]);
+            ax = __dadd_rn(ax, __dmul_rn(w[k], v.x));
+            ay = __dadd_rn(ay, __dmul_rn(w[k], v.y));
+        }
+        finish(i, ax, ay);
+    };
+    for (int i = i0; i < min(P, i1); ++i) one_sided(i, T.wf, T.of);
+    for (int i = max(i0, n - P); i < i1; ++i) one_sided(i, T.wb, T.ob);
+
+    const int ia = max(i0, P), ib = min(i1, n - P);
+    if (ia >= ib) return;
+    // window: old[] = f[i-P .. i+P-1].  Full groups of W outputs issue their W loads up front (W x 16 B
+    // in flight per thread), then compute; the last (< W) outputs go one at a time.
+    double2 old[W - 1];
+#pragma unroll
+    for (int u = 0; u < W - 1; ++u) old[u] = ld(ia - P + u);
+    int i = ia;
+    for (; i + W <= ib; i += W) {
+        double2 nw[W];                                       // f[i+P .. i+P+W-1]
+#pragma unroll
+        for (int u = 0; u < W; ++u) nw[u] = ld(i + P + u);
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int k = 0; k < W; ++k) {                    // x_k = f[i+u-P+k]
+                const double2 x = (u + k < W - 1) ? old[u + k < W - 1 ? u + k : 0] : nw[u + k >= W - 1 ? u + k - (W - 1) : 0];
+                ax = __dadd_rn(ax, __dmul_rn(T.wc[k], x.x));
+                ay = __dadd_rn(ay, __dmul_rn(T.wc[k], x.y));
+            }
+            finish(i + u, ax, ay);
+        }
+#pragma unroll
+        for (int u = 0; u < W - 1; ++u) old[u] = nw[u + 1];
+    }
+    for (; i < ib; ++i) {
+        const double2 v = ld(i + P);
+        double ax = 0.0, ay = 0.0;
+#pragma unroll
+        for (int k = 0; k < W - 1; ++k) {
+            ax = __dadd_rn(ax, __dmul_rn(T.wc[k], old[k].x));
+            ay = __dadd_rn(ay, __dmul_rn(T.wc[k], old[k].y));
+        }
+        ax = __dadd_rn(ax, __dmul_rn(T.wc[W - 1], v.x));
+        ay = __dadd_rn(ay, __dmul_rn(T.wc[W - 1], v.y));
+        finish(i, ax, ay);
+#pragma unroll
+        for (int u = 0; u < W - 2; ++u) old[u] = old[u + 1];
+        old[W - 2] = v;
+    }
+}
+
+// (b) derivative axis IS the contiguous one: the [rows][n] view is cut into chunks of 64 doubles (lane l
+// holds the aligned pair 2l, 2l+1: one 512-byte load per chunk) and a warp takes a group of U consecutive
+// chunks of one row.  All U loads (plus the two edge pairs the group's first / last lanes need from the
+// neighbouring groups) are issued before any arithmetic.  The taps of neighbouring positions come from
+// the neighbouring lanes by warp shuffles, rotated through the previous / next chunk's registers at the
+// chunk edges.  Slab halos (HALO) enter as the positions -P..-1 and n..n+P-1 of the row; the one-sided
+// schemes overwrite the central result on the (at most P) boundary positions of a row end.
+template <int P, bool FUSED, bool HALO, int U>
+__global__ void __launch_bounds__(256)
+fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows, int n, int axis,
+              FdTables T, const double* __restrict__ xdiv, FuseDev F, const double* __restrict__ lo,
+              const double* __restrict__ hi, int gpr /* groups per row */) {
+    constexpr int H = (P + 1) / 2;                           // neighbour lanes needed on each side
+    constexpr int C = 2 * H;                                 // window index of this lane's .x
+    const int lane = threadIdx.x & 31;
+    const i64 g = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= rows * gpr) return;                             // whole warps leave together
+    i64 row;
+    int grp;
+    if (g < 0x7fffffffLL) {                                  // 32-bit divide (a 64-bit one costs ~100 instructions)
+        const unsigned r32 = (unsigned)g / (unsigned)gpr;
+        row = r32;
+        grp = (int)((unsigned)g - r32 * (unsigned)gpr);
+    } else {
+        row = g / gpr;
+        grp = (int)(g - row * gpr);
+    }
+    const int c0 = grp * U;                                  // first chunk of the group
+    const i64 base = row * (i64)n;
+    const double* __restrict__ src = in + base;
+    double* __restrict__ dst = out + base;
+    const bool has_lo = HALO && lo != nullptr, has_hi = HALO && hi != nullptr;
+
+    i64 pre0 = 0, pre_a = 0, post0 = 0, post_a = 0, div0 = 0, div_a = 0;
+    if (FUSED) {
+        const Idx4 ix = unravel4(base, F.shape);             // coordinate along `axis` (the last one) is 0
+        if (F.pre.ptr) { pre0 = coef_off(F.pre, ix); pre_a = F.pre.s[axis]; }
+        if (F.post.ptr) { post0 = coef_off(F.post, ix); post_a = F.post.s[axis]; }
+        if (F.div.ptr) { div0 = coef_off(F.div, ix); div_a = F.div.s[axis]; }
+    }
+    // one position of the row, halo planes included (they arrive already multiplied by `pre`)
+    auto value_at = [&](int q) -> double {
+        if (q < 0) return (has_lo && q >= -P) ? lo[row * P + P + q] : 0.0;
+        if (q >= n) return (has_hi && q - n < P) ? hi[row * P + (q - n)] : 0.0;
+        double x = src[q];
+        if (FUSED && F.pre.ptr) x = __dmul_rn(F.pre.ptr[pre0 + q * pre_a], x);
+        return x;
+    };
+    auto pair_at = [&](int pos) -> double2 {                 // the aligned pair at pos (n is even)
+        double2 v = make_double2(0.0, 0.0);
+        if (pos >= 0 && pos < n) {
+            v = ldg128(src + pos);
+            if (FUSED && F.pre.ptr) {
+                v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
+                v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
+            }
+        } else if (HALO) {
+            v.x = value_at(pos);
+            v.y = value_at(pos + 1);
+        }
+        return v;
+    };
+
+    const int p0 = c0 * 64 + 2 * lane;                       // this lane's pair in the group's first chunk
+    double2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = pair_at(p0 + 64 * u);
+    // virtual previous / next chunk: only the lanes next to the group are ever read
+    double2 pcl = make_double2(0.0, 0.0), ncr = make_double2(0.0, 0.0);
+    if (lane >= 32 - H) pcl = pair_at(p0 - 64);
+    if (lane < H) ncr = pair_at(p0 + 64 * U);
+
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int pos = p0 + 64 * u;
+        if ((c0 + u) * 64 >= n) break;                       // warp-uniform: chunk past the row end
+        const double2 prev = u == 0 ? pcl : v[u > 0 ? u - 1 : 0];
+        const double2 next = u == U - 1 ? ncr : v[u < U - 1 ? u + 1 : 0];
+        double win[4 * H + 2];                               // positions pos-2H .. pos+2H+1 of the row
+        win[C] = v[u].x;
+        win[C + 1] = v[u].y;
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            const double2 s = (lane >= 32 - j) ? prev : v[u];   // what lane (l+j)&31 needs from this lane
+            win[C - 2 * j] = __shfl_sync(0xffffffffu, s.x, (lane - j) & 31);
+            win[C - 2 * j + 1] = __shfl_sync(0xffffffffu, s.y, (lane - j) & 31);
+            const double2 t = (lane < j) ? next : v[u];
+            win[C + 2 * j] = __shfl_sync(0xffffffffu, t.x, (lane + j) & 31);
+            win[C + 2 * j + 1] = __shfl_sync(0xffffffffu, t.y, (lane + j) & 31);
+        }
+        double ax = 0.0, ay = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 2 * P + 1; ++kk) {
+            ax = __dadd_rn(ax, __dmul_rn(T.wc[kk], win[C - P + kk]));
+            ay = __dadd_rn(ay, __dmul_rn(T.wc[kk], win[C + 1 - P + kk]));
+        }
+        // one-sided schemes on the global boundary: only the first / last chunk of a row can hold them
+        if ((c0 + u == 0 && !has_lo) || ((c0 + u) * 64 + 64 + P > n && !has_hi)) {
+            auto one_sided = [&](int q, const double* w, const int* off) -> double {
+                double a = 0.0;
+                for (int k = 0; k < T.n_side; ++k) a = __dadd_rn(a, __dmul_rn(w[k], value_at(q + off[k])));
+                return a;
+            };
+            if (pos < n) {
+                if (!has_lo && pos < P) {
+                    ax = one_sided(pos, T.wf, T.of);
+                    if (pos + 1 < P) ay = one_sided(pos + 1, T.wf, T.of);
+                }
+                if (!has_hi && pos + 1 >= n - P) {
+                    ay = one_sided(pos + 1, T.wb, T.ob);
+                    if (pos >= n - P) ax = one_sided(pos, T.wb, T.ob);
+                }
+            }
+        }
+        if (pos < n) {
+            double2 r;
+            r.x = __dmul_rn(ax, T.inv_h_pow);
+            r.y = __dmul_rn(ay, T.inv_h_pow);
+            if (xdiv) {
+                const double2 xd = ldg128(xdiv + pos);
+                r.x = __ddiv_rn(r.x, xd.x);
+                r.y = __ddiv_rn(r.y, xd.y);
+            }
+            if (FUSED) {
+                r.x = fuse_tail_off(F, r.x, base + pos, post0 + pos * post_a, div0 + pos * div_a);
+                r.y = fuse_tail_off(F, r.y, base + pos + 1, post0 + (pos + 1) * post_a, div0 + (pos + 1) * div_a);
+            }
+            *reinterpret_cast<double2*>(dst + pos) = r;
+        }
+    }
+}
+
 // first / last nb planes along the axis -> [rows][nb]
 __global__ void fd_pack_halo_kernel(const double* __restrict__ in, double* __restrict__ lo_planes,
                                     double* __restrict__ hi_planes, i64 outer, i64 n, i64 inner,
@@ -162,10 +412,78 @@ inline int grid_for(i64 work_items, int block) {
 
 }  // namespace
 
+// central offsets -P..P in ascending stored order, P = nb <= 4: the streaming kernels apply
+static int central_half_width(const FdTables& T) {
+    if (T.n_center % 2 == 0 || T.n_center < 3 || T.n_center > 9) return 0;
+    const int P = T.n_center / 2;
+    if (T.nb != P) return 0;
+    for (int k = 0; k < T.n_center; ++k) if (T.oc[k] != k - P) return 0;
+    return P;
+}
+
+template <int P>
+static int launch_stream(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                         const double* lo, const double* hi, cudaStream_t st) {
+    const i64 target = 148LL * 2048 * 2;                     // threads (two full waves) worth aiming for
+    const int n = (int)p->n;
+    if (p->inner > 1) {
+        const i64 ncol = p->outer * (p->inner / 2);
+        i64 nseg = (target + ncol - 1) / ncol;
+        const i64 max_seg = n / 32 > 0 ? n / 32 : 1;          // keep segments >= 32 rows (window refill <= 2P/32)
+        if (nseg > max_seg) nseg = max_seg;
+        if (nseg < 1) nseg = 1;
+        const int seg_len = (int)((n + nseg - 1) / nseg);
+        nseg = (n + seg_len - 1) / seg_len;
+        const i64 threads = ncol * nseg;
+        const unsigned grid = (unsigned)((threads + 255) / 256);
+        if (F.any) fd_march_kernel<P, true><<<grid, 256, 0, st>>>(in, out, p->outer, n, p->inner, p->axis, p->fd, p->d_xdiv, F, seg_len, (int)nseg);
+        else fd_march_kernel<P, false><<<grid, 256, 0, st>>>(in, out, p->outer, n, p->inner, p->axis, p->fd, p->d_xdiv, F, seg_len, (int)nseg);
+    } else {
+        const i64 rows = p->outer;
+        const int nchunk = (n + 63) / 64;
+        const bool halo = lo || hi;
+        // U consecutive chunks per warp (U x 512 B in flight); small problems keep U = 1 so that every SM gets CTAs
+        const bool deep = rows * nchunk >= 148LL * 8 * 4 * 4 && nchunk >= 4;
+#define NG_FD_ROW(FU, HA, UU)                                                                            \
+    do {                                                                                                 \
+        const int gpr = (nchunk + UU - 1) / UU;                                                          \
+        fd_row_kernel<P, FU, HA, UU><<<(unsigned)((rows * gpr + 7) / 8), 256, 0, st>>>(                    \
+            in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, lo, hi, gpr);                                \
+    } while (0)
+#define NG_FD_ROW2(FU, HA) do { if (deep) NG_FD_ROW(FU, HA, 4); else NG_FD_ROW(FU, HA, 1); } while (0)
+        if (F.any) { if (halo) NG_FD_ROW2(true, true); else NG_FD_ROW2(true, false); }
+        else       { if (halo) NG_FD_ROW2(false, true); else NG_FD_ROW2(false, false); }
+#undef NG_FD_ROW2
+#undef NG_FD_ROW
+    }
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
 int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                  const double* lo, const double* hi, cudaStream_t st) {
     const bool halo = (lo != nullptr) || (hi != nullptr);
     const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    {
+        // streaming kernels: 128-bit accesses throughout, so pairs along the contiguous direction must
+        // be aligned and must not straddle a row of the innermost grid axis
+        const char* se = getenv("NG_FD_STREAM");          // tuning / A-B checks: 0 = gather kernel only
+        const bool off = se && atoi(se) == 0;
+        const int P = off ? 0 : central_half_width(p->fd);
+        const i64 contiguous = p->inner > 1 ? p->inner : p->n;
+        const bool ok = P > 0 && aligned && contiguous % 2 == 0 && p->n >= 2 * P + 1 && p->n < (1LL << 30) &&
+                        p->size > 0 && !(halo && p->inner > 1) &&
+                        (!F.any || F.shape[F.vec_axis] % 2 == 0) &&
+                        (!halo || ((((uintptr_t)lo | (uintptr_t)hi) & 7) == 0));
+        if (ok) {
+            switch (P) {
+                case 1: return launch_stream<1>(p, in, out, F, lo, hi, st);
+                case 2: return launch_stream<2>(p, in, out, F, lo, hi, st);
+                case 3: return launch_stream<3>(p, in, out, F, lo, hi, st);
+                case 4: return launch_stream<4>(p, in, out, F, lo, hi, st);
+            }
+        }
+    }
     // 128-bit path: pairs must not straddle a row of the innermost (non-unit) grid axis when
     // coefficients are indexed per axis
     const bool vec2 = (p->inner % 2 == 0) && aligned && (!F.any || F.shape[F.vec_axis] % 2 == 0);

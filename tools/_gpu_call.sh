@@ -1,7 +1,4 @@
-V=numgrids_b200/lib/variants
-L=gpurun_out/dense_variants.log
-: > $L
-python tools/time_cfg4_variants.py >> $L 2>&1
-for v in minb3 fk32b fk32minb3; do NUMGRIDS_B200_LIB=$PWD/$V/libng_$v.so python tools/time_cfg4_variants.py >> $L 2>&1; done
-for v in ncp2 ncp2minb1; do NG_DENSE_NCP=2 NUMGRIDS_B200_LIB=$PWD/$V/libng_$v.so python tools/time_cfg4_variants.py >> $L 2>&1; done
-cat $L
+timeout 300 python tools/check_fd_stream.py 400 4 > gpurun_out/check_fd_stream.log 2>&1; echo "rc=$?" >> gpurun_out/check_fd_stream.log
+tail -5 gpurun_out/check_fd_stream.log
+timeout 200 python tools/time_fd.py > gpurun_out/time_fd7.log 2>&1
+grep "axis 2\|8192) order . axis 1" gpurun_out/time_fd7.log
