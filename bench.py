@@ -313,6 +313,25 @@ def per_config_extras(torch, ng, peak_gbs, quick):
         out["cfg1_fd_512x512_order1_axis0"] = {"error": repr(e)}
 
     try:
+        # the per-axis finite-difference Diff itself at cfg5's size: Diff(g, 2, axis) on equidistant 1024^3
+        # (streaming kernels: register-window march for axes 0/1, shuffle-tap row kernel for axis 2), 16 B/pt
+        nfd = 256 if quick else 1024
+        ax = ng.create_axis(A.EQUIDISTANT, nfd, 0.0, 1.0)
+        g = ng.Grid(ax, ax, ax)
+        f = torch.rand(nfd, nfd, nfd, dtype=torch.float64, device=dev)
+        o = torch.empty_like(f)
+        res = {}
+        for order, axis in ((2, 0), (2, 1), (2, 2), (1, 0), (1, 2)):
+            op = ng.Diff(g, order, axis).operator.operator
+            ms = timed(lambda: op.apply_ptr(f.data_ptr(), o.data_ptr()), 10, 3, nfd < 512)
+            res[f"order{order}_axis{axis}"] = {"gpts": nfd ** 3 / ms / 1e6, "ms": ms,
+                                               "hbm_frac": 16 * nfd ** 3 / ms / 1e6 / peak_gbs}
+        out[f"fd_diff_{nfd}cubed"] = res
+        del f, o
+    except Exception as e:  # pragma: no cover
+        out["fd_diff"] = {"error": repr(e)}
+
+    try:
         # cfg2: Diff(g, 2, 0) on Chebyshev 256^3 -- FP64-pipe-bound ordered DGEMM (2*256 instr/pt)
         n = 128 if quick else 256
         ax = ng.create_axis(A.CHEBYSHEV, n, 0.0, 1.0)

@@ -244,75 +244,64 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
 // the neighbouring lanes by warp shuffles, rotated through the previous / next chunk's registers at the
 // chunk edges.  Slab halos (HALO) enter as the positions -P..-1 and n..n+P-1 of the row; the one-sided
 // schemes overwrite the central result on the (at most P) boundary positions of a row end.
-template <int P, bool FUSED, bool HALO, int U>
-__global__ void __launch_bounds__(256)
-fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows, int n, int axis,
-              FdTables T, const double* __restrict__ xdiv, FuseDev F, const double* __restrict__ lo,
-              const double* __restrict__ hi, int gpr /* groups per row */) {
-    constexpr int H = (P + 1) / 2;                           // neighbour lanes needed on each side
-    constexpr int C = 2 * H;                                 // window index of this lane's .x
-    const int lane = threadIdx.x & 31;
-    const i64 g = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (g >= rows * gpr) return;                             // whole warps leave together
-    i64 row;
-    int grp;
-    if (g < 0x7fffffffLL) {                                  // 32-bit divide (a 64-bit one costs ~100 instructions)
-        const unsigned r32 = (unsigned)g / (unsigned)gpr;
-        row = r32;
-        grp = (int)((unsigned)g - r32 * (unsigned)gpr);
-    } else {
-        row = g / gpr;
-        grp = (int)(g - row * gpr);
-    }
-    const int c0 = grp * U;                                  // first chunk of the group
-    const i64 base = row * (i64)n;
-    const double* __restrict__ src = in + base;
-    double* __restrict__ dst = out + base;
-    const bool has_lo = HALO && lo != nullptr, has_hi = HALO && hi != nullptr;
+// Per-warp context of the row kernel and the body for one group of U chunks.  HEAD / TAIL say whether
+// the group touches the low / high end of its row: only then can a position fall outside [0, n) (slab
+// halo or nothing there), a chunk be partial, or a one-sided scheme apply; interior groups run without
+// any of those tests.
+template <int P, bool FUSED, bool HALO>
+struct RowCtx {
+    const double* __restrict__ src;
+    double* __restrict__ dst;
+    const double* __restrict__ xdiv;
+    const double* lo_row;                                    // this row's P halo values, or nullptr
+    const double* hi_row;
+    i64 base, pre0, pre_a, post0, post_a, div0, div_a;
+    int n;
 
-    i64 pre0 = 0, pre_a = 0, post0 = 0, post_a = 0, div0 = 0, div_a = 0;
-    if (FUSED) {
-        const Idx4 ix = unravel4(base, F.shape);             // coordinate along `axis` (the last one) is 0
-        if (F.pre.ptr) { pre0 = coef_off(F.pre, ix); pre_a = F.pre.s[axis]; }
-        if (F.post.ptr) { post0 = coef_off(F.post, ix); post_a = F.post.s[axis]; }
-        if (F.div.ptr) { div0 = coef_off(F.div, ix); div_a = F.div.s[axis]; }
-    }
-    // one position of the row, halo planes included (they arrive already multiplied by `pre`)
-    auto value_at = [&](int q) -> double {
-        if (q < 0) return (has_lo && q >= -P) ? lo[row * P + P + q] : 0.0;
-        if (q >= n) return (has_hi && q - n < P) ? hi[row * P + (q - n)] : 0.0;
+    __device__ __forceinline__ double value_at(const FuseDev& F, int q) const {
+        if (q < 0) return (HALO && lo_row && q >= -P) ? lo_row[P + q] : 0.0;
+        if (q >= n) return (HALO && hi_row && q - n < P) ? hi_row[q - n] : 0.0;
         double x = src[q];
         if (FUSED && F.pre.ptr) x = __dmul_rn(F.pre.ptr[pre0 + q * pre_a], x);
         return x;
-    };
-    auto pair_at = [&](int pos) -> double2 {                 // the aligned pair at pos (n is even)
+    }
+    template <bool CHECK>
+    __device__ __forceinline__ double2 pair_at(const FuseDev& F, int pos) const {   // aligned pair (n is even)
         double2 v = make_double2(0.0, 0.0);
-        if (pos >= 0 && pos < n) {
+        if (!CHECK || (pos >= 0 && pos < n)) {
             v = ldg128(src + pos);
             if (FUSED && F.pre.ptr) {
                 v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
                 v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
             }
         } else if (HALO) {
-            v.x = value_at(pos);
-            v.y = value_at(pos + 1);
+            v.x = value_at(F, pos);
+            v.y = value_at(F, pos + 1);
         }
         return v;
-    };
+    }
+};
 
+template <int P, bool FUSED, bool HALO, int U, bool HEAD, bool TAIL>
+__device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, const FdTables& T,
+                                             const FuseDev& F, int c0, int lane) {
+    constexpr int H = (P + 1) / 2;                           // neighbour lanes needed on each side
+    constexpr int C = 2 * H;                                 // window index of this lane's .x
+    const int n = R.n;
     const int p0 = c0 * 64 + 2 * lane;                       // this lane's pair in the group's first chunk
     double2 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = pair_at(p0 + 64 * u);
+    for (int u = 0; u < U; ++u) v[u] = R.template pair_at<TAIL>(F, p0 + 64 * u);
     // virtual previous / next chunk: only the lanes next to the group are ever read
     double2 pcl = make_double2(0.0, 0.0), ncr = make_double2(0.0, 0.0);
-    if (lane >= 32 - H) pcl = pair_at(p0 - 64);
-    if (lane < H) ncr = pair_at(p0 + 64 * U);
+    if (lane >= 32 - H) pcl = R.template pair_at<HEAD>(F, p0 - 64);
+    if (lane < H) ncr = R.template pair_at<TAIL>(F, p0 + 64 * U);
+    const bool one_lo = HEAD && !(HALO && R.lo_row), one_hi = TAIL && !(HALO && R.hi_row);
 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int pos = p0 + 64 * u;
-        if ((c0 + u) * 64 >= n) break;                       // warp-uniform: chunk past the row end
+        if (TAIL && (c0 + u) * 64 >= n) break;               // warp-uniform: chunk past the row end
         const double2 prev = u == 0 ? pcl : v[u > 0 ? u - 1 : 0];
         const double2 next = u == U - 1 ? ncr : v[u < U - 1 ? u + 1 : 0];
         double win[4 * H + 2];                               // positions pos-2H .. pos+2H+1 of the row
@@ -334,39 +323,82 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
             ay = __dadd_rn(ay, __dmul_rn(T.wc[kk], win[C + 1 - P + kk]));
         }
         // one-sided schemes on the global boundary: only the first / last chunk of a row can hold them
-        if ((c0 + u == 0 && !has_lo) || ((c0 + u) * 64 + 64 + P > n && !has_hi)) {
+        if ((one_lo && c0 + u == 0) || (one_hi && (c0 + u) * 64 + 64 + P > n)) {
             auto one_sided = [&](int q, const double* w, const int* off) -> double {
                 double a = 0.0;
-                for (int k = 0; k < T.n_side; ++k) a = __dadd_rn(a, __dmul_rn(w[k], value_at(q + off[k])));
+                for (int k = 0; k < T.n_side; ++k) a = __dadd_rn(a, __dmul_rn(w[k], R.value_at(F, q + off[k])));
                 return a;
             };
             if (pos < n) {
-                if (!has_lo && pos < P) {
+                if (one_lo && pos < P) {
                     ax = one_sided(pos, T.wf, T.of);
                     if (pos + 1 < P) ay = one_sided(pos + 1, T.wf, T.of);
                 }
-                if (!has_hi && pos + 1 >= n - P) {
+                if (one_hi && pos + 1 >= n - P) {
                     ay = one_sided(pos + 1, T.wb, T.ob);
                     if (pos >= n - P) ax = one_sided(pos, T.wb, T.ob);
                 }
             }
         }
-        if (pos < n) {
+        if (!TAIL || pos < n) {
             double2 r;
             r.x = __dmul_rn(ax, T.inv_h_pow);
             r.y = __dmul_rn(ay, T.inv_h_pow);
-            if (xdiv) {
-                const double2 xd = ldg128(xdiv + pos);
+            if (R.xdiv) {
+                const double2 xd = ldg128(R.xdiv + pos);
                 r.x = __ddiv_rn(r.x, xd.x);
                 r.y = __ddiv_rn(r.y, xd.y);
             }
             if (FUSED) {
-                r.x = fuse_tail_off(F, r.x, base + pos, post0 + pos * post_a, div0 + pos * div_a);
-                r.y = fuse_tail_off(F, r.y, base + pos + 1, post0 + (pos + 1) * post_a, div0 + (pos + 1) * div_a);
+                r.x = fuse_tail_off(F, r.x, R.base + pos, R.post0 + pos * R.post_a, R.div0 + pos * R.div_a);
+                r.y = fuse_tail_off(F, r.y, R.base + pos + 1, R.post0 + (pos + 1) * R.post_a,
+                                    R.div0 + (pos + 1) * R.div_a);
             }
-            *reinterpret_cast<double2*>(dst + pos) = r;
+            *reinterpret_cast<double2*>(R.dst + pos) = r;
         }
     }
+}
+
+template <int P, bool FUSED, bool HALO, int U>
+__global__ void __launch_bounds__(256)
+fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows, int n, int axis,
+              FdTables T, const double* __restrict__ xdiv, FuseDev F, const double* __restrict__ lo,
+              const double* __restrict__ hi, int gpr /* groups per row */) {
+    const int lane = threadIdx.x & 31;
+    const i64 g = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= rows * gpr) return;                             // whole warps leave together
+    i64 row;
+    int grp;
+    if (g < 0x7fffffffLL) {                                  // 32-bit divide (a 64-bit one costs ~100 instructions)
+        const unsigned r32 = (unsigned)g / (unsigned)gpr;
+        row = r32;
+        grp = (int)((unsigned)g - r32 * (unsigned)gpr);
+    } else {
+        row = g / gpr;
+        grp = (int)(g - row * gpr);
+    }
+    RowCtx<P, FUSED, HALO> R;
+    R.n = n;
+    R.base = row * (i64)n;
+    R.src = in + R.base;
+    R.dst = out + R.base;
+    R.xdiv = xdiv;
+    R.lo_row = (HALO && lo) ? lo + row * P : nullptr;
+    R.hi_row = (HALO && hi) ? hi + row * P : nullptr;
+    R.pre0 = R.pre_a = R.post0 = R.post_a = R.div0 = R.div_a = 0;
+    if (FUSED) {
+        const Idx4 ix = unravel4(R.base, F.shape);           // coordinate along `axis` (the last one) is 0
+        if (F.pre.ptr) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; }
+        if (F.post.ptr) { R.post0 = coef_off(F.post, ix); R.post_a = F.post.s[axis]; }
+        if (F.div.ptr) { R.div0 = coef_off(F.div, ix); R.div_a = F.div.s[axis]; }
+    }
+    const int c0 = grp * U;                                  // first chunk of the group
+    const bool head = c0 == 0;
+    const bool tail = (c0 + U) * 64 + 64 > n;                // the group or its right neighbour pair reaches the row end
+    if (!head && !tail) fd_row_group<P, FUSED, HALO, U, false, false>(R, T, F, c0, lane);
+    else if (head && !tail) fd_row_group<P, FUSED, HALO, U, true, false>(R, T, F, c0, lane);
+    else if (!head) fd_row_group<P, FUSED, HALO, U, false, true>(R, T, F, c0, lane);
+    else fd_row_group<P, FUSED, HALO, U, true, true>(R, T, F, c0, lane);
 }
 
 // first / last nb planes along the axis -> [rows][nb]
@@ -429,7 +461,7 @@ static int launch_stream(const ng_plan* p, const double* in, double* out, const 
     if (p->inner > 1) {
         const i64 ncol = p->outer * (p->inner / 2);
         i64 nseg = (target + ncol - 1) / ncol;
-        const i64 max_seg = n / 32 > 0 ? n / 32 : 1;          // keep segments >= 32 rows (window refill <= 2P/32)
+        const i64 max_seg = n / 16 > 0 ? n / 16 : 1;          // keep segments >= 16 rows (window refill <= 2P/16, L2 hits)
         if (nseg > max_seg) nseg = max_seg;
         if (nseg < 1) nseg = 1;
         const int seg_len = (int)((n + nseg - 1) / nseg);
@@ -443,14 +475,18 @@ static int launch_stream(const ng_plan* p, const double* in, double* out, const 
         const int nchunk = (n + 63) / 64;
         const bool halo = lo || hi;
         // U consecutive chunks per warp (U x 512 B in flight); small problems keep U = 1 so that every SM gets CTAs
-        const bool deep = rows * nchunk >= 148LL * 8 * 4 * 4 && nchunk >= 4;
+        const bool deep = rows * nchunk >= 148LL * 8 * 4 * 4 && nchunk >= 3;
 #define NG_FD_ROW(FU, HA, UU)                                                                            \
     do {                                                                                                 \
         const int gpr = (nchunk + UU - 1) / UU;                                                          \
         fd_row_kernel<P, FU, HA, UU><<<(unsigned)((rows * gpr + 7) / 8), 256, 0, st>>>(                    \
             in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, lo, hi, gpr);                                \
     } while (0)
-#define NG_FD_ROW2(FU, HA) do { if (deep) NG_FD_ROW(FU, HA, 4); else NG_FD_ROW(FU, HA, 1); } while (0)
+        const char* ue = getenv("NG_FD_ROW_U");               // tuning: force the chunks per warp
+        // measured at 1024^3 / 8192^2 (profiles/r01_tune_fd.txt): U = 1 0.60 / 0.65, U = 2 0.63 / 0.76,
+        // U = 4 0.80 / 0.92, U = 8 0.69 / 0.58 of the HBM peak
+        const int uu = ue ? atoi(ue) : (!deep ? 1 : 4);
+#define NG_FD_ROW2(FU, HA) do { if (uu == 4) NG_FD_ROW(FU, HA, 4); else if (uu == 2) NG_FD_ROW(FU, HA, 2); else NG_FD_ROW(FU, HA, 1); } while (0)
         if (F.any) { if (halo) NG_FD_ROW2(true, true); else NG_FD_ROW2(true, false); }
         else       { if (halo) NG_FD_ROW2(false, true); else NG_FD_ROW2(false, false); }
 #undef NG_FD_ROW2
@@ -471,7 +507,12 @@ int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev&
         const bool off = se && atoi(se) == 0;
         const int P = off ? 0 : central_half_width(p->fd);
         const i64 contiguous = p->inner > 1 ? p->inner : p->n;
+        // tiny arrays are launch/latency-bound: the gather kernel's one-load-deep threads finish sooner
+        // than a march (NG_FD_STREAM_MIN: points from which the march kernel takes over)
+        const char* me = getenv("NG_FD_STREAM_MIN");
+        const i64 march_min = me ? atoll(me) : (1LL << 21);
         const bool ok = P > 0 && aligned && contiguous % 2 == 0 && p->n >= 2 * P + 1 && p->n < (1LL << 30) &&
+                        (p->inner == 1 || p->size >= march_min) &&
                         p->size > 0 && !(halo && p->inner > 1) &&
                         (!F.any || F.shape[F.vec_axis] % 2 == 0) &&
                         (!halo || ((((uintptr_t)lo | (uintptr_t)hi) & 7) == 0));
