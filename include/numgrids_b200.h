@@ -215,6 +215,18 @@ int64_t ng_quad_workspace_doubles(void);
 int ng_quad_apply(int ndim, const int64_t* shape, const double* const* d_w, const double* d_f,
                   double* d_work, double* d_out, void* stream);
 
+/* ---- multilinear interpolation (numgrids/interpol.py:34-46, :60-75 with method="linear"; ---------
+ * numgrids/grids.py:291-327 MultiGrid.transfer) --------------------------------------------------
+ * d_out[t] = interpolant of d_values (C order, src_shape) at target point t.  scattered = 0: the
+ * target is the tensor-product grid dst_shape and table a is indexed by the point's coordinate along
+ * axis a (Interpolator.__call__(Grid)); scattered = 1: dst_shape[0] points, every table indexed by the
+ * point number.  Tables per axis (host-built with the reference's NumPy expressions): d_idx = lower
+ * interval index i, d_y = (xq-x[i])/(x[i+1]-x[i]), d_omy = 1-y; for ndim == 1 (numpy.interp's form)
+ * d_y = xq-x[i] and d_omy = x[i+1]-x[i].  Arithmetic order per dimensionality: see csrc/interp.cu. */
+int ng_interp_linear(int ndim, const int64_t* src_shape, const int64_t* dst_shape, int scattered,
+                     const int32_t* const* d_idx, const double* const* d_y, const double* const* d_omy,
+                     const double* d_values, double* d_out, void* stream);
+
 /* ---- lifetime ---------------------------------------------------------------------------------*/
 int ng_plan_destroy(ng_plan* plan);
 /* bytes of device memory owned by the plan (tables + workspace + host-call staging) */

@@ -4,23 +4,25 @@ Drop-in for the reference's hot-path API: ``Grid``, ``CurvilinearGrid``, ``Spher
 ``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` / ``Axis``, ``Diff``, ``diff``,
 plus the step that follows a derivative apply in a PDE loop: ``BoundaryFace``, ``DirichletBC``,
 ``NeumannBC``, ``RobinBC``, ``apply_bcs`` (in place on device arrays) and
-``Integral`` / ``integrate`` (one streaming quadrature pass, N3).
+``Integral`` / ``integrate`` (one streaming quadrature pass, N3), ``Interpolator`` / ``MultiGrid.transfer``
+with ``method="linear"`` (N4).
 ``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` run hand-written CUDA kernels
 through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.
 
-Reference components outside the hot path (interpolation, AMR,
-I/O, plotting, MultiGrid -- SURVEY.md section 2) are intentionally not provided; accessing their
+Reference components outside the hot path (spline interpolation, AMR,
+I/O, plotting -- SURVEY.md section 2) are intentionally not provided; accessing their
 names raises ``NotImplementedError`` that says so.
 """
 __version__ = "0.1.0"
 
 from . import diff as _diff_module   # load the submodule first so that the `diff` helper below is
                                      # not shadowed when the operators import it lazily
-from .grids import Grid
+from .grids import Grid, MultiGrid
 from .curvilinear import CurvilinearGrid
 from .api import (Diff, AxisType, create_axis, SphericalGrid, CylindricalGrid, PolarGrid, diff,
                   CartesianLaplacian, cartesian_laplacian, integrate)
 from .integration import Integral
+from .interpol import Interpolator
 from .boundary import BoundaryFace, DirichletBC, NeumannBC, RobinBC, apply_bcs
 from ._lib import NumgridsB200Error
 
@@ -28,7 +30,7 @@ from ._lib import NumgridsB200Error
 Axis = create_axis
 
 _OUT_OF_SCOPE = {
-    "MultiGrid", "Interpolator", "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
+    "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
     "estimate_error", "interpolate",
 }
 

@@ -110,3 +110,40 @@ class Grid:
         axes = list(self.axes)
         axes[axis_index] = axes[axis_index].resized(max(2, round(len(axes[axis_index]) * factor)))
         return Grid(*axes)
+
+
+class MultiGrid:
+    """Hierarchy of grids of decreasing resolution on one domain (reference numgrids/grids.py:243-327).
+
+    ``levels[0]`` is the finest grid; every further level has about half the points per axis
+    (``n -> n // 2 + n % 2``) until an axis would drop below ``min_size``.
+    """
+
+    def __init__(self, *axes, min_size: int = 2) -> None:
+        grid = Grid(*axes)
+        self._levels = [grid]
+        while True:
+            sizes = np.array(grid.shape)
+            sizes = sizes // 2 + sizes % 2
+            if min(sizes) < min_size:
+                break
+            axes = [axis.resized(int(size)) for size, axis in zip(sizes, axes)]
+            grid = Grid(*axes)
+            self._levels.append(grid)
+
+    @property
+    def levels(self):
+        return self._levels
+
+    def transfer(self, f, level_from: int, level_to: int, method: str = "linear"):
+        """Coarsen or refine an array by one level (interpolation onto the neighbouring level's grid);
+        the array may live on the device and the result stays there."""
+        from .interpol import Interpolator
+        if tuple(f.shape) != self.levels[level_from].shape:
+            raise ValueError(
+                f"Array shape {tuple(f.shape)} does not match grid shape "
+                f"{self.levels[level_from].shape} at level {level_from}."
+            )
+        if abs(level_from - level_to) != 1:
+            raise ValueError("Can only transfer between adjacent levels.")
+        return Interpolator(self.levels[level_from], f, method=method)(self.levels[level_to])
