@@ -139,7 +139,7 @@ def test_validation_errors():
         ng.Diff(ng.Grid(EquidistantAxis(5, 0, 1)), 2, 0)      # too short for the 6-tap one-sided scheme
     assert ng.Axis is ng.create_axis
     with pytest.raises(NotImplementedError):
-        ng.MultiGrid
+        ng.save_grid
 
 
 def test_grid_surface_is_lazy_and_compatible():
