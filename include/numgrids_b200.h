@@ -215,6 +215,13 @@ int64_t ng_quad_workspace_doubles(void);
 int ng_quad_apply(int ndim, const int64_t* shape, const double* const* d_w, const double* d_f,
                   double* d_work, double* d_out, void* stream);
 
+/* ---- norm of a difference (numgrids/amr.py:96-103, ErrorEstimator._compute_norm) ----------------
+ * out[0] = max|a-b| (NG_NORM_MAX), sqrt(mean((a-b)^2)) (NG_NORM_L2) or mean|a-b| (NG_NORM_MEAN) of two
+ * device arrays of n doubles, one pass.  d_work: >= ng_quad_workspace_doubles() doubles of scratch. */
+enum ng_norm_kind { NG_NORM_MAX = 0, NG_NORM_L2 = 1, NG_NORM_MEAN = 2 };
+int ng_diff_norm(int64_t n, const double* d_a, const double* d_b, int kind, double* d_work,
+                 double* d_out, void* stream);
+
 /* ---- multilinear interpolation (numgrids/interpol.py:34-46, :60-75 with method="linear"; ---------
  * numgrids/grids.py:291-327 MultiGrid.transfer) --------------------------------------------------
  * d_out[t] = interpolant of d_values (C order, src_shape) at target point t.  scattered = 0: the

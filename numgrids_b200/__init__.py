@@ -5,11 +5,11 @@ Drop-in for the reference's hot-path API: ``Grid``, ``CurvilinearGrid``, ``Spher
 plus the step that follows a derivative apply in a PDE loop: ``BoundaryFace``, ``DirichletBC``,
 ``NeumannBC``, ``RobinBC``, ``apply_bcs`` (in place on device arrays) and
 ``Integral`` / ``integrate`` (one streaming quadrature pass, N3), ``Interpolator`` / ``MultiGrid.transfer``
-with ``method="linear"`` (N4).
+with ``method="linear"`` and the ``adapt`` / ``estimate_error`` refinement loop built on them (N4).
 ``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` run hand-written CUDA kernels
 through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.
 
-Reference components outside the hot path (spline interpolation, AMR,
+Reference components outside the hot path (spline interpolation,
 I/O, plotting -- SURVEY.md section 2) are intentionally not provided; accessing their
 names raises ``NotImplementedError`` that says so.
 """
@@ -23,6 +23,7 @@ from .api import (Diff, AxisType, create_axis, SphericalGrid, CylindricalGrid, P
                   CartesianLaplacian, cartesian_laplacian, integrate)
 from .integration import Integral
 from .interpol import Interpolator
+from .amr import ErrorEstimator, AdaptationResult, adapt, estimate_error
 from .boundary import BoundaryFace, DirichletBC, NeumannBC, RobinBC, apply_bcs
 from ._lib import NumgridsB200Error
 
@@ -30,8 +31,7 @@ from ._lib import NumgridsB200Error
 Axis = create_axis
 
 _OUT_OF_SCOPE = {
-    "save_grid", "load_grid", "ErrorEstimator", "AdaptationResult", "adapt",
-    "estimate_error", "interpolate",
+    "save_grid", "load_grid", "interpolate",
 }
 
 

@@ -140,3 +140,109 @@ extern "C" int ng_quad_apply(int ndim, const int64_t* shape, const double* const
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Norm of the difference of two arrays in one pass (16 B/point): the scalar the reference's
+// ErrorEstimator._compute_norm takes of `f_current - f_interpolated` (numgrids/amr.py:96-103):
+//   kind 0  max(|a - b|)          kind 1  sqrt(mean((a - b)**2))          kind 2  mean(|a - b|)
+// The difference and the square are rounded like NumPy's (one DADD, one DMUL); the sums use the same
+// fixed-order two-stage reduction as the quadrature above (max is exact, the sums agree with NumPy's
+// pairwise summation to rounding).
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+template <int KIND>
+__device__ __forceinline__ double norm_term(double a, double b) {
+    const double d = __dsub_rn(a, b);
+    return KIND == 1 ? __dmul_rn(d, d) : fabs(d);
+}
+template <int KIND>
+__device__ __forceinline__ double norm_join(double x, double y) {
+    if (KIND == 0) return (x > y || isnan(x)) ? x : y;       // np.max propagates NaN
+    return x + y;
+}
+
+template <int KIND, bool VEC2>
+__global__ void __launch_bounds__(QUAD_THREADS)
+diff_norm_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, i64 n,
+                         double* __restrict__ partials) {
+    const i64 stride = (i64)gridDim.x * QUAD_THREADS;
+    double acc = 0.0;
+    if (VEC2) {
+        const i64 n2 = n >> 1;
+        for (i64 i = (i64)blockIdx.x * QUAD_THREADS + threadIdx.x; i < n2; i += stride) {
+            const double2 x = __ldg(reinterpret_cast<const double2*>(a) + i);
+            const double2 y = __ldg(reinterpret_cast<const double2*>(b) + i);
+            acc = norm_join<KIND>(acc, norm_term<KIND>(x.x, y.x));
+            acc = norm_join<KIND>(acc, norm_term<KIND>(x.y, y.y));
+        }
+    } else {
+        for (i64 i = (i64)blockIdx.x * QUAD_THREADS + threadIdx.x; i < n; i += stride)
+            acc = norm_join<KIND>(acc, norm_term<KIND>(__ldg(a + i), __ldg(b + i)));
+    }
+    __shared__ double sm[QUAD_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = norm_join<KIND>(acc, __shfl_down_sync(0xffffffffu, acc, o));
+    if (lane == 0) sm[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = sm[0];
+#pragma unroll
+        for (int k = 1; k < QUAD_THREADS / 32; ++k) s = norm_join<KIND>(s, sm[k]);
+        partials[blockIdx.x] = s;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(1024) diff_norm_final_kernel(const double* __restrict__ partials, int np,
+                                                               i64 n, double* __restrict__ out) {
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v = 0.0;
+    for (int k = threadIdx.x; k < np; k += 1024) v = norm_join<KIND>(v, partials[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = norm_join<KIND>(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = sm[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = norm_join<KIND>(v, __shfl_down_sync(0xffffffffu, v, o));
+        if (lane == 0) {
+            if (KIND == 1) v = sqrt(__ddiv_rn(v, (double)n));
+            if (KIND == 2) v = __ddiv_rn(v, (double)n);
+            out[0] = v;
+        }
+    }
+}
+
+template <int KIND>
+int diff_norm_launch(const double* a, const double* b, i64 n, double* work, double* out, cudaStream_t st) {
+    i64 ctas = (n / 2 + QUAD_THREADS - 1) / QUAD_THREADS;
+    if (ctas > QUAD_MAX_CTAS) ctas = QUAD_MAX_CTAS;
+    if (ctas < 1) ctas = 1;
+    const bool vec2 = n % 2 == 0 && ((((uintptr_t)a) | ((uintptr_t)b)) % 16) == 0;
+    if (vec2) diff_norm_partial_kernel<KIND, true><<<(unsigned)ctas, QUAD_THREADS, 0, st>>>(a, b, n, work);
+    else diff_norm_partial_kernel<KIND, false><<<(unsigned)ctas, QUAD_THREADS, 0, st>>>(a, b, n, work);
+    NG_LAUNCH_CHECK();
+    diff_norm_final_kernel<KIND><<<1, 1024, 0, st>>>(work, (int)ctas, n, out);
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+}  // namespace
+
+extern "C" int ng_diff_norm(int64_t n, const double* d_a, const double* d_b, int kind, double* d_work,
+                            double* d_out, void* stream) {
+    NG_REQUIRE(n >= 1, "ng_diff_norm: empty arrays");
+    NG_REQUIRE(d_a && d_b && d_work && d_out, "ng_diff_norm: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kind) {
+        case NG_NORM_MAX: return diff_norm_launch<0>(d_a, d_b, n, d_work, d_out, st);
+        case NG_NORM_L2: return diff_norm_launch<1>(d_a, d_b, n, d_work, d_out, st);
+        case NG_NORM_MEAN: return diff_norm_launch<2>(d_a, d_b, n, d_work, d_out, st);
+    }
+    ng_set_error("ng_diff_norm: unknown norm kind %d", kind);
+    return NG_EINVAL;
+}

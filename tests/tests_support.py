@@ -55,3 +55,14 @@ def build_curv_grid(ng, name, axes):
     if name == "polar":
         return ng.PolarGrid(*axes)
     return ng.CurvilinearGrid(*axes, scale_factors=scale_factor_fns(name))
+
+
+def amr_field(name, mesh):
+    """Analytic fields of the adaptive-refinement golden cases (tests/golden/make_golden_amr.py)."""
+    if name == "poly5":
+        return mesh[0] ** 5
+    if name == "aniso":                       # needs far more resolution along axis 0 than along axis 1
+        return np.sin(9.0 * mesh[0]) * np.exp(-mesh[0]) + mesh[1] ** 2
+    if name == "wave3":
+        return np.sin(4.0 * mesh[0]) * np.log(mesh[1]) + np.cos(3.0 * mesh[2]) * mesh[0]
+    raise KeyError(name)
