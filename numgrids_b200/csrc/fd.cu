@@ -511,7 +511,8 @@ int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev&
         // than a march (NG_FD_STREAM_MIN: points from which the march kernel takes over)
         const char* me = getenv("NG_FD_STREAM_MIN");
         const i64 march_min = me ? atoll(me) : (1LL << 21);
-        const bool ok = P > 0 && aligned && contiguous % 2 == 0 && p->n >= 2 * P + 1 && p->n < (1LL << 30) &&
+        const bool ok = P > 0 && aligned && contiguous % 2 == 0 && p->n >= 2 * P + 1 && p->n >= p->fd.n_side &&
+                        p->n < (1LL << 30) &&
                         (p->inner == 1 || p->size >= march_min) &&
                         p->size > 0 && !(halo && p->inner > 1) &&
                         (!F.any || F.shape[F.vec_axis] % 2 == 0) &&
