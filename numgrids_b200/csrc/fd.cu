@@ -245,7 +245,7 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
 // chunk edges.  Slab halos (HALO) enter as the positions -P..-1 and n..n+P-1 of the row; the one-sided
 // schemes overwrite the central result on the (at most P) boundary positions of a row end.
 // Per-warp context of the row kernel and the body for one group of U chunks.  HEAD / TAIL say whether
-// the group touches the low / high end of its row: only then can a position fall outside [0, n) (slab
+// (and for TAIL, how) the group touches the low / high end of its row: only then can a position fall outside [0, n) (slab
 // halo or nothing there), a chunk be partial, or a one-sided scheme apply; interior groups run without
 // any of those tests.
 template <int P, bool FUSED, bool HALO>
@@ -282,7 +282,7 @@ struct RowCtx {
     }
 };
 
-template <int P, bool FUSED, bool HALO, int U, bool HEAD, bool TAIL>
+template <int P, bool FUSED, bool HALO, int U, bool HEAD, int TAIL>
 __device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, const FdTables& T,
                                              const FuseDev& F, int c0, int lane) {
     constexpr int H = (P + 1) / 2;                           // neighbour lanes needed on each side
@@ -291,17 +291,17 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, co
     const int p0 = c0 * 64 + 2 * lane;                       // this lane's pair in the group's first chunk
     double2 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = R.template pair_at<TAIL>(F, p0 + 64 * u);
+    for (int u = 0; u < U; ++u) v[u] = R.template pair_at<TAIL == 2>(F, p0 + 64 * u);
     // virtual previous / next chunk: only the lanes next to the group are ever read
     double2 pcl = make_double2(0.0, 0.0), ncr = make_double2(0.0, 0.0);
     if (lane >= 32 - H) pcl = R.template pair_at<HEAD>(F, p0 - 64);
-    if (lane < H) ncr = R.template pair_at<TAIL>(F, p0 + 64 * U);
-    const bool one_lo = HEAD && !(HALO && R.lo_row), one_hi = TAIL && !(HALO && R.hi_row);
+    if (lane < H) ncr = R.template pair_at<TAIL != 0>(F, p0 + 64 * U);
+    const bool one_lo = HEAD && !(HALO && R.lo_row), one_hi = TAIL != 0 && !(HALO && R.hi_row);
 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int pos = p0 + 64 * u;
-        if (TAIL && (c0 + u) * 64 >= n) break;               // warp-uniform: chunk past the row end
+        if (TAIL == 2 && (c0 + u) * 64 >= n) break;          // warp-uniform: chunk past the row end
         const double2 prev = u == 0 ? pcl : v[u > 0 ? u - 1 : 0];
         const double2 next = u == U - 1 ? ncr : v[u < U - 1 ? u + 1 : 0];
         double win[4 * H + 2];                               // positions pos-2H .. pos+2H+1 of the row
@@ -323,13 +323,14 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, co
             ay = __dadd_rn(ay, __dmul_rn(T.wc[kk], win[C + 1 - P + kk]));
         }
         // one-sided schemes on the global boundary: only the first / last chunk of a row can hold them
-        if ((one_lo && c0 + u == 0) || (one_hi && (c0 + u) * 64 + 64 + P > n)) {
+        // (TAIL == 1: the group ends exactly at the row end, so only its last chunk; HEAD: only its first)
+        if ((one_lo && u == 0) || (one_hi && (TAIL == 1 ? u == U - 1 : (c0 + u) * 64 + 64 + P > n))) {
             auto one_sided = [&](int q, const double* w, const int* off) -> double {
                 double a = 0.0;
                 for (int k = 0; k < T.n_side; ++k) a = __dadd_rn(a, __dmul_rn(w[k], R.value_at(F, q + off[k])));
                 return a;
             };
-            if (pos < n) {
+            if (TAIL != 2 || pos < n) {
                 if (one_lo && pos < P) {
                     ax = one_sided(pos, T.wf, T.of);
                     if (pos + 1 < P) ay = one_sided(pos + 1, T.wf, T.of);
@@ -340,7 +341,7 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, co
                 }
             }
         }
-        if (!TAIL || pos < n) {
+        if (TAIL != 2 || pos < n) {
             double2 r;
             r.x = __dmul_rn(ax, T.inv_h_pow);
             r.y = __dmul_rn(ay, T.inv_h_pow);
@@ -394,11 +395,18 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
     }
     const int c0 = grp * U;                                  // first chunk of the group
     const bool head = c0 == 0;
-    const bool tail = (c0 + U) * 64 + 64 > n;                // the group or its right neighbour pair reaches the row end
-    if (!head && !tail) fd_row_group<P, FUSED, HALO, U, false, false>(R, T, F, c0, lane);
-    else if (head && !tail) fd_row_group<P, FUSED, HALO, U, true, false>(R, T, F, c0, lane);
-    else if (!head) fd_row_group<P, FUSED, HALO, U, false, true>(R, T, F, c0, lane);
-    else fd_row_group<P, FUSED, HALO, U, true, true>(R, T, F, c0, lane);
+    // 0: the group and its right neighbour pair are inside the row; 1: the group ends exactly at the row
+    // end (only the neighbour pair is outside); 2: ragged (partial or missing chunks)
+    const int tail = (c0 + U) * 64 + 64 <= n ? 0 : ((c0 + U) * 64 == n ? 1 : 2);
+    if (!head) {
+        if (tail == 0) fd_row_group<P, FUSED, HALO, U, false, 0>(R, T, F, c0, lane);
+        else if (tail == 1) fd_row_group<P, FUSED, HALO, U, false, 1>(R, T, F, c0, lane);
+        else fd_row_group<P, FUSED, HALO, U, false, 2>(R, T, F, c0, lane);
+    } else {
+        if (tail == 0) fd_row_group<P, FUSED, HALO, U, true, 0>(R, T, F, c0, lane);
+        else if (tail == 1) fd_row_group<P, FUSED, HALO, U, true, 1>(R, T, F, c0, lane);
+        else fd_row_group<P, FUSED, HALO, U, true, 2>(R, T, F, c0, lane);
+    }
 }
 
 // first / last nb planes along the axis -> [rows][nb]
@@ -486,7 +494,7 @@ static int launch_stream(const ng_plan* p, const double* in, double* out, const 
         // measured at 1024^3 / 8192^2 (profiles/r01_tune_fd.txt): U = 1 0.60 / 0.65, U = 2 0.63 / 0.76,
         // U = 4 0.80 / 0.92, U = 8 0.69 / 0.58 of the HBM peak
         const int uu = ue ? atoi(ue) : (!deep ? 1 : 4);
-#define NG_FD_ROW2(FU, HA) do { if (uu == 4) NG_FD_ROW(FU, HA, 4); else if (uu == 2) NG_FD_ROW(FU, HA, 2); else NG_FD_ROW(FU, HA, 1); } while (0)
+#define NG_FD_ROW2(FU, HA) do { if (uu >= 4) NG_FD_ROW(FU, HA, 4); else NG_FD_ROW(FU, HA, 1); } while (0)
         if (F.any) { if (halo) NG_FD_ROW2(true, true); else NG_FD_ROW2(true, false); }
         else       { if (halo) NG_FD_ROW2(false, true); else NG_FD_ROW2(false, false); }
 #undef NG_FD_ROW2
