@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libnumgrids_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "fd.cu", "dense.cu", "fft.cu", "fft2.cu", "fdlap.cu", "fdlap3d.cu", "curv.cu", "transpose.cu", "bc.cu", "quad.cu", "interp.cu"]
+SOURCES = ["api.cu", "fd.cu", "fd_row.cu", "dense.cu", "fft.cu", "fft2.cu", "fdlap.cu", "fdlap3d.cu", "curv.cu", "transpose.cu", "bc.cu", "quad.cu", "interp.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -130,6 +130,9 @@ struct ng_plan {
 // per-kind entry points implemented in the other translation units
 int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                  const double* lo, const double* hi, cudaStream_t st);
+// contiguous-axis streaming kernel (fd_row.cu); P = half width of the central stencil (1..4)
+int ng_fd_row_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                     const double* lo, const double* hi, cudaStream_t st);
 int ng_dense_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                     cudaStream_t st);
 int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
