@@ -140,6 +140,34 @@ def test_linearity_and_constants_full_size(gpu_ready):
     assert float(d(const).abs().max()) < 1e-9
 
 
+def test_cfg5_full_size_identities(gpu_ready, monkeypatch):
+    """BASELINE size (1024^3 points): the fused Laplacian equals the reference idiom
+    Diff(g,2,0)(f)+Diff(g,2,1)(f)+Diff(g,2,2)(f) bit for bit, and every per-axis streaming kernel
+    equals the gather kernel (itself pinned to the oracle at small sizes) bit for bit."""
+    import torch
+    n = 1024
+    ax = ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0)
+    g = ng.Grid(ax, ax, ax)
+    x = torch.linspace(0.0, 1.0, n, dtype=torch.float64, device="cuda")
+    f = (torch.sin(2 * np.pi * x)[:, None, None] * torch.cos(2 * np.pi * x)[None, :, None]
+         * torch.exp(x)[None, None, :]).contiguous()
+    idiom = ng.Diff(g, 2, 0)(f)
+    idiom += ng.Diff(g, 2, 1)(f)
+    idiom += ng.Diff(g, 2, 2)(f)
+    lap = ng.CartesianLaplacian(g)(f)
+    assert torch.equal(lap, idiom)
+    del lap, idiom
+    for order, axis in ((1, 0), (2, 1), (1, 2), (2, 2)):
+        op = ng.Diff(g, order, axis)
+        monkeypatch.setenv("NG_FD_STREAM", "1")
+        fast = op(f)
+        monkeypatch.setenv("NG_FD_STREAM", "0")
+        slow = op(f)
+        monkeypatch.delenv("NG_FD_STREAM")
+        assert torch.equal(fast.view(torch.int64), slow.view(torch.int64)), (order, axis)
+        del fast, slow
+
+
 def test_host_pipeline_chunked_paths(gpu_ready):
     """Arrays >= 64 MiB go through the chunked H2D / compute / D2H pipeline of the *_host entry
     points; results must equal the device-resident path bit for bit."""
