@@ -1,2 +1,7 @@
-timeout 600 python -m pytest tests/test_gpu_configs.py -x -q -m gpu -k "full_size" > gpurun_out/pytest_full.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_full.log
-tail -5 gpurun_out/pytest_full.log
+V=numgrids_b200/lib/variants
+L=gpurun_out/fft_tail_variants.log
+: > $L
+for v in ffttb1 ffttb2 default ffttb8; do
+  if [ $v = default ]; then python tools/time_cfg4_variants.py >> $L 2>&1; else NUMGRIDS_B200_LIB=$PWD/$V/libng_$v.so python tools/time_cfg4_variants.py >> $L 2>&1; fi
+done
+cut -c1-120 $L
