@@ -332,6 +332,24 @@ def per_config_extras(torch, ng, peak_gbs, quick):
         out["fd_diff"] = {"error": repr(e)}
 
     try:
+        # cfg5 in the reference's second idiom: CurvilinearGrid(..., scale_factors = ones).laplacian(f)
+        # = sum_i D_i(D_i f) with first-derivative stencils: six streaming FD applies with fused elementwise
+        # work (no fused single-pass kernel for this form), at 512^3 because the reference API evaluates the
+        # scale factors on the full meshgrid (24 GiB of host arrays at 1024^3)
+        nii = 128 if quick else 512
+        ax = ng.create_axis(A.EQUIDISTANT, nii, 0.0, 1.0)
+        one = lambda c: np.ones_like(c[0])
+        gc = ng.CurvilinearGrid(ax, ax, ax, scale_factors=(one, one, one))
+        f = torch.rand(nii, nii, nii, dtype=torch.float64, device=dev)
+        ms = timed(lambda: gc.laplacian(f), 5, 2, nii < 512)
+        out[f"cfg5_idiom_ii_unit_curvilinear_laplacian_{nii}cubed"] = {
+            "gpts": nii ** 3 / ms / 1e6, "ms": ms, "passes": 6,
+            "hbm_frac_algorithmic_16B": 16 * nii ** 3 / ms / 1e6 / peak_gbs}
+        del f, gc
+    except Exception as e:  # pragma: no cover
+        out["cfg5_idiom_ii"] = {"error": repr(e)}
+
+    try:
         # cfg2: Diff(g, 2, 0) on Chebyshev 256^3 -- FP64-pipe-bound ordered DGEMM (2*256 instr/pt)
         n = 128 if quick else 256
         ax = ng.create_axis(A.CHEBYSHEV, n, 0.0, 1.0)
