@@ -185,6 +185,20 @@ __device__ __forceinline__ double fuse_tail_off(const FuseDev& F, double d, i64 
     return d;
 }
 
+// fuse_tail_off with the full-shape operands (minuend / addend) already fetched: kernels that stream
+// fetch them together with the input, ahead of the arithmetic (they may alias `out`, so the compiler
+// cannot move those loads over earlier stores itself).  Same steps and order.
+__device__ __forceinline__ double fuse_tail_vals(const FuseDev& F, double d, double m, double a, i64 post_off,
+                                                 i64 div_off) {
+    if (F.minuend) d = __dsub_rn(m, d);
+    if (F.post.ptr) d = __dmul_rn(F.post.ptr[post_off], d);
+    if (F.addend) d = __dadd_rn(a, d);
+    else if (F.add_zero) d = __dadd_rn(0.0, d);
+    if (F.div.ptr) d = __ddiv_rn(d, F.div.ptr[div_off]);
+    if (F.finite) d = isfinite(d) ? d : 0.0;
+    return d;
+}
+
 // inf / nan test on the integer pipe (isfinite() would spend FP64-pipe slots in FP64-bound kernels)
 __device__ __forceinline__ bool ng_nonfinite(double v) {
     return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000;

@@ -139,7 +139,7 @@ __device__ __forceinline__ double2 ldg128(const double* p) {
 #define NG_FD_MINB 1
 #endif
 template <int P, bool FUSED>
-__global__ void __launch_bounds__(256, NG_FD_MINB)
+__global__ void __launch_bounds__(256, FUSED ? 2 : NG_FD_MINB)
 fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 outer, int n, i64 inner,
                 int axis, FdTables T, const double* __restrict__ xdiv, FuseDev F, int seg_len, int nseg) {
     constexpr int W = 2 * P + 1;
@@ -170,15 +170,22 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
         }
         return v;
     };
-    auto finish = [&](int i, double ax, double ay) {
+    // full-shape tail operands of row i (plain loads: they may alias `out`); the launch checks alignment
+    const double2 zero2 = make_double2(0.0, 0.0);
+    auto fetch_m = [&](int i) -> double2 {
+        return (FUSED && F.minuend) ? *reinterpret_cast<const double2*>(F.minuend + base + (i64)i * inner) : zero2;
+    };
+    auto fetch_a = [&](int i) -> double2 {
+        return (FUSED && F.addend) ? *reinterpret_cast<const double2*>(F.addend + base + (i64)i * inner) : zero2;
+    };
+    auto finish = [&](int i, double ax, double ay, const double2& m, const double2& a) {
         double2 r;
         r.x = __dmul_rn(ax, T.inv_h_pow);
         r.y = __dmul_rn(ay, T.inv_h_pow);
         if (xdiv) { const double xd = xdiv[i]; r.x = __ddiv_rn(r.x, xd); r.y = __ddiv_rn(r.y, xd); }
-        const i64 lin = base + (i64)i * inner;
         if (FUSED) {
-            r.x = fuse_tail_off(F, r.x, lin, post0 + i * post_a, div0 + i * div_a);
-            r.y = fuse_tail_off(F, r.y, lin + 1, post0 + i * post_a + post_v, div0 + i * div_a + div_v);
+            r.x = fuse_tail_vals(F, r.x, m.x, a.x, post0 + i * post_a, div0 + i * div_a);
+            r.y = fuse_tail_vals(F, r.y, m.y, a.y, post0 + i * post_a + post_v, div0 + i * div_a + div_v);
         }
         *reinterpret_cast<double2*>(dst + (i64)i * inner) = r;
     };
@@ -189,7 +196,7 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
             ax = __dadd_rn(ax, __dmul_rn(w[k], v.x));
             ay = __dadd_rn(ay, __dmul_rn(w[k], v.y));
         }
-        finish(i, ax, ay);
+        finish(i, ax, ay, fetch_m(i), fetch_a(i));
     };
     for (int i = i0; i < min(P, i1); ++i) one_sided(i, T.wf, T.of);
     for (int i = max(i0, n - P); i < i1; ++i) one_sided(i, T.wb, T.ob);
@@ -203,9 +210,13 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
     for (int u = 0; u < W - 1; ++u) old[u] = ld(ia - P + u);
     int i = ia;
     for (; i + W <= ib; i += W) {
-        double2 nw[W];                                       // f[i+P .. i+P+W-1]
+        double2 nw[W], tm[W], ta[W];                         // f[i+P .. i+P+W-1]; tail operands of rows i .. i+W-1
 #pragma unroll
         for (int u = 0; u < W; ++u) nw[u] = ld(i + P + u);
+        if (FUSED) {
+#pragma unroll
+            for (int u = 0; u < W; ++u) { tm[u] = fetch_m(i + u); ta[u] = fetch_a(i + u); }
+        }
 #pragma unroll
         for (int u = 0; u < W; ++u) {
             double ax = 0.0, ay = 0.0;
@@ -215,7 +226,7 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
                 ax = __dadd_rn(ax, __dmul_rn(T.wc[k], x.x));
                 ay = __dadd_rn(ay, __dmul_rn(T.wc[k], x.y));
             }
-            finish(i + u, ax, ay);
+            finish(i + u, ax, ay, tm[u], ta[u]);
         }
 #pragma unroll
         for (int u = 0; u < W - 1; ++u) old[u] = nw[u + 1];
@@ -230,7 +241,7 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
         }
         ax = __dadd_rn(ax, __dmul_rn(T.wc[W - 1], v.x));
         ay = __dadd_rn(ay, __dmul_rn(T.wc[W - 1], v.y));
-        finish(i, ax, ay);
+        finish(i, ax, ay, fetch_m(i), fetch_a(i));
 #pragma unroll
         for (int u = 0; u < W - 2; ++u) old[u] = old[u + 1];
         old[W - 2] = v;
@@ -333,7 +344,8 @@ int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev&
                         (p->inner == 1 || p->size >= march_min) &&
                         p->size > 0 && !(halo && p->inner > 1) &&
                         (!F.any || F.shape[F.vec_axis] % 2 == 0) &&
-                        (!halo || ((((uintptr_t)lo | (uintptr_t)hi) & 7) == 0));
+                        (!halo || ((((uintptr_t)lo | (uintptr_t)hi) & 7) == 0)) &&
+                        ((((uintptr_t)F.minuend | (uintptr_t)F.addend) & 15) == 0);   // fetched as aligned pairs
         if (ok) {
             switch (P) {
                 case 1: return launch_stream<1>(p, in, out, F, lo, hi, st);

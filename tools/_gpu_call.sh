@@ -1,7 +1,3 @@
-V=numgrids_b200/lib/variants
-L=gpurun_out/fft_tail_variants.log
-: > $L
-for v in ffttb1 ffttb2 default ffttb8; do
-  if [ $v = default ]; then python tools/time_cfg4_variants.py >> $L 2>&1; else NUMGRIDS_B200_LIB=$PWD/$V/libng_$v.so python tools/time_cfg4_variants.py >> $L 2>&1; fi
-done
-cut -c1-120 $L
+timeout 300 python tools/check_fd_stream.py 400 10 2>&1 | tail -3
+python tools/time_fd_fused.py 512 > gpurun_out/time_fd_fused2.log 2>&1
+cat gpurun_out/time_fd_fused2.log
