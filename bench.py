@@ -137,7 +137,7 @@ def time_cpu_oracle(shape, repeats: int, threaded: bool = True):
     if threaded:
         from oracle import pencil_c
         fn = lambda a: pencil_c.cartesian_laplacian3(a, hs, 4)
-        cores = pencil_c.threads()
+        cores = pencil_c.use_all_cores()
     else:
         fn = lambda a: pencil.cartesian_laplacian(a, hs, 4)
         cores = 1

@@ -89,6 +89,16 @@ void po_fdlap3(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2
         }
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU arm asks for the host's cores explicitly */
+void po_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int po_max_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

@@ -35,6 +35,16 @@ def threads() -> int:
     return int(lib().po_max_threads())
 
 
+def use_all_cores() -> int:
+    """Ask OpenMP for every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().po_set_threads(n)
+    return threads()
+
+
 def _tables(h, order, acc):
     c = coefficients(order, acc)
     keep = []
