@@ -102,17 +102,19 @@ __device__ __forceinline__ void dit_inverse(double2* x) {
 // time by this warp-cooperative radix-2 routine (rare, slow): a pencil with a non-finite sample
 // comes out all-NaN (what numpy.fft makes of it), a clean one gets its derivative.
 template <bool FUSED>
-__device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, double* __restrict__ out, i64 p,
-                                             int N, int log2n, double2* S, const double2* __restrict__ Wn,
-                                             const double2* __restrict__ tw, const FuseDev& F) {
+__device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, double* __restrict__ out, i64 base,
+                                             i64 step, int ax, int N, int log2n, double2* S,
+                                             const double2* __restrict__ Wn, const double2* __restrict__ tw,
+                                             const FuseDev& F) {
+    // sample k of the pencil sits at base + k*step and has coordinate k along grid axis `ax`
     const int lane = threadIdx.x & 31;
     Idx4 ix;
-    if (FUSED) ix = unravel4(p * N, F.shape);
+    if (FUSED) ix = unravel4(base, F.shape);
     bool bad = false;
     for (int k = lane; k < N; k += 32) {
-        double v = in[p * N + k];
+        double v = in[base + k * step];
         if (FUSED && F.pre.ptr) {
-            ix.i[F.vec_axis] = k;
+            ix.i[ax] = k;
             v = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], v);
         }
         if (ng_nonfinite(v)) { bad = true; v = 0.0; }
@@ -154,10 +156,10 @@ __device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, doub
     for (int k = lane; k < N; k += 32) {
         double d = bad ? ng_nan() : S[k].x;
         if (FUSED) {
-            ix.i[F.vec_axis] = k;
-            d = fuse_tail(F, d, p * N + k, ix);
+            ix.i[ax] = k;
+            d = fuse_tail(F, d, base + k * step, ix);
         }
-        out[p * N + k] = d;
+        out[base + k * step] = d;
     }
     __syncwarp();
 }
@@ -183,38 +185,47 @@ struct PencilCoef {
 struct PencilTail {
     PencilCoef post, div;
     const double *minuend, *addend;
-    __device__ __forceinline__ void init(const FuseDev& F, i64 lin0, int t, int R2) {
+    i64 mstep;            // elements between this lane's consecutive samples in the full-shape operands
+    // the pencil's sample k sits at lin0 + k*step and has coordinate k along grid axis `ax`
+    // (contiguous pencils: step 1, ax = the innermost axis)
+    __device__ __forceinline__ void init(const FuseDev& F, i64 lin0, i64 step, int ax, int t, int R2) {
         Idx4 ix = unravel4(lin0, F.shape);
-        ix.i[F.vec_axis] = 0;
-        post.init(F.post, ix, F.vec_axis, t, R2);
-        div.init(F.div, ix, F.vec_axis, t, R2);
-        minuend = F.minuend ? F.minuend + lin0 + t : nullptr;
-        addend = F.addend ? F.addend + lin0 + t : nullptr;
+        ix.i[ax] = 0;
+        post.init(F.post, ix, ax, t, R2);
+        div.init(F.div, ix, ax, t, R2);
+        minuend = F.minuend ? F.minuend + lin0 + t * step : nullptr;
+        addend = F.addend ? F.addend + lin0 + t * step : nullptr;
+        mstep = step * R2;
     }
-    // same steps and order as fuse_tail (common.cuh); sample r of this lane sits at offset r*R2
+    // same steps and order as fuse_tail (common.cuh); sample r of this lane sits at offset r*mstep
     __device__ __forceinline__ double apply(const FuseDev& F, double d, int r, int R2) const {
-        if (minuend) d = __dsub_rn(minuend[r * R2], d);
+        if (minuend) d = __dsub_rn(minuend[r * mstep], d);
         if (post.p) d = __dmul_rn(post.at(r), d);
-        if (addend) d = __dadd_rn(addend[r * R2], d);
+        if (addend) d = __dadd_rn(addend[r * mstep], d);
         else if (F.add_zero) d = __dadd_rn(0.0, d);
         if (div.p) d = __ddiv_rn(d, div.at(r));
         if (F.finite) d = ng_nonfinite(d) ? 0.0 : d;
         return d;
     }
 };
-__device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0, int t, int R2) {
+__device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0, int ax, int t, int R2) {
     PencilCoef c;
     Idx4 ix = unravel4(lin0, F.shape);
-    ix.i[F.vec_axis] = 0;
-    c.init(F.pre, ix, F.vec_axis, t, R2);
+    ix.i[ax] = 0;
+    c.init(F.pre, ix, ax, t, R2);
     return c;
 }
 
 // RT samples per lane in pass 1, R2 = n / RT = lanes per transform, G = RT / R2 sub-transforms per lane
-template <int RT, int R2, bool FUSED, int MINB>
+// STR: the transform axis is not the contiguous one -- pencil p = o*inner + c of the [outer][n][inner] view
+// starts at o*n*inner + c and its samples are `inner` elements apart.  The pair (2*pair, 2*pair+1) and the
+// 2*TPW*8 pencils of a CTA are adjacent columns, so the 8-byte accesses of the lanes fall into sectors /
+// lines that the neighbouring thread groups and warps of the CTA touch at the same time (L1 / L2 reuse).
+template <int RT, int R2, bool FUSED, int MINB, bool STR>
 __global__ void __launch_bounds__(256, MINB)
 fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
-                const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil,
+                const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, i64 inner, int axis,
+                int pair16,   // STR: the two pencils of a pair are one aligned 16-byte element of every row
                      const __grid_constant__ FuseDev F) {   // (address taken for the rare slow path: no local copy)
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
     constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
@@ -226,6 +237,15 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     const i64 pa = 2 * pair, pb = pa + 1;
     const bool va = pa < npencil, vb = pb < npencil;
     double2* S = fsm + (size_t)(warp * TPW + tr) * UNITS;
+    // element k of pencil a / b: in[ba + k*step]; coordinate k along grid axis `ax`
+    const i64 step = STR ? inner : 1;
+    const int ax = STR ? axis : F.vec_axis;
+    auto pencil_base = [&](i64 p) -> i64 {
+        if (!STR) return p * N;
+        const i64 o = p / inner;
+        return o * N * inner + (p - o * inner);
+    };
+    const i64 ba = va ? pencil_base(pa) : 0, bb = vb ? pencil_base(pb) : 0;
 
     // multi-index of sample 0 of each pencil (one unravel per pencil; the FFT axis is the innermost
     // non-unit axis, so sample idx only changes that coordinate)
@@ -234,13 +254,17 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     {
         PencilCoef ca, cb;
         const bool pre = FUSED && F.pre.ptr;
-        if (pre) { ca = pencil_pre(F, va ? pa * N : 0, t, R2); cb = pencil_pre(F, vb ? pb * N : 0, t, R2); }
+        if (pre) { ca = pencil_pre(F, ba, ax, t, R2); cb = pencil_pre(F, bb, ax, t, R2); }
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
             double a = 0.0, b = 0.0;
-            if (va) a = in[pa * N + idx];
-            if (vb) b = in[pb * N + idx];
+            if (STR && pair16) {
+                if (va) { const double2 v = *reinterpret_cast<const double2*>(in + ba + idx * step); a = v.x; b = v.y; }
+            } else {
+                if (va) a = in[ba + idx * step];
+                if (vb) b = in[bb + idx * step];
+            }
             if (pre) {                               // (an absent pencil must stay exactly zero)
                 if (va) a = __dmul_rn(ca.at(r), a);
                 if (vb) b = __dmul_rn(cb.at(r), b);
@@ -296,12 +320,12 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         const i64 p0 = ((i64)blockIdx.x * (blockDim.x >> 5) + warp) * TPW * 2;
         for (int q = 0; q < 2 * TPW; ++q)
             if (p0 + q < npencil)
-                fft_slow_pencil<FUSED>(in, out, p0 + q, N, LRT + LR2,
+                fft_slow_pencil<FUSED>(in, out, pencil_base(p0 + q), step, ax, N, LRT + LR2,
                                        fsm + (size_t)(warp * TPW + (q >> 1)) * UNITS, Wn, tw, F);
         return;
     }
     PencilTail ta, tb;
-    if (FUSED) { ta.init(F, va ? pa * N : 0, t, R2); tb.init(F, vb ? pb * N : 0, t, R2); }
+    if (FUSED) { ta.init(F, ba, step, ax, t, R2); tb.init(F, bb, step, ax, t, R2); }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         const int idx = r * R2 + t;
@@ -310,8 +334,12 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
             if (va) a = ta.apply(F, a, r, R2);
             if (vb) b = tb.apply(F, b, r, R2);
         }
-        if (va) out[pa * N + idx] = a;
-        if (vb) out[pb * N + idx] = b;
+        if (STR && pair16) {
+            if (va) *reinterpret_cast<double2*>(out + ba + idx * step) = make_double2(a, b);
+        } else {
+            if (va) out[ba + idx * step] = a;
+            if (vb) out[bb + idx * step] = b;
+        }
     }
 }
 
@@ -404,7 +432,7 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         const bool va = pa < npencil, vb = pb < npencil;
         PencilCoef ca, cb;
         const bool pre = FUSED && F.pre.ptr;
-        if (pre) { ca = pencil_pre(F, va ? pa * N : 0, t, R2); cb = pencil_pre(F, vb ? pb * N : 0, t, R2); }
+        if (pre) { ca = pencil_pre(F, va ? pa * N : 0, F.vec_axis, t, R2); cb = pencil_pre(F, vb ? pb * N : 0, F.vec_axis, t, R2); }
         pf_mbar_wait(mybar, phase);
         phase ^= 1;
         double2 x[RT];
@@ -470,13 +498,13 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             const i64 p0 = (jl * gridDim.x + blockIdx.x) * PPU;
             for (int q = 0; q < PPU; ++q)
                 if (p0 + q < npencil)
-                    fft_slow_pencil<FUSED>(in, out, p0 + q, N, LRT + LR2,
+                    fft_slow_pencil<FUSED>(in, out, (p0 + q) * N, 1, F.vec_axis, N, LRT + LR2,
                                            reinterpret_cast<double2*>(Sall + (size_t)(warp * TPW + (q >> 1)) * N * 16),
                                            Wn, tw, F);
             continue;
         }
         PencilTail ta, tb;
-        if (FUSED) { ta.init(F, va ? pa * N : 0, t, R2); tb.init(F, vb ? pb * N : 0, t, R2); }
+        if (FUSED) { ta.init(F, va ? pa * N : 0, 1, F.vec_axis, t, R2); tb.init(F, vb ? pb * N : 0, 1, F.vec_axis, t, R2); }
         double* const oa = out + pa * N;
         double* const ob = oa + N;
 #pragma unroll
@@ -522,10 +550,10 @@ int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& 
     return NG_OK;
 }
 
-template <int RT, int R2, int MINB>
+template <int RT, int R2, int MINB, bool STR = false>
 int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     constexpr int T = R2, TPW = 32 / T, WARPS = 8;
-    const i64 npencil = p->outer;                       // last axis: one pencil per outer index
+    const i64 npencil = p->outer * p->inner;            // last axis: one pencil per outer index
     const i64 pairs = (npencil + 1) / 2;
     const i64 per_block = (i64)WARPS * TPW;
     const unsigned grid = (unsigned)((pairs + per_block - 1) / per_block);
@@ -534,13 +562,14 @@ int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cu
     do {                                                                                          \
         static bool attr_done = false;                                                            \
         if (!attr_done) {                                                                         \
-            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_kernel<RT, R2, FU, MINB>,                          \
+            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_kernel<RT, R2, FU, MINB, STR>,                     \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                             (int)smem));                                          \
             attr_done = true;                                                                     \
         }                                                                                         \
-        fft2pass_kernel<RT, R2, FU, MINB><<<grid, 32 * WARPS, smem, st>>>(                              \
-            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
+        fft2pass_kernel<RT, R2, FU, MINB, STR><<<grid, 32 * WARPS, smem, st>>>(                         \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, p->inner, p->axis,    \
+            (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F);       \
     } while (0)
     if (F.any) NG_FFT2_GO(true); else NG_FFT2_GO(false);
 #undef NG_FFT2_GO
@@ -554,10 +583,25 @@ int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cu
 int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                        cudaStream_t st, bool* handled) {
     *handled = false;
-    if (p->inner != 1 || !p->d_Wn || !p->d_twn) return NG_OK;
+    if (!p->d_Wn || !p->d_twn) return NG_OK;
     const char* e = getenv("NG_FFT_TWOPASS");
     if (e && atoi(e) == 0) return NG_OK;
     int rc = NG_OK;
+    if (p->inner != 1) {
+        // transform axis not contiguous: the one-shot kernel with strided pencils (adjacent columns per CTA)
+        const char* se = getenv("NG_FFT_STRIDED");      // A/B: 0 = radix-2 shared-memory fallback (fft.cu)
+        if (se && atoi(se) == 0) return NG_OK;
+        switch (p->n) {
+            case 1024: rc = launch<32, 32, 1, true>(p, in, out, F, st); break;
+            case 512: rc = launch<32, 16, 1, true>(p, in, out, F, st); break;
+            case 256: rc = launch<16, 16, 1, true>(p, in, out, F, st); break;
+            case 128: rc = launch<16, 8, 1, true>(p, in, out, F, st); break;
+            case 64: rc = launch<8, 8, 1, true>(p, in, out, F, st); break;
+            default: return NG_OK;
+        }
+        *handled = (rc == NG_OK);
+        return rc;
+    }
     const char* pfe = getenv("NG_FFT_PREFETCH");        // tuning: 0 = one-shot kernel, no input staging
     // the persistent ring kernel needs enough pencils to fill 148 CTAs and a 16-byte aligned input
     const bool ring = !(pfe && atoi(pfe) == 0) && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * 6;
