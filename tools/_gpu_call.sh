@@ -1,3 +1,2 @@
-timeout 300 python tools/check_fft_strided.py 120 0 2>&1 | tail -6
-python tools/time_fft_axes.py > gpurun_out/time_fft_axes2.log 2>&1
-cat gpurun_out/time_fft_axes2.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
