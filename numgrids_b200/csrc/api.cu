@@ -53,6 +53,16 @@ int upload(ng_plan* p, double** d_dst, const double* h_src, i64 count) {
     return NG_OK;
 }
 
+// zero-padded k-major matrix for the general dense kernel (dense.cu): [n_pad][n_pad], n_pad = ceil128(n)
+int upload_padded_mt(ng_plan* p, const double* Mt) {
+    const i64 n = p->n, np = (n + 127) / 128 * 128;
+    if (np > 8192) return NG_OK;                      // (the general kernel is then simply not used)
+    std::vector<double> pad((size_t)(np * np), 0.0);
+    for (i64 k = 0; k < n; ++k) memcpy(&pad[(size_t)(k * np)], Mt + k * n, sizeof(double) * (size_t)n);
+    p->n_pad = (int)np;
+    return upload(p, &p->d_Mtp, pad.data(), np * np);
+}
+
 int require_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -201,6 +211,7 @@ int ng_cheb_plan_create(int ndim, const int64_t* shape, int axis, const double* 
         for (i64 k = 0; k < n; ++k) Mt[(size_t)(k * n + i)] = h_M[i * n + k];
     rc = upload(p, &p->d_M, h_M, n * n);
     if (!rc) rc = upload(p, &p->d_Mt, Mt.data(), n * n);
+    if (!rc) rc = upload_padded_mt(p, Mt.data());
     if (rc) { ng_plan_destroy(p); return rc; }
     *out = p;
     return NG_OK;
@@ -266,6 +277,7 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h
             for (i64 k = 0; k < n; ++k) Mt[(size_t)(k * n + i)] = h_D[i * n + k];
         rc = upload(p, &p->d_M, h_D, n * n);
         if (!rc) rc = upload(p, &p->d_Mt, Mt.data(), n * n);
+        if (!rc) rc = upload_padded_mt(p, Mt.data());
     }
     if (rc) { ng_plan_destroy(p); return rc; }
     *out = p;
@@ -483,7 +495,7 @@ int64_t ng_plan_device_bytes(const ng_plan* plan) { return plan ? plan->device_b
 int ng_plan_destroy(ng_plan* p) {
     if (!p) return NG_OK;
     auto fr = [](double* q) { if (q) cudaFree(q); };
-    fr(p->d_xdiv); fr(p->d_M); fr(p->d_Mt); fr(p->d_W); fr(p->d_tw); fr(p->d_Wn); fr(p->d_twn); fr(p->d_work);
+    fr(p->d_xdiv); fr(p->d_M); fr(p->d_Mt); fr(p->d_Mtp); fr(p->d_W); fr(p->d_tw); fr(p->d_Wn); fr(p->d_twn); fr(p->d_work);
     fr(p->d_stage_in); fr(p->d_stage_out);
     fr(p->cJ.d_ptr);
     for (int a = 0; a < NG_MAX_DIM; ++a) {

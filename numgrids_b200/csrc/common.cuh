@@ -101,6 +101,8 @@ struct ng_plan {
     // PK_CHEB (and the dense fallback of PK_FFT)
     double* d_M = nullptr;    // [n][n] row-major
     double* d_Mt = nullptr;   // transposed copy (k-major) for broadcast-friendly panel loads
+    double* d_Mtp = nullptr;  // the same, zero-padded to [n_pad][n_pad], n_pad = n rounded up to 128 (general kernel)
+    int n_pad = 0;
     int descending = 0;
     int use_fma = 0;
 

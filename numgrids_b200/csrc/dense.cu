@@ -15,6 +15,8 @@
 // loaded coalesced along k and transposed in shared memory, and lanes run along i for the store.
 // The FMA variant (use_fma) serves the dense form of the periodic spectral matrix
 // (numgrids/diff.py:145-157) whose tolerance (1e-11) allows contraction.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -136,6 +138,17 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// zero-filling variants (src-size 0 reads nothing and writes zeros): rows / columns past the array
+__device__ __forceinline__ void cp_async16_z(void* smem_dst, const void* gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8_z(void* smem_dst, const void* gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -146,10 +159,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // LASTAX: the contraction axis is the contiguous one (pencil r = row of a [R][n] matrix, Out = F Mt):
 // the F panel is transposed on the fly by 8-byte cp.async (source coalesced along k), outputs are
 // stored as (i, i+1) pairs of one pencil.
-template <bool DESC, bool FMA, bool FUSED, int NCP, bool LASTAX>
+// GEN: any n and any (even) column count -- Mt is the zero-padded copy (pitch `npitch`, a multiple of 128),
+// k panels past n are zero-filled (0 * 0 adds +-0 to a sum that started at +0.0: the bits do not change),
+// column tiles are cut per outer index with their tail columns zero-filled, rows / columns past the array
+// are not stored and row groups of 32 past n are not computed.  !GEN is the exact-shape kernel unchanged.
+template <bool DESC, bool FMA, bool FUSED, int NCP, bool LASTAX, bool GEN>
 __global__ void __launch_bounds__(256, NCP == 4 ? 1 : NG_DENSE_MINB)
 dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
-                  const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F) {
+                  const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F,
+                  int npitch, i64 npencil_last, int tiles_per_o) {
     constexpr int TFN = 32 * NCP, HALF = TFN / 2;
     // LASTAX stages F by 8-byte copies with consecutive threads walking k: rows one pitch apart.  A
     // pitch of TFN doubles puts all 16 k of a column in one bank (16-way conflict on every copy);
@@ -160,7 +178,18 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     double (*Fs)[FK][TFP] = reinterpret_cast<double (*)[FK][TFP]>(dsm + 2 * FK * FM);  // [2][FK][TFP]
     const i64 col0 = (i64)blockIdx.x * TFN;         // flattened (o, c) column; tiles never straddle o
     const int row0 = blockIdx.y * FM;
-    const i64 o = LASTAX ? 0 : col0 / inner, c0 = LASTAX ? 0 : col0 - o * inner;
+    i64 o = LASTAX ? 0 : col0 / inner, c0 = LASTAX ? 0 : col0 - o * inner;
+    int ncv = TFN;                                  // valid columns (pencils) of this tile
+    if (GEN) {
+        if (LASTAX) {
+            ncv = (int)(npencil_last - col0 < TFN ? npencil_last - col0 : TFN);
+        } else {
+            o = blockIdx.x / tiles_per_o;
+            c0 = (i64)(blockIdx.x - o * tiles_per_o) * TFN;
+            ncv = (int)(inner - c0 < TFN ? inner - c0 : TFN);
+        }
+    }
+    const int jmax = GEN ? ((n - row0 + 31) / 32 < 4 ? (n - row0 + 31) / 32 : 4) : 4;   // 32-row groups with rows < n
     // element (k, c): fbase + k*inner + c;  LASTAX: pencil r = col0 + c, element (k, c) at fbase + c*n + k
     const double* fbase = LASTAX ? in + col0 * (i64)n : in + o * (i64)n * inner + c0;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -171,9 +200,12 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
         for (int b = 0; b < 2 * NCP; ++b) acc[a][b] = 0.0;
 
-    const int npanel = n / FK;
+    const int npanel = GEN ? (n + FK - 1) / FK : n / FK;
     Idx4 pre_ix;                                   // multi-index of (row 0, this thread's chunk column)
-    if (FUSED && F.pre.ptr && !LASTAX) pre_ix = unravel4((o * n) * inner + c0 + (tid % HALF) * 2, F.shape);
+    if (FUSED && F.pre.ptr && !LASTAX) {
+        const int chp = (tid % HALF) * 2;
+        pre_ix = unravel4((o * n) * inner + c0 + ((GEN && chp >= ncv) ? 0 : chp), F.shape);
+    }
     // prologue coefficients (`coeff * v[i]`) of the panel in flight, fetched with the panel so that
     // their global-load latency hides under the previous panel's arithmetic
     double pcn[2 * NCP * FKS];
@@ -185,6 +217,10 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
             for (int q = 0; q < NCP * FKS; ++q) {
                 const int kk = (tid + q * 256) / HALF;
+                if (GEN && (k0 + kk >= n || ((tid + q * 256) % HALF) * 2 >= ncv)) {   // zero-filled chunk
+                    pcn[2 * q] = pcn[2 * q + 1] = 0.0;
+                    continue;
+                }
                 Idx4 ix = pre_ix;
                 ix.i[axis] = k0 + kk;
                 const i64 po = coef_off(F.pre, ix);
@@ -197,7 +233,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         for (int q = 0; q < 4 * FKS; ++q) {
             const int e = tid + q * 256;
             const int kk = e >> 6, ch = (e & 63) * 2;
-            cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * n + row0 + ch);
+            cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * npitch + row0 + ch);
         }
         if (LASTAX) {
             // 16 x TFN doubles as 8-byte copies: consecutive threads walk k (128 B contiguous per pencil)
@@ -205,18 +241,32 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             for (int q = 0; q < 2 * NCP * FKS; ++q) {
                 const int e = tid + q * 256;
                 const int kk = e % FK, c = e / FK;
-                cp_async8(&Fs[buf][kk][c], fbase + (i64)c * n + k0 + kk);
+                if (GEN) {
+                    const bool ok = k0 + kk < n && c < ncv;
+                    cp_async8_z(&Fs[buf][kk][c], ok ? fbase + (i64)c * n + k0 + kk : in, ok);
+                } else {
+                    cp_async8(&Fs[buf][kk][c], fbase + (i64)c * n + k0 + kk);
+                }
             }
         } else {
 #pragma unroll
             for (int q = 0; q < NCP * FKS; ++q) {
                 const int e = tid + q * 256;
                 const int kk = e / HALF, ch = (e % HALF) * 2;
-                cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
+                if (GEN) {
+                    const bool ok = k0 + kk < n && ch < ncv;
+                    cp_async16_z(&Fs[buf][kk][ch], ok ? fbase + (i64)(k0 + kk) * inner + ch : in, ok);
+                } else {
+                    cp_async16(&Fs[buf][kk][ch], fbase + (i64)(k0 + kk) * inner + ch);
+                }
             }
         }
         cp_async_commit();
     };
+    // the panel loop, with the number of live 32-row groups (JM) a compile-time constant: a run-time
+    // test inside the k loop would fence the scheduling of LDS and FP64 instructions across it
+    auto run = [&](auto jm_c) {
+    constexpr int JM = decltype(jm_c)::value;
     stage(DESC ? npanel - 1 : 0, 0);
     for (int pp = 0; pp < npanel; ++pp) {
         const int buf = pp & 1;
@@ -238,6 +288,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                 for (int q = 0; q < 2 * NCP * FKS; ++q) {
                     const int e = tid + q * 256;
                     const int kk = e % FK, c = e / FK;
+                    if (GEN && (k0 + kk >= n || c >= ncv)) continue;      // zero-filled element stays zero
                     const Idx4 ix = unravel4((col0 + c) * (i64)n + k0 + kk, F.shape);
                     Fs[buf][kk][c] = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], Fs[buf][kk][c]);
                 }
@@ -257,7 +308,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             const int kk = DESC ? FK - 1 - q : q;
             double a[8], b[2 * NCP];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < JM; ++j) {
                 const double2 av = *reinterpret_cast<const double2*>(&Ms[buf][kk][ty * 2 + 32 * j]);
                 a[2 * j] = av.x; a[2 * j + 1] = av.y;
             }
@@ -267,19 +318,26 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                 b[2 * j] = bv.x; b[2 * j + 1] = bv.y;
             }
 #pragma unroll
-            for (int x = 0; x < 8; ++x)
+            for (int x = 0; x < 2 * JM; ++x) {
 #pragma unroll
                 for (int y = 0; y < 2 * NCP; ++y) {
                     if (FMA) acc[x][y] = fma(a[x], b[y], acc[x][y]);
                     else acc[x][y] = __dadd_rn(acc[x][y], __dmul_rn(a[x], b[y]));
                 }
+            }
         }
         __syncthreads();
     }
+    };
+    if (!GEN || jmax >= 4) run(std::integral_constant<int, 4>{});
+    else if (jmax == 3) run(std::integral_constant<int, GEN ? 3 : 4>{});
+    else if (jmax == 2) run(std::integral_constant<int, GEN ? 2 : 4>{});
+    else run(std::integral_constant<int, GEN ? 1 : 4>{});
     if (LASTAX) {
         // out[(col0 + c)*n + i]: store (i, i+1) pairs of one pencil; one unravel per pencil
 #pragma unroll
         for (int y = 0; y < 2 * NCP; ++y) {
+            if (GEN && tx * 2 + (y & 1) + 32 * (y >> 1) >= ncv) continue;
             const i64 r = col0 + tx * 2 + (y & 1) + 32 * (y >> 1);
             i64 po = 0, dv = 0, pa = 0, da = 0;             // offsets of (pencil r, i = 0), strides along i
             if (FUSED) {
@@ -290,6 +348,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = row0 + ty * 2 + 32 * j;
+                if (GEN && i >= n) continue;                // n is even: the pair (i, i+1) is inside or outside
                 const i64 lin = r * (i64)n + i;
                 double2 v = make_double2(acc[2 * j][y], acc[2 * j + 1][y]);
                 if (FUSED) {
@@ -305,6 +364,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     // pair (the row only changes the coordinate along `axis`).
 #pragma unroll
     for (int jc = 0; jc < NCP; ++jc) {
+        if (GEN && tx * 2 + 32 * jc >= ncv) continue;                   // inner is even: whole pairs
         const i64 lin0 = (o * n) * inner + c0 + tx * 2 + 32 * jc;       // row 0 of this column pair
         i64 po = 0, dv = 0, pa = 0, da = 0, pv = 0, dvv = 0;   // offsets of row 0, strides along i / the pair
         if (FUSED) {
@@ -315,6 +375,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
             const int i = row0 + ty * 2 + (x & 1) + 32 * (x >> 1);
+            if (GEN && i >= n) continue;
             const i64 lin = lin0 + (i64)i * inner;
             double2 v = make_double2(acc[x][2 * jc], acc[x][2 * jc + 1]);
             if (FUSED) {
@@ -326,23 +387,30 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
 }
 
-template <bool DESC, bool FMA, int NCP, bool LASTAX>
+template <bool DESC, bool FMA, int NCP, bool LASTAX, bool GEN = false>
 int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     constexpr int TFN = 32 * NCP;
     const i64 ncols = p->outer * p->inner;
     dim3 grid((unsigned)(ncols / TFN), (unsigned)(p->n / FM));
+    const int tiles_per_o = (int)((p->inner + TFN - 1) / TFN);
+    if (GEN) {
+        grid.x = LASTAX ? (unsigned)((p->outer + TFN - 1) / TFN) : (unsigned)(p->outer * tiles_per_o);
+        grid.y = (unsigned)((p->n + FM - 1) / FM);
+    }
+    const double* Mt = GEN ? p->d_Mtp : p->d_Mt;
+    const int npitch = GEN ? p->n_pad : (int)p->n;
     const size_t smem = (size_t)2 * FK * (FM + TFN + (LASTAX ? 2 : 0)) * sizeof(double);
 #define NG_DENSE_FAST(FU)                                                                       \
     do {                                                                                        \
         static bool attr_done = false;                                                          \
         if (!attr_done) {                                                                       \
-            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX>,              \
+            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN>,         \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                             (int)smem));                                        \
             attr_done = true;                                                                   \
         }                                                                                       \
-        dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX><<<grid, 256, smem, st>>>(                         \
-            in, out, p->d_Mt, (int)p->n, p->inner, p->axis, F);                                 \
+        dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN><<<grid, 256, smem, st>>>(                    \
+            in, out, Mt, (int)p->n, p->inner, p->axis, F, npitch, p->outer, tiles_per_o);       \
     } while (0)
     if (F.any) NG_DENSE_FAST(true); else NG_DENSE_FAST(false);
 #undef NG_DENSE_FAST
@@ -367,13 +435,24 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
     return launch_fast2<DESC, FMA, 1, false>(p, in, out, F, st);
 }
 
-bool fast_ok(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
-    if (p->n % FM != 0) return false;
-    if (p->inner == 1 ? (p->outer % 32 != 0) : (p->inner % 32 != 0)) return false;
-    if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
-    if (F.any && p->inner != 1 && F.shape[F.vec_axis] % 2 != 0) return false;
-    const char* e = getenv("NG_DENSE_FAST");
-    return !(e && atoi(e) == 0);
+// 0: fallback kernel; 1: exact shapes (n % 128 == 0, columns % 32 == 0); 2: general (GEN) kernel
+int fast_mode(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
+    if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return 0;
+    if (F.any && p->inner != 1 && F.shape[F.vec_axis] % 2 != 0) return 0;
+    const char* e = getenv("NG_DENSE_FAST");          // tuning / A-B: 0 = fallback only, 2 = general kernel even on exact shapes
+    const int force = e ? atoi(e) : 1;
+    if (force == 0) return 0;
+    const bool exact = p->n % FM == 0 && (p->inner == 1 ? p->outer % 32 == 0 : p->inner % 32 == 0);
+    if (exact && force != 2) return 1;
+    // general: 128-bit accesses need whole pairs along the contiguous direction
+    if (!p->d_Mtp || (p->inner == 1 ? p->n % 2 != 0 : p->inner % 2 != 0)) return 0;
+    return 2;
+}
+
+template <bool DESC, bool FMA>
+int launch_general(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    if (p->inner == 1) return launch_fast2<DESC, FMA, 1, true, true>(p, in, out, F, st);
+    return launch_fast2<DESC, FMA, 1, false, true>(p, in, out, F, st);
 }
 
 template <bool LAST, bool DESC, bool FMA>
@@ -402,10 +481,16 @@ int launch1(const ng_plan* p, const double* in, double* out, const FuseDev& F, c
 int ng_dense_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                     cudaStream_t st) {
     if (p->size == 0) return NG_OK;
-    if (fast_ok(p, in, out, F)) {
+    const int mode = fast_mode(p, in, out, F);
+    if (mode == 1) {
         if (p->use_fma) return launch_fast<false, true>(p, in, out, F, st);
         if (p->descending) return launch_fast<true, false>(p, in, out, F, st);
         return launch_fast<false, false>(p, in, out, F, st);
+    }
+    if (mode == 2) {
+        if (p->use_fma) return launch_general<false, true>(p, in, out, F, st);
+        if (p->descending) return launch_general<true, false>(p, in, out, F, st);
+        return launch_general<false, false>(p, in, out, F, st);
     }
     return p->inner == 1 ? launch1<true>(p, in, out, F, st) : launch1<false>(p, in, out, F, st);
 }

@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python tools/check_dense_general.py 200 0 2>&1 | tail -8
+python tools/time_cheb_sizes.py > gpurun_out/time_cheb_sizes2.log 2>&1
+cat gpurun_out/time_cheb_sizes2.log
