@@ -138,8 +138,11 @@ __device__ __forceinline__ double2 ldg128(const double* p) {
 #ifndef NG_FD_MINB
 #define NG_FD_MINB 1
 #endif
-template <int P, bool FUSED>
-__global__ void __launch_bounds__(256, FUSED ? 2 : NG_FD_MINB)
+// XD: LogDiff's `/ x[i]` (two correctly rounded divides per pair).  The divide sequences are latency-bound,
+// so that variant is capped at 64 registers (4 CTAs per SM: 0.80 -> 0.87 of the HBM peak at 1024^3); the
+// plain stencil is faster uncapped (0.97 vs 0.91).
+template <int P, bool FUSED, bool XD>
+__global__ void __launch_bounds__(256, FUSED ? 2 : (XD ? 4 : NG_FD_MINB))
 fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 outer, int n, i64 inner,
                 int axis, FdTables T, const double* __restrict__ xdiv, FuseDev F, int seg_len, int nseg) {
     constexpr int W = 2 * P + 1;
@@ -182,7 +185,7 @@ fd_march_kernel(const double* __restrict__ in, double* __restrict__ out, i64 out
         double2 r;
         r.x = __dmul_rn(ax, T.inv_h_pow);
         r.y = __dmul_rn(ay, T.inv_h_pow);
-        if (xdiv) { const double xd = xdiv[i]; r.x = __ddiv_rn(r.x, xd); r.y = __ddiv_rn(r.y, xd); }
+        if (XD) { const double xd = xdiv[i]; r.x = __ddiv_rn(r.x, xd); r.y = __ddiv_rn(r.y, xd); }
         if (FUSED) {
             r.x = fuse_tail_vals(F, r.x, m.x, a.x, post0 + i * post_a, div0 + i * div_a);
             r.y = fuse_tail_vals(F, r.y, m.y, a.y, post0 + i * post_a + post_v, div0 + i * div_a + div_v);
@@ -315,8 +318,10 @@ static int launch_stream(const ng_plan* p, const double* in, double* out, const 
         nseg = (n + seg_len - 1) / seg_len;
         const i64 threads = ncol * nseg;
         const unsigned grid = (unsigned)((threads + 255) / 256);
-        if (F.any) fd_march_kernel<P, true><<<grid, 256, 0, st>>>(in, out, p->outer, n, p->inner, p->axis, p->fd, p->d_xdiv, F, seg_len, (int)nseg);
-        else fd_march_kernel<P, false><<<grid, 256, 0, st>>>(in, out, p->outer, n, p->inner, p->axis, p->fd, p->d_xdiv, F, seg_len, (int)nseg);
+#define NG_FD_MARCH(FU, XD) fd_march_kernel<P, FU, XD><<<grid, 256, 0, st>>>(in, out, p->outer, n, p->inner, p->axis, p->fd, p->d_xdiv, F, seg_len, (int)nseg)
+        if (F.any) { if (p->d_xdiv) NG_FD_MARCH(true, true); else NG_FD_MARCH(true, false); }
+        else       { if (p->d_xdiv) NG_FD_MARCH(false, true); else NG_FD_MARCH(false, false); }
+#undef NG_FD_MARCH
     } else {
         return ng_fd_row_launch(P, p, in, out, F, lo, hi, st);
     }
