@@ -1,2 +1,3 @@
-timeout 200 python tools/check_fd_stream.py 300 13 2>&1 | tail -1
-timeout 100 python tools/time_fd_fused.py 512 2>&1 | grep "axis 2"
+python tools/run_fd_fused.py 512 2 post > gpurun_out/plain_fdf.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:'fd_row' -s 2 -c 1 -f -o gpurun_out/prof_fd_row_fused python tools/run_fd_fused.py 512 2 post > gpurun_out/ncu_fdf.log 2>&1
+echo done
