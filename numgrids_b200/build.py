@@ -19,6 +19,9 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libnumgrids_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "fd.cu", "fd_row.cu", "dense.cu", "fft.cu", "fft2.cu", "fdlap.cu", "fdlap3d.cu", "curv.cu", "transpose.cu", "bc.cu", "quad.cu", "interp.cu"]
+# translation units compiled more than once with different macros (object name -> (source, defines)):
+# the contiguous-axis FD kernel is the slowest file to compile; its half widths 3-4 build as a second object
+EXTRA_OBJECTS = {"fd_row_wide.o": ("fd_row.cu", ["-DNG_ROW_PSET=1"])}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
@@ -48,6 +51,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
 
+    for obj, (src, defs) in EXTRA_OBJECTS.items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, obj)
+        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs):
+            cmd = [NVCC, *FLAGS, *defs, "-c", s, "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append(cmd)
+
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -59,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             for msg in ex.map(run, jobs):
                 if verbose and msg:
                     print(msg)
-    objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES] + [os.path.join(OBJDIR, o) for o in EXTRA_OBJECTS]
     if force or jobs or not os.path.exists(LIB):
         run([NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static"])
     return LIB

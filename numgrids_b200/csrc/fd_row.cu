@@ -213,14 +213,29 @@ int launch_row(const ng_plan* p, const double* in, double* out, const FuseDev& F
 
 }  // namespace
 
+// This file is compiled twice (numgrids_b200/build.py) so that the two halves build in parallel:
+// NG_ROW_PSET = 0 instantiates the half widths 1 and 2 and the dispatcher, NG_ROW_PSET = 1 the half widths 3 and 4.
+#ifndef NG_ROW_PSET
+#define NG_ROW_PSET 0
+#endif
+int ng_fd_row_launch_wide(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                          const double* lo, const double* hi, cudaStream_t st);
+#if NG_ROW_PSET == 0
 int ng_fd_row_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
                      const double* lo, const double* hi, cudaStream_t st) {
     switch (P) {
         case 1: return launch_row<1>(p, in, out, F, lo, hi, st);
         case 2: return launch_row<2>(p, in, out, F, lo, hi, st);
-        case 3: return launch_row<3>(p, in, out, F, lo, hi, st);
-        case 4: return launch_row<4>(p, in, out, F, lo, hi, st);
+        case 3:
+        case 4: return ng_fd_row_launch_wide(P, p, in, out, F, lo, hi, st);
     }
     ng_set_error("ng_fd_row_launch: unsupported half width %d", P);
     return NG_EINVAL;
 }
+#else
+int ng_fd_row_launch_wide(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                          const double* lo, const double* hi, cudaStream_t st) {
+    if (P == 3) return launch_row<3>(p, in, out, F, lo, hi, st);
+    return launch_row<4>(p, in, out, F, lo, hi, st);
+}
+#endif

@@ -17,6 +17,7 @@ r = subprocess.run([B.NVCC, *B.FLAGS, *defs, "-Xptxas=-v", "-c", os.path.join(B.
 if r.returncode:
     sys.exit(r.stdout + r.stderr)
 objs = [obj if s == src else os.path.join(B.OBJDIR, s.replace(".cu", ".o")) for s in B.SOURCES]
+objs += [os.path.join(B.OBJDIR, o) for o in B.EXTRA_OBJECTS]
 out = os.path.join(vdir, f"libng_{name}.so")
 subprocess.run([B.NVCC, "-shared", "-o", out, *objs, "-cudart", "static"], check=True)
 spill = [l for l in r.stderr.splitlines() if "spill" in l and "0 bytes spill stores, 0 bytes spill loads" not in l]
