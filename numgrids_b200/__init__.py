@@ -1,17 +1,16 @@
 """numgrids_b200 -- B200-native (sm_100a) implementation of the numgrids differentiation hot path.
 
-Drop-in for the reference's hot-path API: ``Grid``, ``CurvilinearGrid``, ``SphericalGrid``,
-``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` / ``Axis``, ``Diff``, ``diff``,
-plus the step that follows a derivative apply in a PDE loop: ``BoundaryFace``, ``DirichletBC``,
-``NeumannBC``, ``RobinBC``, ``apply_bcs`` (in place on device arrays) and
-``Integral`` / ``integrate`` (one streaming quadrature pass, N3), ``Interpolator`` / ``MultiGrid.transfer``
-with ``method="linear"`` and the ``adapt`` / ``estimate_error`` refinement loop built on them (N4).
-``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` run hand-written CUDA kernels
-through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.
+Drop-in for the reference's package surface (same names as numgrids/__init__.py): ``Grid``, ``MultiGrid``,
+``CurvilinearGrid``, ``SphericalGrid``, ``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` /
+``Axis``, ``Diff``, ``diff``, ``integrate`` / ``Integral``, ``interpolate`` / ``Interpolator`` (linear),
+``BoundaryFace`` / ``DirichletBC`` / ``NeumannBC`` / ``RobinBC`` / ``apply_bcs``, ``ErrorEstimator`` /
+``AdaptationResult`` / ``adapt`` / ``estimate_error``, ``save_grid`` / ``load_grid``.
 
-Reference components outside the hot path (spline interpolation,
-I/O, plotting -- SURVEY.md section 2) are intentionally not provided; accessing their
-names raises ``NotImplementedError`` that says so.
+``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` -- the hot path -- and the operators around it
+(boundary applies, quadrature, linear interpolation / multigrid transfer, refinement estimates) run hand-written
+CUDA kernels through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.  Sparse-matrix assembly
+(``as_matrix``, ``apply_to_system``) and file I/O are host code.  Not provided: quadratic / cubic spline
+interpolation (global fits inside SciPy) and plotting.
 """
 __version__ = "0.1.0"
 
@@ -24,15 +23,15 @@ from .api import (Diff, AxisType, create_axis, SphericalGrid, CylindricalGrid, P
 from .integration import Integral
 from .interpol import Interpolator
 from .amr import ErrorEstimator, AdaptationResult, adapt, estimate_error
+from .io import save_grid, load_grid
+from .api import interpolate
 from .boundary import BoundaryFace, DirichletBC, NeumannBC, RobinBC, apply_bcs
 from ._lib import NumgridsB200Error
 
 # Backward compatibility alias kept by the reference (numgrids/__init__.py:13)
 Axis = create_axis
 
-_OUT_OF_SCOPE = {
-    "save_grid", "load_grid", "interpolate",
-}
+_OUT_OF_SCOPE = set()
 
 
 def __getattr__(name):

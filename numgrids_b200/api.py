@@ -91,6 +91,15 @@ def diff(grid, f, order=1, axis_index=0, acc=4):
     return ops[key](f)
 
 
+def interpolate(grid, f, locations, method="cubic"):
+    """Interpolate a meshed function at a Grid, a point or a list of points (numgrids/api.py:286-306).
+
+    The reference always builds a cubic interpolant here; ``method`` is an extension: pass ``"linear"`` for
+    the device kernel (``"cubic"`` / ``"quadratic"`` raise ``NotImplementedError``, see interpol.py)."""
+    from .interpol import Interpolator
+    return Interpolator(grid, f, method=method)(locations)
+
+
 def integrate(grid, f):
     """Integrate a meshed function over the whole grid; the operator is cached on the grid
     under the reference's key (numgrids/api.py:309-335)."""

@@ -138,8 +138,6 @@ def test_validation_errors():
     with pytest.raises(ValueError):
         ng.Diff(ng.Grid(EquidistantAxis(5, 0, 1)), 2, 0)      # too short for the 6-tap one-sided scheme
     assert ng.Axis is ng.create_axis
-    with pytest.raises(NotImplementedError):
-        ng.save_grid
 
 
 def test_grid_surface_is_lazy_and_compatible():
