@@ -234,6 +234,15 @@ int ng_interp_linear(int ndim, const int64_t* src_shape, const int64_t* dst_shap
                      const int32_t* const* d_idx, const double* const* d_y, const double* const* d_omy,
                      const double* d_values, double* d_out, void* stream);
 
+/* Tensor-product B-spline evaluation (Interpolator methods "cubic" / "quadratic": SciPy's NdBSpline / BSpline
+ * behind numgrids/interpol.py:34-46).  d_coef: the spline coefficients (C order, coef_shape) the host obtained
+ * from SciPy exactly as the reference does; per axis a: nbasis[a] = degree + 1, d_first[a][t] = first coefficient
+ * index and d_basis[a][t*nbasis[a] + j] = j-th non-zero basis value at target coordinate t (SciPy's de Boor
+ * recursion, host-built).  Target layout and `scattered` as for ng_interp_linear.  Terms summed in SciPy's order. */
+int ng_interp_bspline(int ndim, const int64_t* coef_shape, const int64_t* dst_shape, int scattered,
+                      const int32_t* nbasis, const int32_t* const* d_first, const double* const* d_basis,
+                      const double* d_coef, double* d_out, void* stream);
+
 /* ---- lifetime ---------------------------------------------------------------------------------*/
 int ng_plan_destroy(ng_plan* plan);
 /* bytes of device memory owned by the plan (tables + workspace + host-call staging) */

@@ -78,6 +78,7 @@ SIGNATURES = {
     "ng_quad_apply": (C.c_int, [C.c_int, _I64, _PP, _P, _P, _P, _P]),
     "ng_diff_norm": (C.c_int, [C.c_int64, _P, _P, C.c_int, _P, _P, _P]),
     "ng_interp_linear": (C.c_int, [C.c_int, _I64, _I64, C.c_int, _PP, _PP, _PP, _P, _P, _P]),
+    "ng_interp_bspline": (C.c_int, [C.c_int, _I64, _I64, C.c_int, _I32, _PP, _PP, _P, _P, _P]),
     "ng_plan_destroy": (C.c_int, [_P]),
     "ng_plan_device_bytes": (C.c_int64, [_P]),
 }

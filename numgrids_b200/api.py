@@ -94,8 +94,8 @@ def diff(grid, f, order=1, axis_index=0, acc=4):
 def interpolate(grid, f, locations, method="cubic"):
     """Interpolate a meshed function at a Grid, a point or a list of points (numgrids/api.py:286-306).
 
-    The reference always builds a cubic interpolant here; ``method`` is an extension: pass ``"linear"`` for
-    the device kernel (``"cubic"`` / ``"quadratic"`` raise ``NotImplementedError``, see interpol.py)."""
+    The reference always builds a cubic interpolant here; ``method`` is an extension (``"linear"``, and
+    ``"quadratic"`` on 1-D grids, see interpol.py)."""
     from .interpol import Interpolator
     return Interpolator(grid, f, method=method)(locations)
 

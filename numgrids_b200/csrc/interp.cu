@@ -123,3 +123,97 @@ extern "C" int ng_interp_linear(int ndim, const int64_t* src_shape, const int64_
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Tensor-product B-spline evaluation: Interpolator with method "cubic" (N-D: SciPy's NdBSpline behind
+// RegularGridInterpolator) and "cubic" / "quadratic" in 1-D (interp1d -> make_interp_spline -> BSpline),
+// reference numgrids/interpol.py:34-46.  The spline coefficients are the host's (SciPy's own solve, as in
+// the reference); per target coordinate and axis the host passes the first coefficient index and the k+1
+// non-zero basis values (SciPy's de Boor recursion).  Each point sums its (k+1)^d terms in SciPy's order:
+// last axis fastest, factor = ((1*b_0)*b_1)*..., value += c * factor -- bit-identical to SciPy's evaluation.
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct SplineArgs {
+    const int* first[NG_MAX_DIM];      // first coefficient index per target coordinate
+    const double* basis[NG_MAX_DIM];   // [ntargets][nb] basis values
+    i64 cstride[NG_MAX_DIM];           // coefficient strides (elements)
+    i64 dshape[NG_MAX_DIM];
+    int nb[NG_MAX_DIM];                // k + 1 per axis
+    i64 total;
+    int ndim, scattered;
+};
+
+__global__ void __launch_bounds__(256) interp_bspline_kernel(const double* __restrict__ c, double* __restrict__ out, SplineArgs A) {
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < A.total; t += (i64)gridDim.x * blockDim.x) {
+        i64 ti[NG_MAX_DIM] = {0, 0, 0, 0};
+        if (A.scattered) {
+            for (int a = 0; a < A.ndim; ++a) ti[a] = t;
+        } else {
+            i64 r = t;
+            for (int a = A.ndim - 1; a > 0; --a) { ti[a] = r % A.dshape[a]; r /= A.dshape[a]; }
+            ti[0] = r;
+        }
+        i64 base = 0;
+        const double* b[NG_MAX_DIM] = {nullptr, nullptr, nullptr, nullptr};
+        int terms = 1;
+        for (int a = 0; a < A.ndim; ++a) {
+            base += (i64)A.first[a][ti[a]] * A.cstride[a];
+            b[a] = A.basis[a] + ti[a] * A.nb[a];
+            terms *= A.nb[a];
+        }
+        double res = 0.0;
+        for (int e = 0; e < terms; ++e) {                    // flat tap index, last axis fastest
+            int j[NG_MAX_DIM] = {0, 0, 0, 0};
+            int r = e;
+            for (int a = A.ndim - 1; a > 0; --a) { j[a] = r % A.nb[a]; r /= A.nb[a]; }
+            j[0] = r;
+            double factor = 1.0;
+            i64 o = base;
+            for (int a = 0; a < A.ndim; ++a) {
+                factor = __dmul_rn(factor, b[a][j[a]]);
+                o += (i64)j[a] * A.cstride[a];
+            }
+            res = __dadd_rn(res, __dmul_rn(c[o], factor));
+        }
+        out[t] = res;
+    }
+}
+
+}  // namespace
+
+extern "C" int ng_interp_bspline(int ndim, const int64_t* coef_shape, const int64_t* dst_shape, int scattered,
+                                 const int32_t* nbasis, const int32_t* const* d_first,
+                                 const double* const* d_basis, const double* d_coef, double* d_out,
+                                 void* stream) {
+    NG_REQUIRE(ndim >= 1 && ndim <= NG_MAX_DIM && coef_shape && dst_shape && nbasis, "ng_interp_bspline: bad shape");
+    NG_REQUIRE(d_first && d_basis && d_coef && d_out, "ng_interp_bspline: NULL buffer");
+    SplineArgs A;
+    memset(&A, 0, sizeof(A));
+    A.ndim = ndim;
+    A.scattered = scattered ? 1 : 0;
+    i64 st = 1, total = 1;
+    for (int a = ndim - 1; a >= 0; --a) {
+        NG_REQUIRE(nbasis[a] >= 1 && nbasis[a] <= 8, "ng_interp_bspline: degree + 1 must be in 1..8 (axis %d)", a);
+        NG_REQUIRE(coef_shape[a] >= nbasis[a], "ng_interp_bspline: axis %d has fewer coefficients than basis functions", a);
+        A.cstride[a] = st;
+        st *= coef_shape[a];
+    }
+    for (int a = 0; a < ndim; ++a) {
+        NG_REQUIRE(d_first[a] && d_basis[a], "ng_interp_bspline: table %d is NULL", a);
+        NG_REQUIRE(dst_shape[a] >= 0, "ng_interp_bspline: negative target extent");
+        A.first[a] = d_first[a];
+        A.basis[a] = d_basis[a];
+        A.nb[a] = nbasis[a];
+        A.dshape[a] = dst_shape[a];
+        if (!scattered) total *= dst_shape[a];
+    }
+    if (scattered) total = dst_shape[0];
+    A.total = total;
+    if (total == 0) return NG_OK;
+    i64 grid = (total + 255) / 256;
+    if (grid > 148LL * 32) grid = 148LL * 32;
+    interp_bspline_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_coef, d_out, A);
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}

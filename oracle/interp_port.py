@@ -50,3 +50,24 @@ def linear_on_grid(values: np.ndarray, src_coords, dst_coords) -> np.ndarray:
     mesh = np.meshgrid(*dst_coords, indexing="ij")
     pts = np.array([m.reshape(-1) for m in mesh]).T
     return linear_points(values, src_coords, pts).reshape([len(d) for d in dst_coords])
+
+
+def bspline_from_tables(coef: np.ndarray, first, basis, scattered: bool = False) -> np.ndarray:
+    """SciPy's B-spline evaluation order (NdBSpline / BSpline): for every target, the (k+1)^d terms with the last
+    axis fastest, factor = ((1*b_0)*b_1)*..., value = value + c*factor.  `first[a]` / `basis[a]` are the per-axis
+    tables (first coefficient index, basis values) per target coordinate -- tensor-product targets unless
+    `scattered`, where every table is indexed by the point number."""
+    nd = coef.ndim
+    out_shape = [len(first[0])] if scattered else [len(f) for f in first]
+    res = np.zeros(out_shape)
+    for combo in itertools.product(*[range(b.shape[1]) for b in basis]):
+        factor = np.ones(out_shape)
+        idx = []
+        for a, j in enumerate(combo):
+            shp = [-1] if scattered else [1] * nd
+            if not scattered:
+                shp[a] = -1
+            factor = factor * basis[a][:, j].reshape(shp)
+            idx.append((first[a].astype(np.int64) + j).reshape(shp))
+        res = res + coef[tuple(idx)] * factor
+    return res

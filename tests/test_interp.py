@@ -44,10 +44,13 @@ def test_multigrid_levels_and_errors():
     with pytest.raises(ValueError, match="adjacent levels"):
         mg.transfer(np.zeros((16, 16)), 0, 2)
     g = ng.Grid(ax, ax)
-    with pytest.raises(NotImplementedError):
-        ng.Interpolator(g, np.zeros(g.shape))                        # default method is "cubic", like the reference
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match="not defined"):
         ng.Interpolator(g, np.zeros(g.shape), method="septic")
+    with pytest.raises(ValueError, match="not defined"):
+        ng.Interpolator(g, np.zeros(g.shape), method="quadratic")     # RegularGridInterpolator has no such method either
+    tiny = ng.Grid(ng.create_axis(ng.AxisType.EQUIDISTANT, 3, 0.0, 1.0), ax)
+    with pytest.raises(ValueError, match="requires at least"):
+        ng.Interpolator(tiny, np.zeros(tiny.shape), method="cubic")
     with pytest.raises(ValueError, match="out of bounds in dimension 1"):
         ng.interpol.axis_table(np.linspace(0, 1, 5), np.array([0.5, 1.5]), 1)
     i, x0, x1 = ng.interpol.axis_table(np.linspace(0, 1, 5), np.array([0.0, 0.25, 0.3, 1.0]), 0)
@@ -116,3 +119,56 @@ def test_transfer_large_against_oracle(gpu_ready):
     assert np.array_equal(down.cpu().numpy(), ref_down)
     up = mg.transfer(down, 1, 0)
     assert np.array_equal(up.cpu().numpy(), ip.linear_on_grid(ref_down, c1, c0))
+
+
+# ------------------------------------------------------------------------------------------ spline methods
+def _spline_cases():
+    z, meta = load_golden("spline_cases.npz")
+    for ci, (method, src, dst) in enumerate(meta["cases"]):
+        yield z, ci, method, ng.Grid(*build_axes(ng, src)), ng.Grid(*build_axes(ng, dst))
+
+
+def test_spline_tables_reproduce_reference_golden():
+    """Host side of the cubic / quadratic methods (SciPy's fit + basis tables) through the restated evaluation
+    order against the reference's results.  The fit is iterative in N-D (gcrotmk): equal to rounding across hosts."""
+    from numgrids_b200 import interpol
+    for z, ci, method, gs, gd in _spline_cases():
+        k = {"cubic": 3, "quadratic": 2}[method]
+        cs, cd = [a.coords for a in gs.axes], [a.coords for a in gd.axes]
+        for name in ("smooth", "noise"):
+            f, ref = z[f"c{ci}_{name}_f"], z[f"c{ci}_{name}_out"]
+            knots, coef = interpol.spline_fit(cs, f, k)
+            fi, bv = interpol.spline_tables(knots, k, cs, cd)
+            out = ip.bspline_from_tables(coef, fi, bv)
+            assert np.max(np.abs(out - ref)) <= 1e-9 * np.max(np.abs(ref)), (ci, name)
+    with pytest.raises(ValueError, match="out of bounds in dimension 0"):
+        interpol.spline_tables(knots, k, cs, [np.array([c[-1] + 1.0]) for c in cs])
+
+
+@pytest.mark.gpu
+def test_spline_interpolator_golden_and_scipy_order(gpu_ready):
+    """Device evaluation: equal to the golden vectors of the real reference (to the fit's portability) and
+    bit-identical to the restatement of SciPy's evaluation order fed with the same host tables."""
+    import torch
+    from numgrids_b200 import interpol
+    for z, ci, method, gs, gd in _spline_cases():
+        k = {"cubic": 3, "quadratic": 2}[method]
+        cs, cd = [a.coords for a in gs.axes], [a.coords for a in gd.axes]
+        for name in ("smooth", "noise"):
+            f, ref = z[f"c{ci}_{name}_f"], z[f"c{ci}_{name}_out"]
+            out = ng.Interpolator(gs, f, method=method)(gd)
+            assert isinstance(out, np.ndarray) and out.shape == gd.shape
+            assert np.max(np.abs(out - ref)) <= 1e-9 * np.max(np.abs(ref)), (ci, name)
+            knots, coef = interpol.spline_fit(cs, f, k)
+            assert np.array_equal(out, ip.bspline_from_tables(coef, *interpol.spline_tables(knots, k, cs, cd))), (ci, name)
+            out_d = ng.Interpolator(gs, torch.from_numpy(f).cuda(), method=method)(gd)
+            assert out_d.is_cuda and np.array_equal(out_d.cpu().numpy(), out)
+        f, pts, refp = z[f"c{ci}_noise_f"], z[f"c{ci}_pts"], z[f"c{ci}_pts_out"]
+        inter = ng.Interpolator(gs, f, method=method)
+        outp = inter([tuple(p) for p in pts])
+        assert np.max(np.abs(outp - refp)) <= 1e-9 * np.max(np.abs(refp)), ci
+        assert inter(tuple(pts[2])) == outp[2]
+        if method == "cubic":
+            assert ng.interpolate(gs, f, tuple(pts[3])) == outp[3]          # the reference's helper: always cubic
+        with pytest.raises(ValueError, match="out of bounds"):
+            inter(tuple(c[-1] + 1.0 for c in cs))
