@@ -2,15 +2,15 @@
 
 Drop-in for the reference's package surface (same names as numgrids/__init__.py): ``Grid``, ``MultiGrid``,
 ``CurvilinearGrid``, ``SphericalGrid``, ``CylindricalGrid``, ``PolarGrid``, ``create_axis`` / ``AxisType`` /
-``Axis``, ``Diff``, ``diff``, ``integrate`` / ``Integral``, ``interpolate`` / ``Interpolator`` (linear),
+``Axis``, ``Diff``, ``diff``, ``integrate`` / ``Integral``, ``interpolate`` / ``Interpolator``,
 ``BoundaryFace`` / ``DirichletBC`` / ``NeumannBC`` / ``RobinBC`` / ``apply_bcs``, ``ErrorEstimator`` /
 ``AdaptationResult`` / ``adapt`` / ``estimate_error``, ``save_grid`` / ``load_grid``.
 
 ``Diff.__call__`` and ``grid.laplacian/gradient/divergence/curl`` -- the hot path -- and the operators around it
 (boundary applies, quadrature, linear interpolation / multigrid transfer, refinement estimates) run hand-written
 CUDA kernels through the C ABI in ``include/numgrids_b200.h``; there is no CPU fallback.  Sparse-matrix assembly
-(``as_matrix``, ``apply_to_system``) and file I/O are host code.  Not provided: quadratic / cubic spline
-interpolation (global fits inside SciPy) and plotting.
+(``as_matrix``, ``apply_to_system``), the spline fit of the cubic ``Interpolator`` (SciPy's, as in the reference)
+and file I/O are host code.  Not provided: plotting.
 """
 __version__ = "0.1.0"
 
