@@ -44,6 +44,17 @@ def global_shape_for(n_gpus: int, scale: int):
     return tuple(max(16, s // scale) for s in g)
 
 
+def workload_config(n_gpus: int, scale: int):
+    """The `config` object both arms print (identical by construction, so the driver can see it is the same
+    workload): the CPU arm times the same operator on `cpu_sample_shape`, a sub-block of it, and reports a rate."""
+    return {"workload": "cfg5: fused Cartesian FD Laplacian Diff(g,2,0)+Diff(g,2,1)+Diff(g,2,2) "
+                        "(acc=4), 1024^3 points per GPU, last-axis slabs + halo exchange",
+            "global_shape": list(global_shape_for(n_gpus, scale)),
+            "cpu_sample_shape": list(cpu_sample_shape(scale, True)),
+            "field": "sin(2 pi X) cos(2 pi Y) exp(Z) from global coordinates",
+            "l2": "inputs (8 GiB in + 8 GiB out per GPU) are far larger than the 126 MB L2; no flush needed"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -107,6 +118,56 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+class NvmlSampler:
+    """In-process NVML polling (~1 kHz) of SM clock, power and throttle reasons: the timed region of the
+    headline is a few tens of milliseconds, which nvidia-smi's 100 ms loop barely sees."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.stop_flag, self.thread, self.h = gpu_index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.h = None
+
+    def _run(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+            except Exception:
+                break
+            time.sleep(0.0005)
+
+    def start(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self, t0=None, t1=None):
+        if self.thread is None:
+            return None
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)] or self.rows
+        if not rows:
+            return None
+        nv = self.nv
+        bits = 0
+        for r in rows:
+            bits |= int(r[3])
+        names = {"sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap, "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown}
+        sm = [r[1] for r in rows]
+        return {"samples": len(rows), "sm_mhz_median": statistics.median(sm), "sm_mhz_min": min(sm),
+                "power_w_max": max(r[2] for r in rows), "reasons": sorted(k for k, v in names.items() if bits & v)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -189,9 +250,7 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "cfg5: fused Cartesian FD Laplacian Diff(g,2,0)+Diff(g,2,1)+Diff(g,2,2) "
-                               "(acc=4), 1024^3 points per GPU, last-axis slabs + halo exchange",
-                   "global_shape": list(gshape), "sample_shape": list(shape)},
+        "config": workload_config(args.gpus, scale),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"each step = one Laplacian of a {shape[0]}x{shape[1]}x{shape[2]} sub-block of the "
                                    f"workload; C/OpenMP restatement of the reference path (oracle/pencil_c.c, "
@@ -215,6 +274,50 @@ def make_local_field(torch, gshape, z0, z1, device):
     fy = torch.cos(2 * np.pi * xs[1])[None, :, None]
     fz = torch.exp(xs[2][z0:z1])[None, None, :]
     return (fx * fy * fz).contiguous()
+
+
+def parity_check(torch, gshape, hs, z0, z1, out, dev):
+    """The timed output against the oracle: three 24-plane x blocks (both global x boundaries and the middle)
+    of this rank's slab, full y and z extent, bit for bit.  The oracle (oracle/pencil_c.c, the C restatement
+    pinned to the NumPy one) runs on the same input values -- the field regenerated on the device over the
+    block's planes +- 8 and the slab's z range +- 8 (the neighbour ranks' columns), copied to the host."""
+    from oracle import pencil_c
+    pencil_c.use_all_cores()
+    nx, Z = gshape[0], gshape[2]
+    ze0, ze1 = max(z0 - 8, 0), min(z1 + 8, Z)
+    xs = [torch.linspace(0, 1, n, dtype=torch.float64, device=dev) for n in gshape]
+    fx = torch.sin(2 * np.pi * xs[0])[:, None, None]
+    fy = torch.cos(2 * np.pi * xs[1])[None, :, None]
+    fz = torch.exp(xs[2][ze0:ze1])[None, None, :]
+    worst, equal, pts = 0.0, True, 0
+    mid = max(nx // 2 - 12, 0)
+    for a, b in ((0, min(24, nx)), (mid, min(mid + 24, nx)), (max(nx - 24, 0), nx)):
+        lo, hi = max(a - 8, 0), min(b + 8, nx)
+        blk = (fx[lo:hi] * fy * fz).contiguous().cpu().numpy()
+        ref = pencil_c.cartesian_laplacian3(blk, hs, 4)[a - lo:b - lo, :, z0 - ze0:z0 - ze0 + (z1 - z0)]
+        got = out[a:b].cpu().numpy()
+        equal = equal and bool(np.array_equal(got, ref))
+        den = float(np.max(np.abs(ref))) or 1.0
+        worst = max(worst, float(np.max(np.abs(got - ref))) / den)
+        pts += got.size
+    return equal, worst, pts
+
+
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Run this process (and first-touch its pinned buffers) on the CPUs NVML reports as local to the GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs local to GPU {gpu_index}"
+    except Exception as e:  # pragma: no cover
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
 
 
 def time_events(torch, fn, steps, warmup):
@@ -414,6 +517,62 @@ def per_config_extras(torch, ng, peak_gbs, quick):
     return out
 
 
+def multi_gpu_extras(torch, dist, ng, rank, world, dev, quick):
+    """N > 1: the other sharded paths of SURVEY 8(e), device-resident, max over ranks of the per-apply time.
+    (a) FFT along the SHARDED axis (slab -> pencil redistribution over NVLink peer memory, apply, and back):
+        cfg3 per GPU, global grid 512N x 512 x 1024, slabs 512N x 512 x 1024/N, pencils 512 x 512 x 1024;
+    (b) spherical Laplacian on phi slabs: Chebyshev r, theta local; FFT phi through the redistribution."""
+    from numgrids_b200.slab import SlabCurvilinear, SlabDiff
+    A = ng.AxisType
+    out = {}
+
+    def timed(fn, steps=5, warmup=2):
+        for _ in range(warmup):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    try:
+        b_ = 128 if quick else 512
+        nper = 256 if quick else 1024
+        g = ng.Grid(ng.create_axis(A.EQUIDISTANT, b_ * world, 0.0, 1.0), ng.create_axis(A.EQUIDISTANT, b_, 0.0, 1.0),
+                    ng.create_axis(A.EQUIDISTANT_PERIODIC, nper, 0.0, 2 * np.pi))
+        d = SlabDiff(g, 1, 2, rank=rank, nranks=world)
+        f = torch.randn(*d.local_shape, dtype=torch.float64, device=dev)
+        o = torch.empty_like(f)
+        ms = timed(lambda: d(f, out=o))
+        pts = int(np.prod(g.shape))
+        out["fft_on_sharded_axis"] = {
+            "global_shape": list(g.shape), "local_slab": list(d.local_shape), "ms": ms, "gpts": pts / ms / 1e6,
+            "exchange": "NVLink peer memory (symmetric)" if d._symm is not None and not d._symm_failed else "all_to_all_single"}
+        del f, o, d
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        out["fft_on_sharded_axis"] = {"error": repr(e)}
+    try:
+        nr = 64 if quick else 128
+        g = ng.SphericalGrid(ng.create_axis(A.CHEBYSHEV, nr, 0.5, 2.0), ng.create_axis(A.CHEBYSHEV, nr, 0.3, np.pi - 0.3),
+                             ng.create_axis(A.EQUIDISTANT_PERIODIC, 256 * world, 0.0, 2 * np.pi))
+        sc = SlabCurvilinear(g, rank=rank, nranks=world)
+        f = torch.randn(*sc.local_shape, dtype=torch.float64, device=dev)
+        ms = timed(lambda: sc.laplacian(f))
+        pts = int(np.prod(g.shape))
+        out["spherical_laplacian_phi_slabs"] = {"global_shape": list(g.shape), "local_slab": list(sc.local_shape),
+                                                "ms": ms, "gpts": pts / ms / 1e6}
+    except Exception as e:  # pragma: no cover
+        out["spherical_laplacian_phi_slabs"] = {"error": repr(e)}
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -440,12 +599,13 @@ def run_gpu_arm(args):
     f = make_local_field(torch, gshape, slab.z0, slab.z1, dev)
     out = torch.empty_like(f)
     local_pts = f.numel()
+    local_shape = list(f.shape)
     global_pts = int(np.prod(gshape))
     peak_gbs, peak_src = measured_peaks()
     lo_n, hi_n = neighbours(rank, world)
 
     kernel_ms = []
-    stencil_ev = []      # N > 1 with overlap: (start_A, end_A, start_B, end_B) of the two stencil launches
+    stencil_ev = []      # N > 1 with overlap: one dict of CUDA events per step (slab.py)
 
     def step(record=False):
         if world == 1:
@@ -475,22 +635,37 @@ def run_gpu_arm(args):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
+    nvml = NvmlSampler(local_rank)
     if rank == 0:
         sampler.start()
+        nvml.start()
         time.sleep(0.15)
     launches0 = _lib.launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step(record=True)
     e1.record()
     barrier()
+    t_host1 = time.perf_counter()
     launches = _lib.launch_count() - launches0
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        clocks["nvml_1khz"] = nvml.stop(t_host0, t_host1)
     k_ms = [a.elapsed_time(b) for a, b in kernel_ms]
-    k_ms += [e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in stencil_ev]
+    parts = None
+    if stencil_ev:
+        # the stencil of a step spans from the start of the interior launch to the join of the two streams
+        k_ms += [e["int0"].elapsed_time(e["join"]) for e in stencil_ev]
+        mean = lambda a, b: statistics.mean(e[a].elapsed_time(e[b]) for e in stencil_ev)
+        parts = {"interior_ms": mean("int0", "int1"), "boundary_ms": mean("edge0", "edge1"),
+                 "stencil_span_ms": mean("int0", "join")}
+        if "pack0" in stencil_ev[0]:
+            parts["pack_ms"] = mean("pack0", "pack1")
+            parts["signal_wait_ms"] = mean("pack1", "edge0")
     t = torch.tensor([elapsed_ms, statistics.mean(k_ms), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -498,31 +673,52 @@ def run_gpu_arm(args):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         elapsed_ms, kern_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+        if parts is not None:                       # per-part times: max over ranks
+            keys = sorted(parts)
+            pt = torch.tensor([parts[k] for k in keys], dtype=torch.float64, device=dev)
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+            parts = {k: float(v) for k, v in zip(keys, pt)}
     else:
         kern_ms = float(t[1])
     ms_per_step = elapsed_ms / args.steps
     value = global_pts / ms_per_step / 1e6
 
+    # ---- parity: every rank checks the array it just timed against the oracle (bit for bit)
+    try:
+        p_equal, p_err, p_pts = parity_check(torch, gshape, hs, slab.z0, slab.z1, out, dev)
+        pv = torch.tensor([0.0 if p_equal else 1.0, p_err, float(p_pts)], dtype=torch.float64, device=dev)
+        if world > 1:
+            pmax = pv.clone()
+            dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+            psum = pv.clone()
+            dist.all_reduce(psum, op=dist.ReduceOp.SUM)
+            pv = torch.stack([pmax[0], pmax[1], psum[2]])
+        parity = {"parity_checked": True, "bit_exact": bool(pv[0] == 0.0), "max_rel_linf": float(pv[1]),
+                  "points_compared": int(pv[2]),
+                  "sample": "per rank: x planes [0,24), [nx/2-12,nx/2+12), [nx-24,nx) of the timed output, full y/z "
+                            "extent, vs oracle/pencil_c.c (C restatement pinned to the NumPy one) on the same input"}
+    except Exception as e:  # pragma: no cover
+        parity = {"parity_checked": False, "error": repr(e)}
+
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region
     e2e = None
     try:
         e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        numa = bind_to_gpu_numa_node(local_rank)          # pinned buffers on the GPU's own NUMA node (first touch)
         h_in = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
         h_out = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
         h_in.copy_(f)
+        h_out.zero_()
         if world == 1:
             lap = _lib.load()
 
             def e2e_step():     # the C-ABI host call: H2D + kernel + D2H, synchronous
                 _lib.check(lap.ng_fdlap_apply_host(slab.plan.handle, h_in.data_ptr(), h_out.data_ptr()))
         else:
-            d_in = torch.empty_like(f)
+            slab.stencil_events = None
 
-            def e2e_step():
-                d_in.copy_(h_in, non_blocking=True)
-                slab(d_in, out=out, overlap=not args.no_overlap)
-                h_out.copy_(out, non_blocking=True)
-                torch.cuda.synchronize()
+            def e2e_step():     # chunked H2D || halo exchange || stencil || D2H per rank (slab.py)
+                slab.apply_host(h_in, h_out)
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -538,11 +734,20 @@ def run_gpu_arm(args):
         e2e = {"value": global_pts / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * local_pts * world,
                "d2h_bytes_per_step": 8 * local_pts * world, "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "matches_device_result": ok,
-               "path": "ng_fdlap_apply_host (C ABI, pinned host buffers)" if world == 1 else
-                       "pinned H2D + slab apply + D2H per rank"}
+               "path": "ng_fdlap_apply_host (C ABI, pinned host buffers, chunked 3-stream pipeline)" if world == 1 else
+                       "SlabLaplacian.apply_host per rank: chunked H2D || per-chunk halo exchange || stencil || D2H",
+               "host_numa_binding": numa}
         del h_in, h_out
     except Exception as e:  # pragma: no cover
         e2e = {"value": None, "unit": UNIT, "error": repr(e), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+    multi = None
+    if world > 1 and not args.no_extras:
+        out = None
+        if getattr(slab, "_host_state", None):
+            slab._host_state = None
+        torch.cuda.empty_cache()
+        multi = multi_gpu_extras(torch, dist, ng, rank, world, dev, quick=scale > 1)
 
     if rank != 0:
         if world > 1:
@@ -566,8 +771,8 @@ def run_gpu_arm(args):
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "fdlap3d_ring2_kernel<2,4,8> (plane ring, TMA)", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "fp64_instr_per_point": 34,
-                "fp64_pipe_frac_at_1965MHz": 34.0 * local_pts / (kern_ms * 1e-3) / (148 * 64 * 1.965e9)}
+                "fp64_instr_per_point": 32,
+                "fp64_pipe_frac_at_1965MHz": 32.0 * local_pts / (kern_ms * 1e-3) / (148 * 64 * 1.965e9)}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample
     cpu_baseline = None
@@ -576,7 +781,7 @@ def run_gpu_arm(args):
 
     extras = None
     if world == 1 and not args.no_extras:
-        del out
+        out = None
         torch.cuda.empty_cache()
         extras = per_config_extras(torch, ng, peak_gbs, quick=scale > 1)
 
@@ -584,17 +789,16 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg5: fused Cartesian FD Laplacian Diff(g,2,0)+Diff(g,2,1)+Diff(g,2,2) "
-                               "(acc=4), 1024^3 points per GPU, last-axis slabs + halo exchange",
-                   "global_shape": list(gshape), "local_shape": list(f.shape),
-                   "l2": "inputs (8 GiB in + 8 GiB out per GPU) are far larger than the 126 MB L2; no flush needed",
-                   "field": "sin(2 pi X) cos(2 pi Y) exp(Z) from global coordinates",
-                   "halo_exchange": ("none (1 GPU)" if world == 1 else
-                                     ("NVLink peer stores from the pack kernel (symmetric memory) + per-neighbour signals"
-                                      if getattr(slab, "_symm", None) is not None else
-                                      "NCCL send/recv: " + str(getattr(slab, "_symm_error", "disabled"))))},
+        "config": workload_config(n_gpus, scale),
+        "details": {"local_shape": local_shape,
+                    "halo_exchange": ("none (1 GPU)" if world == 1 else
+                                      ("NVLink peer stores from the pack kernel (symmetric memory) + per-neighbour signals; "
+                                       "interior z tiles on the main stream, boundary z tiles behind the signals on a side stream"
+                                       if getattr(slab, "_symm", None) is not None else
+                                       "NCCL send/recv: " + str(getattr(slab, "_symm_error", "disabled"))))},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-        "clocks": clocks, "per_config": extras,
+        "clocks": clocks, "parity": parity, "parity_checked": bool(parity.get("parity_checked") and parity.get("bit_exact")),
+        "step_parts": parts, "per_config": extras if extras is not None else multi,
     }
     print(json.dumps(line))
     if world > 1:

@@ -78,6 +78,12 @@ const char* ng_last_error(void);
 int ng_device_count(void);
 /* number of kernels this library launched since load (for bench.py's gpu_launches) */
 int64_t ng_launch_count(void);
+/* name of the kernel instance the calling thread launched last ("" before the first launch): lets a test
+ * assert that the instance it means to check against the oracle is the one that ran */
+const char* ng_last_kernel(void);
+/* Tuning / A-B switches (NG_* environment variables) are read once per call site and cached; call this
+ * after changing the environment to make the library read them again.  Not needed in production. */
+void ng_tuning_reload(void);
 
 /* ---- finite differences: FiniteDifferenceDiff / LogDiff ------------------------------------
  * Replaces findiff.FinDiff(axis, h, order, acc)(f) behind numgrids/diff.py:88 and :259-262.
@@ -172,6 +178,10 @@ int ng_fdlap_apply_slab_range(const ng_plan* plan, const double* d_in, double* d
 int ng_fdlap_apply_slab_part(const ng_plan* plan, const double* d_in, double* d_out,
                              const double* d_lo_halo, const double* d_hi_halo, int z_part, void* stream);
 int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out);
+/* ng_fd_pack_halo for the planes [x_begin, x_end) of axis 0 only (rows x_begin*R .. x_end*R of the [rows][nb]
+ * buffers, R = rows per plane): lets a chunked host pipeline exchange halos chunk by chunk. */
+int ng_fdlap_pack_halo_range(const ng_plan* plan, const double* d_in, double* d_lo_planes,
+                             double* d_hi_planes, int64_t x_begin, int64_t x_end, void* stream);
 
 /* ---- curvilinear composites: CurvilinearGrid.gradient/divergence/laplacian/curl ---------------
  * numgrids/curvilinear.py:153-317.  axis_plans[i] is the first-derivative plan of axis i

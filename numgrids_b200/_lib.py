@@ -48,6 +48,8 @@ SIGNATURES = {
     "ng_last_error": (C.c_char_p, []),
     "ng_device_count": (C.c_int, []),
     "ng_launch_count": (C.c_int64, []),
+    "ng_last_kernel": (C.c_char_p, []),
+    "ng_tuning_reload": (None, []),
     "ng_fd_plan_create": (C.c_int, [C.c_int, _I64, C.c_int, C.c_int, _D, _I32, C.c_int, _D, _I32, _D,
                                     _I32, C.c_double, _D, _PP]),
     "ng_cheb_plan_create": (C.c_int, [C.c_int, _I64, C.c_int, _D, C.c_int, _PP]),
@@ -67,6 +69,7 @@ SIGNATURES = {
     "ng_fdlap_apply_slab_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "ng_fdlap_apply_slab_part": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "ng_fdlap_apply_host": (C.c_int, [_P, _P, _P]),
+    "ng_fdlap_pack_halo_range": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "ng_curv_plan_create": (C.c_int, [C.c_int, _I64, _PP, _PP]),
     "ng_curv_set_coef": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int64, _I64]),
     "ng_curv_laplacian": (C.c_int, [_P, _P, _P, _P]),
@@ -125,6 +128,16 @@ def require_gpu() -> None:
 
 def launch_count() -> int:
     return int(load().ng_launch_count())
+
+
+def last_kernel() -> str:
+    """Name of the kernel instance this thread launched last (tests pin kernel selection with it)."""
+    return load().ng_last_kernel().decode()
+
+
+def tuning_reload() -> None:
+    """Make the library re-read its NG_* tuning switches from the environment."""
+    load().ng_tuning_reload()
 
 
 # ---------------------------------------------------------------- small ctypes helpers

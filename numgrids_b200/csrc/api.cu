@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -18,6 +19,41 @@ void ng_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
+}
+
+thread_local const char* t_ng_last_kernel = "";
+static std::atomic<int> g_env_gen{0};
+
+long long ng_env_cached(NgEnvCache* c, const char* name, long long dflt) {
+    const int gen = g_env_gen.load(std::memory_order_acquire);
+    if (c->gen.load(std::memory_order_acquire) == gen) return c->val.load(std::memory_order_relaxed);
+    const char* s = getenv(name);
+    const long long v = s ? atoll(s) : dflt;
+    c->val.store(v, std::memory_order_relaxed);
+    c->gen.store(gen, std::memory_order_release);
+    return v;
+}
+
+int ng_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return d;
+}
+
+// Device memory of a plan lives on the device that was current when its first table was uploaded.
+int ng_plan_bind_device(ng_plan* p) {
+    const int d = ng_current_device();
+    if (p->device < 0) p->device = d;
+    NG_REQUIRE(p->device == d, "plan tables live on CUDA device %d but the current device is %d", p->device, d);
+    return NG_OK;
+}
+
+int ng_check_plan_device(const ng_plan* p, const char* who) {
+    if (!p || p->device < 0) return NG_OK;
+    const int d = ng_current_device();
+    NG_REQUIRE(p->device == d, "%s: the plan was created on CUDA device %d but the current device is %d "
+               "(create one plan per device)", who, p->device, d);
+    return NG_OK;
 }
 
 int ng_fdlap_upload_params(ng_plan* p);
@@ -46,6 +82,8 @@ int set_shape(ng_plan* p, int ndim, const int64_t* shape, int axis) {
 }
 
 int upload(ng_plan* p, double** d_dst, const double* h_src, i64 count) {
+    int rc = ng_plan_bind_device(p);
+    if (rc) return rc;
     NG_CUDA_OK(cudaMalloc((void**)d_dst, sizeof(double) * (size_t)(count > 0 ? count : 1)));
     p->device_bytes += sizeof(double) * count;
     if (count > 0)
@@ -78,6 +116,8 @@ int require_device() {
 int ensure_stage(ng_plan* p, int nbuf_in) {
     const i64 need = p->size * nbuf_in;
     if (p->stage_elems >= need && p->d_stage_in && p->d_stage_out) return NG_OK;
+    int rc = ng_plan_bind_device(p);
+    if (rc) return rc;
     if (p->d_stage_in) cudaFree(p->d_stage_in);
     if (p->d_stage_out) cudaFree(p->d_stage_out);
     p->d_stage_in = p->d_stage_out = nullptr;
@@ -119,6 +159,8 @@ void ng_fuse_to_dev(const ng_plan* p, const ng_fuse* f, FuseDev* out) {
 
 int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                  cudaStream_t st) {
+    int rc = ng_check_plan_device(p, "apply");
+    if (rc) return rc;
     switch (p->kind) {
         case PK_FD: return ng_fd_launch(p, in, out, F, nullptr, nullptr, st);
         case PK_CHEB: return ng_dense_launch(p, in, out, F, st);
@@ -134,6 +176,8 @@ extern "C" {
 int ng_abi_version(void) { return NG_ABI_VERSION; }
 const char* ng_last_error(void) { return t_err; }
 int64_t ng_launch_count(void) { return g_ng_launches.load(); }
+const char* ng_last_kernel(void) { return t_ng_last_kernel; }
+void ng_tuning_reload(void) { g_env_gen.fetch_add(1, std::memory_order_acq_rel); }
 
 int ng_device_count(void) {
     int n = 0;
@@ -230,7 +274,7 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h
     p->kind = PK_FFT;
     const i64 n = p->n;
     const bool pow2 = n >= 2 && (n & (n - 1)) == 0 && n <= 8192;
-    static const bool force_dense = getenv("NG_FFT_DENSE") && atoi(getenv("NG_FFT_DENSE"));
+    const bool force_dense = NG_ENV_INT("NG_FFT_DENSE", 0) != 0;
     if (pow2 && !(force_dense && h_D)) {
         p->fft_pow2 = 1;
         int l = 0;
@@ -312,12 +356,18 @@ static int host_pipeline(ng_plan* plan, const double* h_in, double* h_out, i64 h
     if (rc) return rc;
     const i64 n0 = plan->shape[0];
     const i64 plane = plan->size / n0;                       // elements per axis-0 plane
-    static cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-    if (!st[0])
-        for (int i = 0; i < 3; ++i) NG_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    // three staging streams per device, created on first use
+    static std::mutex st_mutex;
+    static cudaStream_t st_all[64][3] = {};
+    cudaStream_t* st = st_all[ng_current_device() & 63];
+    {
+        std::lock_guard<std::mutex> lock(st_mutex);
+        if (!st[0])
+            for (int i = 0; i < 3; ++i) NG_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    }
     // ~256 MiB chunks, at least 8 planes, at most 64 chunks
     i64 chunk_elems = 32LL << 20;                             // 256 MiB
-    if (const char* e = getenv("NG_HOST_CHUNK_MB")) chunk_elems = (i64)atoi(e) * 131072;   // tests
+    if (const i64 mb = NG_ENV_INT("NG_HOST_CHUNK_MB", 0)) chunk_elems = mb * 131072;   // tests
     if (chunk_elems < 1) chunk_elems = 1;
     i64 cp = chunk_elems / (plane > 0 ? plane : 1);
     if (cp < 8) cp = 8;
@@ -379,6 +429,7 @@ int ng_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
     NG_REQUIRE(plan->kind == PK_FD || plan->kind == PK_CHEB || plan->kind == PK_FFT,
                "plan kind %d cannot be applied with ng_apply_host", plan->kind);
     int rc = require_device();
+    if (!rc) rc = ng_check_plan_device(plan, "ng_apply_host");
     if (rc) return rc;
     // pencils along an axis other than 0 are independent across axis-0 planes: chunk a shallow view
     const bool chunkable = plan->axis != 0 && plan->ndim > 1;
@@ -482,6 +533,7 @@ int ng_fdlap_apply_slab_part(const ng_plan* plan, const double* d_in, double* d_
 int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out) {
     NG_REQUIRE(plan && plan->kind == PK_FDLAP && h_in && h_out, "ng_fdlap_apply_host: bad arguments");
     int rc = require_device();
+    if (!rc) rc = ng_check_plan_device(plan, "ng_fdlap_apply_host");
     if (rc) return rc;
     // output planes [a, b) need input planes [a-2, b+2) (and up to 5 further in on the global
     // boundary, which the >= 8-plane chunks cover): run chunk k when chunk k+1 has landed

@@ -52,6 +52,42 @@ extern std::atomic<long long> g_ng_launches;
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// tuning switches, kernel trace, per-device function attributes
+// ---------------------------------------------------------------------------------------------
+// Tuning / A-B switches come from the environment but are read ONCE per call site: the value is
+// cached until ng_tuning_reload() (tests and tuning tools call it after changing the environment),
+// so the hot path never calls getenv().
+struct NgEnvCache {
+    std::atomic<int> gen{-1};
+    std::atomic<long long> val{0};
+};
+long long ng_env_cached(NgEnvCache* c, const char* name, long long dflt);
+#define NG_ENV_INT(name, dflt)                                  \
+    ([]() -> long long {                                        \
+        static NgEnvCache cache_;                               \
+        return ng_env_cached(&cache_, name, (long long)(dflt)); \
+    }())
+
+// name of the kernel instance the calling thread launched last (ng_last_kernel(); tests assert that
+// the instance they mean to check is the one that ran)
+extern thread_local const char* t_ng_last_kernel;
+#define NG_TRACE(name) (t_ng_last_kernel = (name))
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).
+// Usage: NG_FUNC_SMEM(bytes, kernel<template, args>);
+int ng_current_device();
+#define NG_FUNC_SMEM(bytes, ...)                                                                  \
+    do {                                                                                          \
+        static std::atomic<unsigned long long> done_{0};                                          \
+        const unsigned long long bit_ = 1ull << (ng_current_device() & 63);                       \
+        if (!(done_.load(std::memory_order_relaxed) & bit_)) {                                    \
+            NG_CUDA_OK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)(bytes)));                                       \
+            done_.fetch_or(bit_, std::memory_order_relaxed);                                      \
+        }                                                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
 // tables passed to kernels by value
 // ---------------------------------------------------------------------------------------------
 struct FdTables {
@@ -93,6 +129,7 @@ struct ng_plan {
     i64 size = 1;
     i64 outer = 1, n = 1, inner = 1;   // [outer][n][inner] view around `axis`
     i64 device_bytes = 0;
+    int device = -1;                   // CUDA device that holds the plan's tables (-1: the plan owns no device memory)
 
     // PK_FD
     FdTables fd;
@@ -145,6 +182,10 @@ int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const doubl
                     const double* hi, i64 xbeg, i64 xend, int zmode, cudaStream_t st);
 int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                  cudaStream_t st);
+// NG_OK when the calling thread's current device is the one the plan's tables live on
+int ng_check_plan_device(const ng_plan* p, const char* who);
+// call before the first cudaMalloc on behalf of a plan: records (or checks) the owning device
+int ng_plan_bind_device(ng_plan* p);
 void ng_fuse_to_dev(const ng_plan* p, const ng_fuse* f, FuseDev* out);
 
 // ---------------------------------------------------------------------------------------------

@@ -33,6 +33,8 @@ FuseDev base_fuse(const ng_plan* p) {
 
 int ensure_work(ng_plan* p) {
     if (p->d_work) return NG_OK;
+    int rc = ng_plan_bind_device(p);
+    if (rc) return rc;
     NG_CUDA_OK(cudaMalloc((void**)&p->d_work, sizeof(double) * (size_t)p->size));
     p->device_bytes += sizeof(double) * p->size;
     return NG_OK;
@@ -43,7 +45,7 @@ int check_curv(const ng_plan* p, const char* who) {
         ng_set_error("%s: curvilinear plan required", who);
         return NG_EINVAL;
     }
-    return NG_OK;
+    return ng_check_plan_device(p, who);
 }
 
 #define NG_NEED(c, what)                                                           \
@@ -109,6 +111,8 @@ int ng_curv_set_coef(ng_plan* p, int kind, int index, const double* h_values, in
     NG_REQUIRE(reach < count, "ng_curv_set_coef: strides reach element %lld of a %lld-element table",
                (long long)reach, (long long)count);
     if (c->d_ptr) { cudaFree(c->d_ptr); p->device_bytes -= sizeof(double) * c->count; c->d_ptr = nullptr; }
+    rc = ng_plan_bind_device(p);
+    if (rc) return rc;
     NG_CUDA_OK(cudaMalloc((void**)&c->d_ptr, sizeof(double) * (size_t)count));
     NG_CUDA_OK(cudaMemcpy(c->d_ptr, h_values, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice));
     p->device_bytes += sizeof(double) * count;

@@ -402,18 +402,16 @@ int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev&
     const size_t smem = (size_t)2 * FK * (FM + TFN + (LASTAX ? 2 : 0)) * sizeof(double);
 #define NG_DENSE_FAST(FU)                                                                       \
     do {                                                                                        \
-        static bool attr_done = false;                                                          \
-        if (!attr_done) {                                                                       \
-            NG_CUDA_OK(cudaFuncSetAttribute(dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN>,         \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                            (int)smem));                                        \
-            attr_done = true;                                                                   \
-        }                                                                                       \
+        NG_FUNC_SMEM(smem, dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN>);                 \
         dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN><<<grid, 256, smem, st>>>(                    \
             in, out, Mt, (int)p->n, p->inner, p->axis, F, npitch, p->outer, tiles_per_o);       \
     } while (0)
     if (F.any) NG_DENSE_FAST(true); else NG_DENSE_FAST(false);
 #undef NG_DENSE_FAST
+    NG_TRACE(GEN ? (LASTAX ? "dense_fast<gen,lastax>" : "dense_fast<gen>")
+                 : NCP == 4 ? (LASTAX ? "dense_fast<ncp4,lastax>" : "dense_fast<ncp4>")
+                 : NCP == 2 ? (LASTAX ? "dense_fast<ncp2,lastax>" : "dense_fast<ncp2>")
+                            : (LASTAX ? "dense_fast<ncp1,lastax>" : "dense_fast<ncp1>"));
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -421,8 +419,7 @@ int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev&
 template <bool DESC, bool FMA>
 int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     const i64 big_tiles = (p->outer * p->inner / FN) * (p->n / FM);
-    const char* e = getenv("NG_DENSE_NCP");
-    const int force = e ? atoi(e) : 0;
+    const int force = (int)NG_ENV_INT("NG_DENSE_NCP", 0);     // tuning: force the columns-per-thread variant
     if (p->inner == 1) {                       // contiguous contraction axis
         const bool wide_l = force ? force == 4 : (big_tiles >= 4 * 148 && p->outer % FN == 0);
         if (wide_l && p->outer % FN == 0) return launch_fast2<DESC, FMA, 4, true>(p, in, out, F, st);
@@ -439,8 +436,7 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
 int fast_mode(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
     if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return 0;
     if (F.any && p->inner != 1 && F.shape[F.vec_axis] % 2 != 0) return 0;
-    const char* e = getenv("NG_DENSE_FAST");          // tuning / A-B: 0 = fallback only, 2 = general kernel even on exact shapes
-    const int force = e ? atoi(e) : 1;
+    const int force = (int)NG_ENV_INT("NG_DENSE_FAST", 1);    // tuning / A-B: 0 = fallback only, 2 = general kernel even on exact shapes
     if (force == 0) return 0;
     const bool exact = p->n % FM == 0 && (p->inner == 1 ? p->outer % 32 == 0 : p->inner % 32 == 0);
     if (exact && force != 2) return 1;
@@ -465,6 +461,7 @@ int launch3(const ng_plan* p, const double* in, double* out, const FuseDev& F, c
     else
         dense_apply_kernel<LAST, DESC, FMA, false><<<grid, NT, 0, st>>>(
             in, out, p->d_Mt, p->outer, (int)p->n, p->inner, p->axis, F);
+    NG_TRACE("dense_apply");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }

@@ -325,6 +325,7 @@ static int launch_stream(const ng_plan* p, const double* in, double* out, const 
         if (F.any) { if (p->d_xdiv) NG_FD_MARCH(true, true); else NG_FD_MARCH(true, false); }
         else       { if (p->d_xdiv) NG_FD_MARCH(false, true); else NG_FD_MARCH(false, false); }
 #undef NG_FD_MARCH
+        NG_TRACE("fd_march");
     } else {
         return ng_fd_row_launch(P, p, in, out, F, lo, hi, st);
     }
@@ -339,14 +340,12 @@ int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev&
     {
         // streaming kernels: 128-bit accesses throughout, so pairs along the contiguous direction must
         // be aligned and must not straddle a row of the innermost grid axis
-        const char* se = getenv("NG_FD_STREAM");          // tuning / A-B checks: 0 = gather kernel only
-        const bool off = se && atoi(se) == 0;
+        const bool off = NG_ENV_INT("NG_FD_STREAM", 1) == 0;   // tuning / A-B checks: 0 = gather kernel only
         const int P = off ? 0 : central_half_width(p->fd);
         const i64 contiguous = p->inner > 1 ? p->inner : p->n;
         // tiny arrays are launch/latency-bound: the gather kernel's one-load-deep threads finish sooner
         // than a march (NG_FD_STREAM_MIN: points from which the march kernel takes over)
-        const char* me = getenv("NG_FD_STREAM_MIN");
-        const i64 march_min = me ? atoll(me) : (1LL << 21);
+        const i64 march_min = NG_ENV_INT("NG_FD_STREAM_MIN", 1LL << 21);
         const bool ok = P > 0 && aligned && contiguous % 2 == 0 && p->n >= 2 * P + 1 && p->n >= p->fd.n_side &&
                         p->n < (1LL << 30) &&
                         (p->inner == 1 || p->size >= march_min) &&
@@ -381,6 +380,7 @@ int ng_fd_launch(const ng_plan* p, const double* in, double* out, const FuseDev&
         else       { if (halo) NG_FD_GO(1, false, true); else NG_FD_GO(1, false, false); }
     }
 #undef NG_FD_GO
+    NG_TRACE("fd_apply");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -398,6 +398,35 @@ extern "C" int ng_fd_pack_halo_fused(const ng_plan* p, const double* d_in, const
     if (total == 0) return NG_OK;
     fd_pack_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         d_in, d_lo_planes, d_hi_planes, p->outer, p->n, p->inner, p->fd.nb, F);
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+// Planes [x_begin, x_end) of axis 0 only: rows x_begin*R .. x_end*R of the [rows][nb] halo buffers
+// (R = rows per axis-0 plane).  The chunked host pipeline exchanges halos chunk by chunk with it.
+extern "C" int ng_fdlap_pack_halo_range(const ng_plan* p, const double* d_in, double* d_lo_planes,
+                                        double* d_hi_planes, int64_t x_begin, int64_t x_end, void* stream) {
+    NG_REQUIRE(p && p->kind == PK_FDLAP && p->ndim >= 2, "ng_fdlap_pack_halo_range: Laplacian plan (ndim >= 2) required");
+    NG_REQUIRE(d_in, "ng_fdlap_pack_halo_range: null input");
+    NG_REQUIRE(0 <= x_begin && x_begin <= x_end && x_end <= p->shape[0],
+               "ng_fdlap_pack_halo_range: [%lld, %lld) is not inside axis 0", (long long)x_begin, (long long)x_end);
+    const int nb = p->lap[p->ndim - 1].nb;
+    const i64 n = p->shape[p->ndim - 1];
+    const i64 per_plane = p->size / n / p->shape[0];           // rows per axis-0 plane
+    const i64 r0 = x_begin * per_plane, rows = (x_end - x_begin) * per_plane;
+    if (rows == 0) return NG_OK;
+    const double* src = d_in + r0 * n;
+    double* lo = d_lo_planes ? d_lo_planes + r0 * nb : nullptr;
+    double* hi = d_hi_planes ? d_hi_planes + r0 * nb : nullptr;
+    const bool al = (((uintptr_t)src | (uintptr_t)lo | (uintptr_t)hi) & 15) == 0;
+    if (nb == 2 && n % 2 == 0 && al) {
+        fd_pack_halo_last2_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(
+            src, (double2*)lo, (double2*)hi, rows, n);
+    } else {
+        FuseDev F;
+        memset(&F, 0, sizeof(F));
+        fd_pack_halo_kernel<<<grid_for(rows * nb, 256), 256, 0, (cudaStream_t)stream>>>(src, lo, hi, rows, n, 1, nb, F);
+    }
     NG_LAUNCH_CHECK();
     return NG_OK;
 }

@@ -197,15 +197,16 @@ int launch_row(const ng_plan* p, const double* in, double* out, const FuseDev& F
         fd_row_kernel<P, FU, HA, UU><<<(unsigned)((rows * gpr + 7) / 8), 256, 0, st>>>(                    \
             in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, lo, hi, gpr);                                \
     } while (0)
-        const char* ue = getenv("NG_FD_ROW_U");               // tuning: force the chunks per warp
+        const int ue = (int)NG_ENV_INT("NG_FD_ROW_U", 0);     // tuning: force the chunks per warp
         // measured at 1024^3 / 8192^2 (profiles/r01_tune_fd.txt): U = 1 0.60 / 0.65, U = 2 0.63 / 0.76,
         // U = 4 0.80 / 0.92, U = 8 0.69 / 0.58 of the HBM peak
-        const int uu = ue ? atoi(ue) : (!deep ? 1 : 4);
+        const int uu = ue ? ue : (!deep ? 1 : 4);
 #define NG_FD_ROW2(FU, HA) do { if (uu >= 4) NG_FD_ROW(FU, HA, 4); else NG_FD_ROW(FU, HA, 1); } while (0)
         if (F.any) { if (halo) NG_FD_ROW2(true, true); else NG_FD_ROW2(true, false); }
         else       { if (halo) NG_FD_ROW2(false, true); else NG_FD_ROW2(false, false); }
 #undef NG_FD_ROW2
 #undef NG_FD_ROW
+        NG_TRACE(uu >= 4 ? "fd_row<u4>" : "fd_row<u1>");
     }
     NG_LAUNCH_CHECK();
     return NG_OK;

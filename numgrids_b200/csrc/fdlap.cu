@@ -70,6 +70,8 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
                     const double* hi, i64 xbeg, i64 xend, int zmode, cudaStream_t st) {
     if (p->size == 0 || xend <= xbeg) return NG_OK;
+    int drc = ng_check_plan_device(p, "ng_fdlap_apply");
+    if (drc) return drc;
     bool handled = false;
     int rc = ng_fdlap3d_try_launch(p, in, out, lo, hi, (int)xbeg, (int)xend, zmode, st, &handled);
     if (rc != NG_OK || handled) return rc;
@@ -80,6 +82,7 @@ int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const doubl
     if (g > 148LL * 64) g = 148LL * 64;
     fdlap_generic_kernel<<<(unsigned)g, 256, 0, st>>>(in, out, (const LapParams*)p->d_M, first, last,
                                                       lo, hi);
+    NG_TRACE("fdlap_generic");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -96,6 +99,8 @@ int ng_fdlap_upload_params(ng_plan* p) {
         s *= p->shape[a];
     }
     for (int a = 0; a < p->ndim; ++a) hp.t[a] = p->lap[a];
+    int brc = ng_plan_bind_device(p);
+    if (brc) return brc;
     NG_CUDA_OK(cudaMalloc((void**)&p->d_M, sizeof(LapParams)));
     p->device_bytes += sizeof(LapParams);
     NG_CUDA_OK(cudaMemcpy(p->d_M, &hp, sizeof(LapParams), cudaMemcpyHostToDevice));

@@ -148,13 +148,7 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
     const bool last = p->inner == 1;
 #define NG_FFT_GO(LA, FU)                                                                        \
     do {                                                                                         \
-        static bool attr_done = false;                                                           \
-        if (!attr_done) {                                                                        \
-            NG_CUDA_OK(cudaFuncSetAttribute(fft_diff_kernel<LA, FU>,                             \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                            200 * 1024));                                        \
-            attr_done = true;                                                                    \
-        }                                                                                        \
+        NG_FUNC_SMEM(200 * 1024, fft_diff_kernel<LA, FU>);                                       \
         fft_diff_kernel<LA, FU><<<(unsigned)nblk, FFT_NT, smem, st>>>(                           \
             in, out, (const double2*)p->d_W, (const double2*)p->d_tw, p->outer, n, p->log2n,     \
             p->inner, P, F);                                                                     \
@@ -162,6 +156,7 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
     if (last) { if (F.any) NG_FFT_GO(true, true); else NG_FFT_GO(true, false); }
     else      { if (F.any) NG_FFT_GO(false, true); else NG_FFT_GO(false, false); }
 #undef NG_FFT_GO
+    NG_TRACE("fft_radix2");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }

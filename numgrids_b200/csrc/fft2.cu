@@ -531,10 +531,8 @@ int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& 
 #define NG_FFT2_RING(FU)                                                                          \
     do {                                                                                          \
         static int per_sm = 0;                           /* persistent: resident CTAs per SM */   \
+        NG_FUNC_SMEM(smem, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>);                         \
         if (!per_sm) {                                                                            \
-            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>,         \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                            (int)smem));                                          \
             int occ = 0;                                                                          \
             NG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                             \
                 &occ, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>, 32 * NW, smem));              \
@@ -546,6 +544,7 @@ int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& 
     } while (0)
     if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false);
 #undef NG_FFT2_RING
+    NG_TRACE("fft2pass_ring");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -560,19 +559,14 @@ int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cu
     const size_t smem = (size_t)WARPS * TPW * RT * (R2 + 1) * sizeof(double2);
 #define NG_FFT2_GO(FU)                                                                            \
     do {                                                                                          \
-        static bool attr_done = false;                                                            \
-        if (!attr_done) {                                                                         \
-            NG_CUDA_OK(cudaFuncSetAttribute(fft2pass_kernel<RT, R2, FU, MINB, STR>,                     \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                            (int)smem));                                          \
-            attr_done = true;                                                                     \
-        }                                                                                         \
+        NG_FUNC_SMEM(smem, fft2pass_kernel<RT, R2, FU, MINB, STR>);                               \
         fft2pass_kernel<RT, R2, FU, MINB, STR><<<grid, 32 * WARPS, smem, st>>>(                         \
             in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, p->inner, p->axis,    \
             (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F);       \
     } while (0)
     if (F.any) NG_FFT2_GO(true); else NG_FFT2_GO(false);
 #undef NG_FFT2_GO
+    NG_TRACE(STR ? "fft2pass<strided>" : "fft2pass");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -584,13 +578,11 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
                        cudaStream_t st, bool* handled) {
     *handled = false;
     if (!p->d_Wn || !p->d_twn) return NG_OK;
-    const char* e = getenv("NG_FFT_TWOPASS");
-    if (e && atoi(e) == 0) return NG_OK;
+    if (NG_ENV_INT("NG_FFT_TWOPASS", 1) == 0) return NG_OK;
     int rc = NG_OK;
     if (p->inner != 1) {
         // transform axis not contiguous: the one-shot kernel with strided pencils (adjacent columns per CTA)
-        const char* se = getenv("NG_FFT_STRIDED");      // A/B: 0 = radix-2 shared-memory fallback (fft.cu)
-        if (se && atoi(se) == 0) return NG_OK;
+        if (NG_ENV_INT("NG_FFT_STRIDED", 1) == 0) return NG_OK;   // A/B: 0 = radix-2 shared-memory fallback (fft.cu)
         switch (p->n) {
             case 1024: rc = launch<32, 32, 1, true>(p, in, out, F, st); break;
             case 512: rc = launch<32, 16, 1, true>(p, in, out, F, st); break;
@@ -602,11 +594,11 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
         *handled = (rc == NG_OK);
         return rc;
     }
-    const char* pfe = getenv("NG_FFT_PREFETCH");        // tuning: 0 = one-shot kernel, no input staging
     // the persistent ring kernel needs enough pencils to fill 148 CTAs and a 16-byte aligned input
-    const bool ring = !(pfe && atoi(pfe) == 0) && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * 6;
-    const char* ve = getenv("NG_FFT_VARIANT");          // tuning: warps / input stages per CTA
-    const int variant = ve ? atoi(ve) : (p->n >= 512 ? 2 : 3);   // measured: profiles/r01_tune_fft.txt
+    // (NG_FFT_PREFETCH, tuning: 0 = one-shot kernel, no input staging)
+    const bool ring = NG_ENV_INT("NG_FFT_PREFETCH", 1) != 0 && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * 6;
+    const int ve = (int)NG_ENV_INT("NG_FFT_VARIANT", 0);          // tuning: warps / input stages per CTA
+    const int variant = ve ? ve : (p->n >= 512 ? 2 : 3);   // measured: profiles/r01_tune_fft.txt
     switch (p->n) {
         case 1024:
             rc = !ring ? launch<32, 32, 1>(p, in, out, F, st)

@@ -223,7 +223,7 @@ class SlabLaplacian:
         lo_n, hi_n = neighbours(self.rank, self.nranks)
         lo_h = b["lo_halo"] if lo_n is not None else None
         hi_h = b["hi_halo"] if hi_n is not None else None
-        tm = getattr(self, "stencil_events", None)        # optional [(e0, e1, e2, e3), ...] sink for bench.py
+        tm = getattr(self, "stencil_events", None)        # optional sink for bench.py: one dict of events per step
         if not overlap or len(self.local_shape) != 3:
             exchange_halos(b["lo_planes"], b["hi_planes"], b["lo_halo"], b["hi_halo"], self.rank, self.nranks,
                            self.group)
@@ -236,20 +236,19 @@ class SlabLaplacian:
         with t.cuda.stream(comm):
             exchange_halos(b["lo_planes"], b["hi_planes"], b["lo_halo"], b["hi_halo"], self.rank, self.nranks,
                            self.group)
-            ev = comm.record_event()
-        if tm is not None:
-            e = [t.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record()
-        self.apply_part(f, out, 1, lo_h, hi_h)            # interior z tiles: no halo dependence
-        if tm is not None:
-            e[1].record()
-        main.wait_event(ev)
-        if tm is not None:
-            e[2].record()
+            arrived = comm.record_event()
+        ev = {k: t.cuda.Event(enable_timing=True) for k in ("int0", "int1", "edge0", "edge1", "join")} \
+            if tm is not None else None
+        if ev: ev["int0"].record()
+        self.apply_part(f, out, 1)                        # interior z tiles: no halo dependence
+        if ev: ev["int1"].record()
+        main.wait_event(arrived)
+        if ev: ev["edge0"].record()
         self.apply_part(f, out, 2, lo_h, hi_h)            # first / last z tile (or everything on fallbacks)
-        if tm is not None:
-            e[3].record()
-            tm.append(tuple(e))
+        if ev:
+            ev["edge1"].record()
+            ev["join"].record()
+            tm.append(ev)
         return out
 
     # -- NVLink peer-memory exchange (pack kernel stores straight into the neighbours' halos) -------
@@ -268,6 +267,12 @@ class SlabLaplacian:
         return True
 
     def _call_symm(self, f, out):
+        """main stream: interior z tiles.  side stream: pack kernel (stores straight into the neighbours'
+        halo buffers) -> signals -> the two boundary z tiles.  The boundary launch needs no SM until the
+        interior launch has handed out its last CTAs, so it fills that launch's tail instead of following
+        it; the main stream joins the side stream at the end of the step.  Reuse of halo set q: my signal
+        of step s+1 is enqueued behind my boundary launch of step s on the same stream, and a neighbour
+        overwrites set q again only after it has seen that signal."""
         t = _device.torch()
         sh = self._symm
         q = sh.step & 1
@@ -276,30 +281,104 @@ class SlabLaplacian:
         if getattr(self, "_comm_stream", None) is None:
             self._comm_stream = t.cuda.Stream()
         comm = self._comm_stream
-        comm.wait_stream(main)            # f is ready; my previous stencil (reader of set q) is ordered before
+        tm = getattr(self, "stencil_events", None)        # optional sink for bench.py: one dict of events per step
+        ev = {k: t.cuda.Event(enable_timing=True) for k in
+              ("pack0", "pack1", "edge0", "edge1", "int0", "int1", "join")} if tm is not None else None
+        comm.wait_stream(main)            # f is ready
+        lo_h, hi_h = sh.mine(q)
         with t.cuda.stream(comm):
             to_lo, to_hi = sh.targets(q)
+            if ev: ev["pack0"].record()
             _lib.check(_lib.load().ng_fd_pack_halo(
                 self.plan.handle, f.data_ptr(), to_lo.data_ptr() if to_lo is not None else None,
                 to_hi.data_ptr() if to_hi is not None else None, _device.current_stream_ptr()), "ng_fd_pack_halo")
+            if ev: ev["pack1"].record()
             sh.signal_and_wait(q)
-            ev = comm.record_event()
-        lo_h, hi_h = sh.mine(q)
-        tm = getattr(self, "stencil_events", None)
-        if tm is not None:
-            e = [t.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record()
-        self.apply_part(f, out, 1, lo_h, hi_h)            # interior z tiles under the exchange
-        if tm is not None:
-            e[1].record()
-        main.wait_event(ev)
-        if tm is not None:
-            e[2].record()
-        self.apply_part(f, out, 2, lo_h, hi_h)
-        if tm is not None:
-            e[3].record()
-            tm.append(tuple(e))
+            if ev: ev["edge0"].record()
+            self.apply_part(f, out, 2, lo_h, hi_h)        # first / last z tile, neighbour planes staged by TMA
+            if ev: ev["edge1"].record()
+            done = comm.record_event()
+        if ev: ev["int0"].record()
+        self.apply_part(f, out, 1)                        # interior z tiles: never read a halo
+        if ev: ev["int1"].record()
+        main.wait_event(done)
+        if ev:
+            ev["join"].record()
+            tm.append(ev)
         return out
+
+    # -- host buffers in, host buffers out: chunked pipeline with per-chunk halo exchange ------------
+    def apply_host(self, h_in, h_out, chunk_mib=256):
+        """One distributed apply from this rank's slab in (pinned) HOST memory into `h_out` (host), the
+        multi-GPU counterpart of ``ng_fdlap_apply_host``.  The slab is cut into chunks of axis-0 planes;
+        per chunk k: H2D on a copy stream -> pack kernel stores the chunk's first/last z columns straight into
+        the neighbours' halo buffers + signals (side stream) -> stencil of chunk k-1 (it needs chunk k's first
+        two planes along x and its own halo rows) -> D2H of chunk k-1 on a second copy stream.  Both PCIe
+        directions, the NVLink halo traffic and the kernels overlap; the call returns when h_out is complete."""
+        t = _device.torch()
+        if tuple(h_in.shape) != self.local_shape or tuple(h_out.shape) != self.local_shape:
+            raise ValueError(f"host slabs must have the local shape {self.local_shape}")
+        dev = t.device("cuda", t.cuda.current_device())
+        st = getattr(self, "_host_state", None)
+        if st is None:
+            st = self._host_state = {
+                "d_in": t.empty(self.local_shape, dtype=t.float64, device=dev),
+                "d_out": t.empty(self.local_shape, dtype=t.float64, device=dev),
+                "s_in": t.cuda.Stream(), "s_cmp": t.cuda.Stream(), "s_out": t.cuda.Stream(), "s_comm": t.cuda.Stream()}
+        d_in, d_out = st["d_in"], st["d_out"]
+        nx = self.local_shape[0]
+        # the same chunking on every rank (the per-chunk signals pair up): sized from the widest slab
+        zl_max = -(-self.global_shape[-1] // self.nranks)
+        plane = int(np.prod(self.local_shape[1:-1])) * zl_max
+        cp = max(8, (chunk_mib << 17) // plane)
+        if self.nranks == 1 or not self._use_symm(d_in):
+            # no peer memory: one exchange for the whole slab (NCCL / gloo), copies not overlapped with it
+            d_in.copy_(h_in, non_blocking=True)
+            self(d_in, out=d_out)
+            h_out.copy_(d_out, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+            return h_out
+        chunks = [(a, min(a + cp, nx)) for a in range(0, nx, cp)]
+        sh = self._symm
+        q = sh.step & 1
+        sh.step += 1
+        to_lo, to_hi = sh.targets(q)
+        lo_h, hi_h = sh.mine(q)
+        lib = _lib.load()
+        in_done, halo_done = [], []
+        main = t.cuda.current_stream()
+        for s_ in (st["s_in"], st["s_comm"], st["s_cmp"], st["s_out"]):
+            s_.wait_stream(main)
+
+        def run(c):
+            a, b = chunks[c]
+            with t.cuda.stream(st["s_cmp"]):
+                st["s_cmp"].wait_event(in_done[min(c + 1, len(chunks) - 1)])
+                st["s_cmp"].wait_event(halo_done[c])
+                self.apply_range(d_in, d_out, a, b, lo_h, hi_h)
+                done = st["s_cmp"].record_event()
+            with t.cuda.stream(st["s_out"]):
+                st["s_out"].wait_event(done)
+                h_out[a:b].copy_(d_out[a:b], non_blocking=True)
+
+        for k, (a, b) in enumerate(chunks):
+            with t.cuda.stream(st["s_in"]):
+                d_in[a:b].copy_(h_in[a:b], non_blocking=True)
+                in_done.append(st["s_in"].record_event())
+            with t.cuda.stream(st["s_comm"]):
+                st["s_comm"].wait_event(in_done[k])
+                _lib.check(lib.ng_fdlap_pack_halo_range(
+                    self.plan.handle, d_in.data_ptr(), to_lo.data_ptr() if to_lo is not None else None,
+                    to_hi.data_ptr() if to_hi is not None else None, a, b, _device.current_stream_ptr()),
+                    "ng_fdlap_pack_halo_range")
+                sh.signal_and_wait(q)
+                halo_done.append(st["s_comm"].record_event())
+            if k >= 1:
+                run(k - 1)
+        run(len(chunks) - 1)
+        for s_ in (st["s_in"], st["s_comm"], st["s_cmp"], st["s_out"]):
+            s_.synchronize()
+        return h_out
 
     # -- single-GPU emulation of all ranks (tests; no inter-process waits, see B200_PROFILING.md) ----
     @staticmethod

@@ -36,6 +36,77 @@ def test_cfg2_chebyshev_cube_bit_exact(gpu_ready, n):
         assert np.array_equal(out, ref), (n, order, axis, rel_linf(out, ref))
 
 
+def test_cfg2_chebyshev_256_cube_bit_exact_bench_instance(gpu_ready):
+    """BASELINE cfg2 at its stated size: Diff(g, 2, 0) on Chebyshev 256^3 and the other axes / order 1, bit for
+    bit against the oracle.  At this size the dispatcher picks the 4-column-pair tile variant (the instance
+    bench.py times), which the 48^3 / 128^3 cases never reach -- asserted through ng_last_kernel()."""
+    from numgrids_b200 import _lib
+    from oracle import pencil_c
+    n = 256
+    ax = ng.create_axis(A.CHEBYSHEV, n, 0.0, 1.0)
+    g = ng.Grid(ax, ax, ax)
+    x = ax.coords
+    f = (np.sin(3 * x)[:, None, None] * np.cos(2 * x)[None, :, None] * np.exp(-x)[None, None, :])
+    pax = [pencil.make_axis("chebyshev", n, 0.0, 1.0)] * 3
+    seen = set()
+    for order, axis in ((2, 0), (2, 1), (2, 2), (1, 0), (1, 1), (1, 2)):
+        out = ng.Diff(g, order, axis)(f)
+        seen.add(_lib.last_kernel())
+        M = pencil.chebyshev_matrix(n, 0.0, 1.0, order, last_axis_of_nd=(axis == 2))
+        ref = pencil_c.dense_apply(f, axis, M, pencil.chebyshev_descending(order, axis, 3))   # C oracle (pinned to the
+        assert np.array_equal(out, ref), (order, axis, rel_linf(out, ref))                    # NumPy one, test_oracle_c)
+        if (order, axis) == (2, 0):          # the BASELINE case once more against the NumPy oracle itself
+            assert np.array_equal(out, pencil.make_diff(pax, 2, 0)(f))
+    assert seen == {"dense_fast<ncp4>", "dense_fast<ncp4,lastax>"}, seen
+
+
+@pytest.mark.parametrize("n", [1024, 512, 256, 128])
+def test_cfg3_fft_ring_kernel_vs_oracle(gpu_ready, n):
+    """The persistent ring kernel -- the instance bench.py times at cfg3 -- needs >= 1776 pencils: 64 x 32 x n
+    has 2048.  Orders 1 and 2 against numpy.fft (oracle), tolerance 1e-11 (order 2 at n = 1024: 3e-11, see
+    test_cfg3_fft_axis_1024)."""
+    from numgrids_b200 import _lib
+    e0 = ng.create_axis(A.EQUIDISTANT, 64, 0.0, 1.0)
+    e1 = ng.create_axis(A.EQUIDISTANT, 32, 0.0, 1.0)
+    p = ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi)
+    g = ng.Grid(e0, e1, p)
+    X, Y, P = g.meshed_coords
+    f = np.exp(np.sin(P)) * np.cos(2 * X) + Y * np.sin(3 * P)
+    import torch
+    fd = torch.from_numpy(f).cuda()
+    for order in (1, 2):
+        out = ng.Diff(g, order, 2)(fd)
+        assert _lib.last_kernel() == "fft2pass_ring", _lib.last_kernel()
+        ref = pencil.fft_apply(f, 2, pencil.fft_multiplier(n, p.spacing, order))
+        err = rel_linf(out.cpu().numpy(), ref)
+        print(f"ring kernel n={n} order {order}: rel Linf {err:.3e}")
+        assert err <= (3e-11 if (order == 2 and n == 1024) else TOL_FFT), (n, order, err)
+
+
+def test_cfg3_full_size_512x512x1024(gpu_ready):
+    """BASELINE cfg3 at its stated size (2 GiB array, 262 144 pencils): pencils are independent, so three
+    8-plane blocks of the full-size result are compared with numpy.fft on the same blocks."""
+    import torch
+    from numgrids_b200 import _lib
+    e = ng.create_axis(A.EQUIDISTANT, 512, 0.0, 1.0)
+    p = ng.create_axis(A.EQUIDISTANT_PERIODIC, 1024, 0.0, 2 * np.pi)
+    g = ng.Grid(e, e, p)
+    x = torch.from_numpy(e.coords).cuda()
+    ph = torch.from_numpy(p.coords).cuda()
+    f = (torch.exp(torch.sin(ph))[None, None, :] * torch.cos(2 * x)[:, None, None]
+         + x[None, :, None] * torch.sin(3 * ph)[None, None, :]).contiguous()
+    out = ng.Diff(g, 1, 2)(f)
+    assert _lib.last_kernel() == "fft2pass_ring"
+    W = pencil.fft_multiplier(1024, p.spacing, 1)
+    worst = 0.0
+    for a in (0, 252, 504):
+        blk = f[a:a + 8].cpu().numpy()
+        ref = pencil.fft_apply(blk, 2, W)
+        worst = max(worst, rel_linf(out[a:a + 8].cpu().numpy(), ref))
+    print(f"cfg3 full size: rel Linf {worst:.3e}")
+    assert worst <= TOL_FFT
+
+
 def test_cfg3_fft_axis_1024(gpu_ready):
     """Periodic 1024-point last axis, reduced batch (32x32), Nyquist zeroed; tolerance 1e-11."""
     e = ng.create_axis(A.EQUIDISTANT, 32, 0.0, 1.0)
@@ -145,6 +216,7 @@ def test_cfg5_full_size_identities(gpu_ready, monkeypatch):
     Diff(g,2,0)(f)+Diff(g,2,1)(f)+Diff(g,2,2)(f) bit for bit, and every per-axis streaming kernel
     equals the gather kernel (itself pinned to the oracle at small sizes) bit for bit."""
     import torch
+    from numgrids_b200 import _lib
     n = 1024
     ax = ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0)
     g = ng.Grid(ax, ax, ax)
@@ -160,12 +232,84 @@ def test_cfg5_full_size_identities(gpu_ready, monkeypatch):
     for order, axis in ((1, 0), (2, 1), (1, 2), (2, 2)):
         op = ng.Diff(g, order, axis)
         monkeypatch.setenv("NG_FD_STREAM", "1")
+        _lib.tuning_reload()
         fast = op(f)
         monkeypatch.setenv("NG_FD_STREAM", "0")
+        _lib.tuning_reload()
         slow = op(f)
         monkeypatch.delenv("NG_FD_STREAM")
+        _lib.tuning_reload()
         assert torch.equal(fast.view(torch.int64), slow.view(torch.int64)), (order, axis)
         del fast, slow
+
+
+def _lap_blocks_vs_oracle(f_dev, out_dev, hs, blocks, margin=8):
+    """Compare output planes [a, b) of axis 0 with the C oracle run on input planes [a-margin, b+margin)
+    (clipped to the array: a real boundary stays a real boundary; an artificial cut is >= 6 planes away
+    from every compared plane, further than the widest one-sided stencil reaches)."""
+    from oracle import pencil_c
+    nx = f_dev.shape[0]
+    for a, b in blocks:
+        lo, hi = max(a - margin, 0), min(b + margin, nx)
+        ref = pencil_c.cartesian_laplacian3(f_dev[lo:hi].cpu().numpy(), hs, 4)[a - lo:b - lo]
+        got = out_dev[a:b].cpu().numpy()
+        assert np.array_equal(got, ref), ((a, b), rel_linf(got, ref))
+
+
+def test_cfg5_1024_cube_vs_oracle(gpu_ready):
+    """BASELINE cfg5 at its stated per-GPU size: the fused Laplacian of a 1024^3 field against the C/OpenMP
+    oracle (oracle/pencil_c.c, pinned bit for bit to the NumPy restatement), array_equal -- on the whole array
+    when the host has the memory (3 x 8 GiB), else on x blocks at both boundaries and in the middle."""
+    import psutil
+    import torch
+    from numgrids_b200 import _lib
+    from oracle import pencil_c
+    n = 1024
+    ax = ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0)
+    g = ng.Grid(ax, ax, ax)
+    x = torch.linspace(0.0, 1.0, n, dtype=torch.float64, device="cuda")
+    f = (torch.sin(2 * np.pi * x)[:, None, None] * torch.cos(2 * np.pi * x)[None, :, None]
+         * torch.exp(x)[None, None, :]).contiguous()
+    out = ng.CartesianLaplacian(g)(f)
+    assert _lib.last_kernel() == "fdlap3d_ring2", _lib.last_kernel()
+    hs = [ax.spacing] * 3
+    _lap_blocks_vs_oracle(f, out, hs, [(0, 24), (500, 524), (1000, 1024)])
+    if psutil.virtual_memory().available > 40 * 2 ** 30:
+        pencil_c.use_all_cores()
+        ref = pencil_c.cartesian_laplacian3(f.cpu().numpy(), hs, 4)
+        got = out.cpu().numpy()
+        assert np.array_equal(got, ref), rel_linf(got, ref)
+        print("cfg5 1024^3: whole array equals the oracle bit for bit")
+
+
+def test_cfg5_slab_shapes_vs_oracle(gpu_ready):
+    """The per-GPU slab shapes of the 2/4/8-GPU weak-scaling runs (halos from random neighbour planes): the
+    interior part (plain instance) + boundary part (slab instance) against the oracle applied to the array
+    extended by the halo columns."""
+    import torch
+    from numgrids_b200 import _lib
+    from numgrids_b200.slab import SlabLaplacian
+    from oracle import pencil_c
+    torch.manual_seed(7)
+    for shape in ((96, 72, 256), (40, 200, 128), (64, 48, 64)):
+        hs = [0.01, 0.02, 0.03]
+        lap = SlabLaplacian(shape, hs)
+        f = torch.randn(*shape, dtype=torch.float64, device="cuda")
+        rows = shape[0] * shape[1]
+        lo = torch.randn(rows, 2, dtype=torch.float64, device="cuda")
+        hi = torch.randn(rows, 2, dtype=torch.float64, device="cuda")
+        for use_lo, use_hi in ((True, True), (True, False), (False, True)):
+            ext = torch.cat(([lo.view(shape[0], shape[1], 2)] if use_lo else []) + [f]
+                            + ([hi.view(shape[0], shape[1], 2)] if use_hi else []), dim=2)
+            ref = pencil_c.cartesian_laplacian3(ext.cpu().numpy(), hs, 4)
+            ref = ref[:, :, (2 if use_lo else 0):(2 if use_lo else 0) + shape[2]]
+            out = torch.full_like(f, float("nan"))
+            lap.apply_part(f, out, 1, lo if use_lo else None, hi if use_hi else None)
+            if shape[2] > 128:
+                assert _lib.last_kernel() == "fdlap3d_ring2"            # interior tiles: plain instance
+            lap.apply_part(f, out, 2, lo if use_lo else None, hi if use_hi else None)
+            assert _lib.last_kernel() == "fdlap3d_ring2<slab>"
+            assert np.array_equal(out.cpu().numpy(), ref), (shape, use_lo, use_hi)
 
 
 def test_host_pipeline_chunked_paths(gpu_ready):
@@ -173,7 +317,9 @@ def test_host_pipeline_chunked_paths(gpu_ready):
     points; results must equal the device-resident path bit for bit."""
     import os
     import torch
+    from numgrids_b200 import _lib
     os.environ["NG_HOST_CHUNK_MB"] = "8"               # force chunking (default chunk is 256 MiB)
+    _lib.tuning_reload()
     n = 224                                            # 224^3 doubles = 86 MiB -> 11 axis-0 chunks
     ax = ng.create_axis(A.EQUIDISTANT, n, 0.0, 1.0)
     g = ng.Grid(ax, ax, ax)
@@ -191,6 +337,7 @@ def test_host_pipeline_chunked_paths(gpu_ready):
     d = ng.Diff(g2, 1, 2)
     assert np.array_equal(d(f2), d(torch.from_numpy(f2).cuda()).cpu().numpy())
     del os.environ["NG_HOST_CHUNK_MB"]
+    _lib.tuning_reload()
 
 
 def test_laplacian_plane_ranges(gpu_ready):

@@ -66,6 +66,7 @@ for case in range(ncase):
     outs = []
     for mode in ("2", "0") + (("1",) if exact else ()):
         os.environ["NG_DENSE_FAST"] = mode
+        lib.ng_tuning_reload()
         o = torch.full(shape, float("nan"), dtype=torch.float64, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
         rc = (lib.ng_apply_fused(op.plan.handle, f.data_ptr(), o.data_ptr(), C.byref(fuse), st) if fuse is not None

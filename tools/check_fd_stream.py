@@ -84,6 +84,7 @@ for case in range(ncase):
     outs = []
     for stream_on in ("1", "0"):
         os.environ["NG_FD_STREAM"] = stream_on
+        lib.ng_tuning_reload()
         o = torch.full(shape, float("nan"), dtype=torch.float64, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
         if halo is not None:

@@ -68,6 +68,7 @@ for case in range(ncase):
     outs = []
     for mode in ("1", "0"):
         os.environ["NG_FFT_STRIDED"] = mode
+        lib.ng_tuning_reload()
         o = torch.full(shape, 7.0, dtype=torch.float64, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
         rc = (lib.ng_apply_fused(op.plan.handle, f.data_ptr(), o.data_ptr(), C.byref(fuse), st) if fuse is not None
