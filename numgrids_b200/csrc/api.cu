@@ -526,7 +526,7 @@ int ng_fdlap_apply_slab_part(const ng_plan* plan, const double* d_in, double* d_
                              const double* d_lo_halo, const double* d_hi_halo, int z_part, void* stream) {
     NG_REQUIRE(plan && plan->kind == PK_FDLAP, "ng_fdlap_apply_slab_part: Laplacian plan required");
     NG_REQUIRE(d_in && d_out && d_in != d_out, "ng_fdlap_apply_slab_part: bad buffers");
-    NG_REQUIRE(z_part >= 0 && z_part <= 2, "ng_fdlap_apply_slab_part: z_part must be 0, 1 or 2");
+    NG_REQUIRE(z_part >= 0 && z_part <= 3, "ng_fdlap_apply_slab_part: z_part must be 0, 1 or 2");
     return ng_fdlap_launch(plan, d_in, d_out, d_lo_halo, d_hi_halo, 0, plan->shape[0], z_part, (cudaStream_t)stream);
 }
 

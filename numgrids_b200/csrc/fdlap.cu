@@ -75,7 +75,7 @@ int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const doubl
     bool handled = false;
     int rc = ng_fdlap3d_try_launch(p, in, out, lo, hi, (int)xbeg, (int)xend, zmode, st, &handled);
     if (rc != NG_OK || handled) return rc;
-    if (zmode == 1) return NG_OK;                 // generic kernel: part 2 computes everything
+    if (zmode == 1 || zmode == 3) return NG_OK;   // generic kernel: part 2 computes everything
     const i64 plane = p->size / p->shape[0];
     const i64 first = xbeg * plane, last = xend * plane;
     i64 g = (last - first + 255) / 256;

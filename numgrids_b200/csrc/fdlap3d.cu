@@ -445,8 +445,10 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // zmode 0: every z tile; 1: interior tiles only (no halo dependence); 2: the first and last tile
+    // (3, timing experiments only: tiles 1 and ztiles-2, two interior tiles launched like the boundary pair)
     const int zt_idx = zmode == 1 ? (int)blockIdx.x + 1
-                                  : (zmode == 2 ? (blockIdx.x == 0 ? 0 : nz / RING_TZ - 1) : (int)blockIdx.x);
+                       : zmode == 2 ? (blockIdx.x == 0 ? 0 : nz / RING_TZ - 1)
+                       : zmode == 3 ? (blockIdx.x == 0 ? 1 : nz / RING_TZ - 2) : (int)blockIdx.x;
     const int z0 = zt_idx * RING_TZ;
     const int yb = blockIdx.y * TY;
     const int xs = xbeg + blockIdx.z * xchunk;
@@ -657,7 +659,8 @@ int launch_ring2(const ng_plan* p, const double* in, double* out, const double* 
                         (SLAB ? (size_t)S * 2 * (((ROWS * 2 + 15) / 16) * 16) * sizeof(double) : 0) + 128;
     NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB>);
     const unsigned ztiles = (unsigned)(nz / RING_TZ);
-    const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2) : ztiles);
+    const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2)
+                         : zmode == 3 ? (ztiles >= 4 ? 2 : 0) : ztiles);
     *launched = true;
     if (gxz == 0) return NG_OK;                     // nothing to do for this z part (e.g. no interior tiles)
     const unsigned gz = (unsigned)((xend - xbeg + xchunk - 1) / xchunk);
@@ -737,7 +740,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         if (rc) return rc;
         if (launched) { *handled = true; return NG_OK; }
     }
-    if (zmode == 1) { *handled = true; return NG_OK; }     // fallback kernel: part 2 computes everything
+    if (zmode == 1 || zmode == 3) { *handled = true; return NG_OK; }     // fallback kernel: part 2 computes everything
     {
         const unsigned gz = (unsigned)((xend - xbeg + xchunk - 1) / xchunk);
         dim3 grid(gx, (unsigned)((ny + 2 * 8 - 1) / (2 * 8)), gz);

@@ -67,7 +67,7 @@ class Clock:
 
 
 def env(**kw):
-    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK"):
+    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -108,7 +108,7 @@ variants = {
     "slab: interior part alone": ({}, lambda: lap.apply_part(f, out, 1)),
     "slab: boundary part alone (halos)": ({}, lambda: lap.apply_part(f, out, 2, lo, hi)),
     "slab: boundary part alone (one-sided z)": ({}, lambda: lap.apply_part(f, out, 2)),
-    "march fallback": ({"NG_FDLAP_RING": 0}, lambda: lap.apply_local(f, out)),
+    "experiment: tiles 1 and nt-2 alone": ({}, lambda: lap.apply_part(f, out, 3)),
 }
 names = list(variants)
 res = {n: [] for n in names}
