@@ -119,6 +119,7 @@ struct CoefHost {           // device-resident compact coefficient table owned b
     double* d_ptr = nullptr;
     i64 count = 0;
     i64 stride[NG_MAX_DIM] = {0, 0, 0, 0};
+    bool is_one = false;    // the table is the single value 1.0 (multiplying / dividing by it is exact: skipped)
 };
 
 struct ng_plan {
@@ -159,6 +160,7 @@ struct ng_plan {
     CoefHost cJ, cLap[NG_MAX_DIM], cDiv[NG_MAX_DIM], cGrad[NG_MAX_DIM], cH[NG_MAX_DIM],
         cCurl[NG_MAX_DIM];
     double* d_work = nullptr;
+    void* d_curvlap = nullptr;   // parameter block of the single-pass Laplacian (curvlap3d.cu)
 
     // host-call staging (ng_apply_host / ng_fdlap_apply_host)
     double* d_stage_in = nullptr;

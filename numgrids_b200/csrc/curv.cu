@@ -15,6 +15,8 @@
 // Every elementwise step is a separately rounded IEEE operation in the reference's order.
 #include "common.cuh"
 
+int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStream_t st, bool* handled);
+
 namespace {
 
 CoefDev to_dev(const CoefHost& c) {
@@ -118,6 +120,11 @@ int ng_curv_set_coef(ng_plan* p, int kind, int index, const double* h_values, in
     p->device_bytes += sizeof(double) * count;
     c->count = count;
     for (int a = 0; a < NG_MAX_DIM; ++a) c->stride[a] = a < p->ndim ? stride[a] : 0;
+    c->is_one = (count == 1 && h_values[0] == 1.0);
+    if (p->d_curvlap) {          // the single-pass kernel's parameter block is rebuilt from the new tables
+        cudaFree(p->d_curvlap);
+        p->d_curvlap = nullptr;
+    }
     return NG_OK;
 }
 
@@ -127,9 +134,14 @@ int ng_curv_laplacian(ng_plan* p, const double* d_f, double* d_out, void* stream
     NG_REQUIRE(d_f && d_out && d_f != d_out, "ng_curv_laplacian: bad buffers");
     NG_NEED(p->cJ, "J");
     for (int i = 0; i < p->ndim; ++i) NG_NEED(p->cLap[i], "J/h_i**2");
+    cudaStream_t st = (cudaStream_t)stream;
+    {   // all-finite-difference 3-D grids: one pass, `inner` never leaves the SM (curvlap3d.cu)
+        bool handled = false;
+        rc = ng_curvlap3d_try_launch(p, d_f, d_out, st, &handled);
+        if (rc || handled) return rc;
+    }
     rc = ensure_work(p);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
     for (int i = 0; i < p->ndim; ++i) {
         const ng_plan* D = p->axis_plans[i];
         FuseDev F1 = base_fuse(D);
