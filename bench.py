@@ -659,13 +659,14 @@ def run_gpu_arm(args):
     parts = None
     if stencil_ev:
         # the stencil of a step spans from the start of the interior launch to the join of the two streams
-        k_ms += [e["int0"].elapsed_time(e["join"]) for e in stencil_ev]
+        k_ms += [e["int0"].elapsed_time(e["join"]) for e in stencil_ev]       # (pack and signals are not the stencil)
         mean = lambda a, b: statistics.mean(e[a].elapsed_time(e[b]) for e in stencil_ev)
         parts = {"interior_ms": mean("int0", "int1"), "boundary_ms": mean("edge0", "edge1"),
                  "stencil_span_ms": mean("int0", "join")}
         if "pack0" in stencil_ev[0]:
             parts["pack_ms"] = mean("pack0", "pack1")
             parts["signal_wait_ms"] = mean("pack1", "edge0")
+            parts["step_span_ms"] = mean("pack0", "join")
     t = torch.tensor([elapsed_ms, statistics.mean(k_ms), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()

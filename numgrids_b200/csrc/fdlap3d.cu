@@ -733,7 +733,9 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         const int slots = (int)NG_ENV_INT("NG_FDLAP_S", 8);
         bool launched = false;
         int rc;
-        if (slab) rc = launch_ring2<2, 4, 8, 3, true>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
+        if (slab && NG_ENV_INT("NG_FDLAP_EDGE_TEST", 0))        // timing experiment (wrong edge columns): boundary tiles with neither halo nor one-sided work
+            rc = launch_ring2<2, 4, 8, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
+        else if (slab) rc = launch_ring2<2, 4, 8, 3, true>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slots == 10) rc = launch_ring2<2, 4, 10, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slots == 6) rc = launch_ring2<2, 4, 6, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else rc = launch_ring2<2, 4, 8, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);

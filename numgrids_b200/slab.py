@@ -267,12 +267,16 @@ class SlabLaplacian:
         return True
 
     def _call_symm(self, f, out):
-        """main stream: interior z tiles.  side stream: pack kernel (stores straight into the neighbours'
-        halo buffers) -> signals -> the two boundary z tiles.  The boundary launch needs no SM until the
-        interior launch has handed out its last CTAs, so it fills that launch's tail instead of following
-        it; the main stream joins the side stream at the end of the step.  Reuse of halo set q: my signal
-        of step s+1 is enqueued behind my boundary launch of step s on the same stream, and a neighbour
-        overwrites set q again only after it has seen that signal."""
+        """main stream: pack kernel (stores this rank's edge columns straight into the neighbours' halo
+        buffers over NVLink), then the interior z tiles.  side stream, behind the pack: signals, then the two
+        boundary z tiles.  The pack runs BEFORE the stencil rather than next to it: its 16-byte reads (one per
+        row and side) are DRAM-activate bound, 0.06-0.2 ms alone but 2.5 ms when they compete with the
+        stencil's streams (measured, profiles/r02_slab_step_parts.txt), which would delay the boundary launch.
+        The boundary launch needs no SM until the interior launch has handed out its last CTAs, so it fills
+        that launch's tail; the main stream joins the side stream at the end of the step.  Reuse of halo set
+        q: my signal of step s+1 follows my boundary launch of step s on the side stream, my pack of step s+2
+        follows the join of step s+1 -- behind my wait for the neighbours' signals of step s+1, which they
+        sent after their boundary launch of step s (the last reader of set q)."""
         t = _device.torch()
         sh = self._symm
         q = sh.step & 1
@@ -284,15 +288,16 @@ class SlabLaplacian:
         tm = getattr(self, "stencil_events", None)        # optional sink for bench.py: one dict of events per step
         ev = {k: t.cuda.Event(enable_timing=True) for k in
               ("pack0", "pack1", "edge0", "edge1", "int0", "int1", "join")} if tm is not None else None
-        comm.wait_stream(main)            # f is ready
         lo_h, hi_h = sh.mine(q)
+        to_lo, to_hi = sh.targets(q)
+        if ev: ev["pack0"].record()
+        _lib.check(_lib.load().ng_fd_pack_halo(
+            self.plan.handle, f.data_ptr(), to_lo.data_ptr() if to_lo is not None else None,
+            to_hi.data_ptr() if to_hi is not None else None, _device.current_stream_ptr()), "ng_fd_pack_halo")
+        packed = main.record_event()
+        if ev: ev["pack1"].record()
         with t.cuda.stream(comm):
-            to_lo, to_hi = sh.targets(q)
-            if ev: ev["pack0"].record()
-            _lib.check(_lib.load().ng_fd_pack_halo(
-                self.plan.handle, f.data_ptr(), to_lo.data_ptr() if to_lo is not None else None,
-                to_hi.data_ptr() if to_hi is not None else None, _device.current_stream_ptr()), "ng_fd_pack_halo")
-            if ev: ev["pack1"].record()
+            comm.wait_event(packed)
             sh.signal_and_wait(q)
             if ev: ev["edge0"].record()
             self.apply_part(f, out, 2, lo_h, hi_h)        # first / last z tile, neighbour planes staged by TMA

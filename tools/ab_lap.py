@@ -67,7 +67,7 @@ class Clock:
 
 
 def env(**kw):
-    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING"):
+    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -109,6 +109,7 @@ variants = {
     "slab: boundary part alone (halos)": ({}, lambda: lap.apply_part(f, out, 2, lo, hi)),
     "slab: boundary part alone (one-sided z)": ({}, lambda: lap.apply_part(f, out, 2)),
     "experiment: tiles 1 and nt-2 alone": ({}, lambda: lap.apply_part(f, out, 3)),
+    "experiment: boundary tiles as interior": ({"NG_FDLAP_EDGE_TEST": 1}, lambda: lap.apply_part(f, out, 2, lo, hi)),
 }
 names = list(variants)
 res = {n: [] for n in names}
