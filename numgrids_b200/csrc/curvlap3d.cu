@@ -9,11 +9,11 @@
 // 6 x 16 B/point of memory traffic.  Here `inner` never leaves the SM: one read of f and one write
 // of the result per point (16 B/point + the compact coefficient tables).
 //
-// Mapping.  A CTA owns a tile of TY = R*WY rows (y) x 64 z and marches along x; a producer lane streams
-// planes of the tile with a +-4 halo (two chained radius-2 stencils) -- one 3-D tensor-map TMA per plane,
-// box 72 x (TY+8) x 1, out-of-bounds zero-filled -- into a ring of S = 8 shared-memory slots; WY consumer
-// warps, each R rows x 64 z (a double2 per lane and row), work independently of each other (mbarriers
-// only):
+// Mapping.  A CTA owns a tile of TY = R*WY rows (y) x 64 z and marches along x; planes of the tile with a
+// +-4 halo (two chained radius-2 stencils) stream through a ring of S = 8 shared-memory slots -- one 3-D
+// tensor-map TMA per plane, box 72 x (TY+8) x 1, out-of-bounds zero-filled, issued by whichever warp
+// frees a slot last; the WY warps, each R rows x 64 z (a double2 per lane and row), work independently
+// of each other (mbarriers and one shared counter per slot only):
 //   x: gx(q) = c_x * D_x f at plane q from the own pairs of planes q-2..q+2 in the ring (5 LDS.128); a
 //      5-plane register window of gx gives the outer derivative of plane q-2;
 //   y: the R+8 rows y0-4..y0+R+3 of the centre plane's own column pair (LDS.128) -> gy on rows
@@ -41,7 +41,6 @@ namespace {
 constexpr int CL_TZ = 64;                    // z points per tile (one double2 per lane)
 constexpr int CL_H = 4;                      // halo on every side
 constexpr int CL_PITCH = CL_TZ + 2 * CL_H;   // doubles per staged row
-constexpr int CL_S = 8;                      // ring slots (power of two)
 
 struct ClAxis {
     double wc[5], wf[5], wb[5], ih;
@@ -297,18 +296,23 @@ __device__ __forceinline__ void cl_output(int x, int y0, int z0, int lane, int n
     }
 }
 
-template <int R, int WY, bool GEN>
-__global__ void __launch_bounds__(32 * (WY + 1), 2)
+// No producer warp: the register file is split by scheduler, so a ninth warp on the SM would cap every
+// thread at 168 registers (three warps on one scheduler) and the 5-plane gx window would spill; with
+// exactly two CTAs x four warps each thread may use 255.  Slots are handed back through a shared counter:
+// the LAST warp to finish an iteration re-arms the slot's mbarrier and issues the TMA for the plane that
+// takes its place at once, so the ring stays S-5 planes ahead without anybody waiting for a producer.
+template <int R, int WY, int S, bool GEN>
+__global__ void __launch_bounds__(32 * WY, 256 / (32 * WY))
 curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx, int ny, int nz, int xchunk,
                  const __grid_constant__ ClTabs T, const __grid_constant__ ClGen G, const ClParams* __restrict__ P,
                  const __grid_constant__ CUtensorMap tmap) {
     constexpr int TY = R * WY;
     constexpr int ROWS = TY + 2 * CL_H;
     constexpr unsigned PB = CL_PITCH * 8, PLANE_B = ROWS * PB;
-    constexpr int S = CL_S;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned ring = (cl_smem_u32(smem_raw) + 127u) & ~127u;        // TMA destinations: 128-byte aligned
-    const unsigned full = ring + S * PLANE_B, empty = full + 8 * S;
+    const unsigned full = ring + S * PLANE_B;
+    int* const done = reinterpret_cast<int*>(smem_raw + (full - cl_smem_u32(smem_raw)) + 8 * S);   // warps finished with a slot
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int z0 = blockIdx.x * CL_TZ;
@@ -322,31 +326,38 @@ curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full + 8 * s), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * s), "r"(WY) : "memory");
+            done[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int n = 0; n < S && n < nplanes; ++n) {  // the first S planes: every slot is free
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * n), "r"(PLANE_B) : "memory");
+            cl_tma_3d(ring + n * PLANE_B, &tmap, z0 - CL_H, yb - CL_H, p_first + n, full + 8 * n);
+        }
     }
     __syncthreads();
 
-    if (warp == WY) {
-        // ================= producer: one tensor-map TMA per plane =================
+    // hand slot `it % S` back; the last of the WY warps refills it with plane it + S
+    auto release = [&](int it) {
+        __syncwarp();
         if (lane == 0) {
-            for (int n = 0; n < nplanes; ++n) {
-                const int s = n & (S - 1);
-                if (n >= S) cl_wait(empty + 8 * s, ((n / S) - 1) & 1);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * s), "r"(PLANE_B) : "memory");
-                cl_tma_3d(ring + s * PLANE_B, &tmap, z0 - CL_H, yb - CL_H, p_first + n, full + 8 * s);
+            const int s = it % S;
+            __threadfence_block();
+            if (atomicAdd(&done[s], 1) == WY - 1) {
+                done[s] = 0;
+                const int n = it + S;
+                if (n < nplanes) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * s), "r"(PLANE_B) : "memory");
+                    cl_tma_3d(ring + s * PLANE_B, &tmap, z0 - CL_H, yb - CL_H, p_first + n, full + 8 * s);
+                }
             }
         }
-        return;
-    }
+    };
 
-    // ===================== consumer warps =====================
     const int y0 = yb + warp * R;
-    if (y0 >= ny) {                                    // warp outside the grid (ragged last y tile): hand the slots back
+    if (y0 >= ny) {                                    // warp outside the grid (ragged last y tile): keep pace, hand the slots back
         for (int it = 0; it < niter; ++it) {
-            cl_wait(full + 8 * ((it + 4) & (S - 1)), ((it + 4) / S) & 1);
-            if (lane == 0) cl_arrive(empty + 8 * (it & (S - 1)));
+            cl_wait(full + 8 * ((it + 4) % S), ((it + 4) / S) & 1);
+            release(it);
         }
         return;
     }
@@ -367,13 +378,13 @@ curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx
         // one iteration: plane q+2 lands -> gx(q) -> output plane q-2 -> slot of plane q-2 goes back
         const int q = xs - 2 + it;
         g0 = g1; g1 = g2; g2 = g3; g3 = g4;
-        cl_wait(full + 8 * ((it + 4) & (S - 1)), ((it + 4) / S) & 1);
+        cl_wait(full + 8 * ((it + 4) % S), ((it + 4) / S) & 1);
         if (q >= 2 && q < nx - 2) {
-            const unsigned a0 = ring + ((it) & (S - 1)) * PLANE_B + my_off;
-            const unsigned a1 = ring + ((it + 1) & (S - 1)) * PLANE_B + my_off;
-            const unsigned a2 = ring + ((it + 2) & (S - 1)) * PLANE_B + my_off;
-            const unsigned a3 = ring + ((it + 3) & (S - 1)) * PLANE_B + my_off;
-            const unsigned a4 = ring + ((it + 4) & (S - 1)) * PLANE_B + my_off;
+            const unsigned a0 = ring + (it % S) * PLANE_B + my_off;
+            const unsigned a1 = ring + ((it + 1) % S) * PLANE_B + my_off;
+            const unsigned a2 = ring + ((it + 2) % S) * PLANE_B + my_off;
+            const unsigned a3 = ring + ((it + 3) % S) * PLANE_B + my_off;
+            const unsigned a4 = ring + ((it + 4) % S) * PLANE_B + my_off;
 #pragma unroll
             for (int r = 0; r < R; ++r)
                 g4.v[r] = cl_finish_xy<GEN>(cl_sum5(T.a[0].wc, cl_lds2(a0 + r * PB), cl_lds2(a1 + r * PB), cl_lds2(a2 + r * PB),
@@ -388,11 +399,10 @@ curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx
             for (int r = 0; r < R; ++r) g4.v[r] = make_double2(0.0, 0.0);
         }
         if (it >= 4) {                                  // the first four iterations only fill the window
-            const unsigned slot = ring + (it & (S - 1)) * PLANE_B;
+            const unsigned slot = ring + (it % S) * PLANE_B;
             cl_output<R, GEN>(q - 2, y0, z0, lane, nx, ny, nz, T, G, P, in, out, slot + my_off, slot + tile_off, g0, g1, g2, g3, g4);
         }
-        __syncwarp();
-        if (lane == 0) cl_arrive(empty + 8 * (it & (S - 1)));
+        release(it);
     }
 }
 
@@ -435,6 +445,40 @@ int cl_make_tmap(CUtensorMap* tm, const double* in, i64 nx, i64 ny, i64 nz, int 
     return NG_OK;
 }
 
+template <int R, int WY, int S>
+int cl_launch(ng_plan* p, const double* in, double* out, const ClParams& hp, bool gen, cudaStream_t st) {
+    constexpr int TY = R * WY;
+    const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
+    CUtensorMap tm;
+    int rc = cl_make_tmap(&tm, in, nx, ny, nz, TY + 2 * CL_H);
+    if (rc) return rc;
+    // x chunks: 8 planes of every chunk are loaded for the window only -- long chunks where there are enough
+    // tiles to fill the machine a few times over, shorter ones on small grids
+    const i64 tiles = (nz / CL_TZ) * ((ny + TY - 1) / TY);
+    const i64 resident = 148 * (TY >= 32 ? 1 : 2);
+    int xchunk = (int)NG_ENV_INT("NG_CURV_XCHUNK", 0);
+    if (xchunk < 1) {
+        xchunk = 128;
+        while (xchunk > 32 && tiles * ((nx + xchunk - 1) / xchunk) < resident * 4) xchunk /= 2;
+    }
+    if (xchunk > nx) xchunk = (int)nx;
+    dim3 grid((unsigned)(nz / CL_TZ), (unsigned)((ny + TY - 1) / TY), (unsigned)((nx + xchunk - 1) / xchunk));
+    const size_t smem = (size_t)S * (TY + 2 * CL_H) * CL_PITCH * 8 + 8 * S + 4 * S + 128;
+    if (gen) {
+        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, S, true>);
+        curvlap3d_kernel<R, WY, S, true><<<grid, 32 * WY, smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
+                                                                            (const ClParams*)p->d_curvlap, tm);
+        NG_TRACE("curvlap3d<gen>");
+    } else {
+        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, S, false>);
+        curvlap3d_kernel<R, WY, S, false><<<grid, 32 * WY, smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
+                                                                             (const ClParams*)p->d_curvlap, tm);
+        NG_TRACE("curvlap3d<unit>");
+    }
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
 }  // namespace
 
 // The single-pass kernel covers a PK_CURV plan when every axis is a first-derivative finite-difference plan
@@ -443,8 +487,7 @@ int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStrea
     *handled = false;
     if (p->ndim != 3 || NG_ENV_INT("NG_CURV_FUSED", 1) == 0) return NG_OK;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
-    constexpr int R = 4, WY = 4, TY = R * WY;
-    if (nz % CL_TZ != 0 || ny % R != 0 || ny < 16 || nx < 16 || ny * nz >= (1LL << 28) || nx * ny * nz >= (1LL << 40)) return NG_OK;
+    if (nz % CL_TZ != 0 || ny % 4 != 0 || ny < 16 || nx < 16 || ny * nz >= (1LL << 28) || nx * ny * nz >= (1LL << 40)) return NG_OK;
     if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return NG_OK;
     for (int a = 0; a < 3; ++a) {
         const ng_plan* q = p->axis_plans[a];
@@ -476,32 +519,12 @@ int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStrea
         NG_CUDA_OK(cudaMalloc((void**)&p->d_curvlap, sizeof(ClParams)));
         NG_CUDA_OK(cudaMemcpyAsync(p->d_curvlap, &hp, sizeof(ClParams), cudaMemcpyHostToDevice, st));
     }
-    CUtensorMap tm;
-    int rc = cl_make_tmap(&tm, in, nx, ny, nz, TY + 2 * CL_H);
+    int rc;
+    switch ((int)NG_ENV_INT("NG_CURV_CFG", 0)) {    // tuning: tile rows / ring depth (profiles/r02_tune_curvlap.txt)
+        case 1: rc = cl_launch<4, 8, 9>(p, in, out, hp, gen, st); break;      // 32 x 64 tiles, one CTA of 8 warps per SM
+        default: rc = cl_launch<4, 4, 8>(p, in, out, hp, gen, st); break;     // 16 x 64 tiles, two CTAs of 4 warps per SM
+    }
     if (rc) return rc;
-    // x chunks: 8 planes of every chunk are loaded for the window only -- long chunks where there are enough
-    // tiles to fill the machine (2 CTAs per SM), shorter ones on small grids
-    const i64 tiles = (nz / CL_TZ) * ((ny + TY - 1) / TY);
-    int xchunk = (int)NG_ENV_INT("NG_CURV_XCHUNK", 0);
-    if (xchunk < 1) {
-        xchunk = 128;
-        while (xchunk > 32 && tiles * ((nx + xchunk - 1) / xchunk) < 148 * 2 * 4) xchunk /= 2;
-    }
-    if (xchunk > nx) xchunk = (int)nx;
-    dim3 grid((unsigned)(nz / CL_TZ), (unsigned)((ny + TY - 1) / TY), (unsigned)((nx + xchunk - 1) / xchunk));
-    const size_t smem = (size_t)CL_S * (TY + 2 * CL_H) * CL_PITCH * 8 + 2 * CL_S * 8 + 128;
-    if (gen) {
-        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, true>);
-        curvlap3d_kernel<R, WY, true><<<grid, 32 * (WY + 1), smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
-                                                                         (const ClParams*)p->d_curvlap, tm);
-        NG_TRACE("curvlap3d<gen>");
-    } else {
-        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, false>);
-        curvlap3d_kernel<R, WY, false><<<grid, 32 * (WY + 1), smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
-                                                                          (const ClParams*)p->d_curvlap, tm);
-        NG_TRACE("curvlap3d<unit>");
-    }
-    NG_LAUNCH_CHECK();
     *handled = true;
     return NG_OK;
 }

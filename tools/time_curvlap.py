@@ -44,13 +44,14 @@ for name, fns, shape in cases:
         g._jacobian = np.broadcast_to(1.0, shape)
     f = torch.rand(*shape, dtype=torch.float64, device="cuda")
     pts = f.numel()
-    for mode in ("1", "0"):
-        os.environ["NG_CURV_FUSED"] = mode
+    for mode, cfg, xc in (("1", "0", "0"), ("1", "0", "128"), ("1", "0", "256"), ("1", "1", "0"), ("1", "1", "128"), ("0", "0", "0")):
+        os.environ["NG_CURV_FUSED"], os.environ["NG_CURV_CFG"], os.environ["NG_CURV_XCHUNK"] = mode, cfg, xc
         _lib.tuning_reload()
         med, mn = timed(lambda: g.laplacian(f))
-        print(f"{name:16s} {shape}  fused={mode} [{_lib.last_kernel():16s}]  median {med:7.3f} ms  min {mn:7.3f} ms  "
+        print(f"{name:16s} {shape}  fused={mode} cfg={cfg} xchunk={xc:>3s} [{_lib.last_kernel():16s}]  median {med:7.3f} ms  min {mn:7.3f} ms  "
               f"{pts / med / 1e6:7.1f} Gpts/s  {16 * pts / med / 1e6 / PEAK:5.3f} of HBM peak at 16 B/pt")
-    del os.environ["NG_CURV_FUSED"]
+    for k in ("NG_CURV_FUSED", "NG_CURV_CFG", "NG_CURV_XCHUNK"):
+        del os.environ[k]
     _lib.tuning_reload()
     del f, g
     torch.cuda.empty_cache()
