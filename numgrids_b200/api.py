@@ -154,10 +154,14 @@ class CartesianLaplacian:
 
     def __call__(self, f):
         shape = self.grid.shape
+        if _device.is_complex(f):            # real linear operator: componentwise, like the three-call idiom
+            re, im = _device.split_complex(f)
+            return _device.join_complex(self(re), self(im))
         if _device.is_device_array(f):
             x = _device.as_device_tensor(f, shape)
-            out = _device.empty_like_device(x)
-            self.apply_ptr(x.data_ptr(), out.data_ptr())
+            with _device.device_of(x):
+                out = _device.empty_like_device(x)
+                self.apply_ptr(x.data_ptr(), out.data_ptr())
             return out
         a = _device.as_host_array(f, shape)
         _lib.require_gpu()

@@ -452,15 +452,12 @@ int cl_launch(ng_plan* p, const double* in, double* out, const ClParams& hp, boo
     CUtensorMap tm;
     int rc = cl_make_tmap(&tm, in, nx, ny, nz, TY + 2 * CL_H);
     if (rc) return rc;
-    // x chunks: 8 planes of every chunk are loaded for the window only -- long chunks where there are enough
-    // tiles to fill the machine a few times over, shorter ones on small grids
-    const i64 tiles = (nz / CL_TZ) * ((ny + TY - 1) / TY);
-    const i64 resident = 148 * (TY >= 32 ? 1 : 2);
+    // x chunks: 8 planes of every chunk are loaded for the window only, yet SHORT chunks win (B200, 512^3:
+    // 16 planes 1.58 ms, 64 planes 1.83 ms, 256 planes 3.1 ms, profiles/r02_tune_curvlap.txt): a warp issues
+    // one instruction per ~5 cycles (dependent FP64 chains, two warps per scheduler), so the machine only
+    // fills when many CTAs at different points of their march share an SM over time
     int xchunk = (int)NG_ENV_INT("NG_CURV_XCHUNK", 0);
-    if (xchunk < 1) {
-        xchunk = 128;
-        while (xchunk > 32 && tiles * ((nx + xchunk - 1) / xchunk) < resident * 4) xchunk /= 2;
-    }
+    if (xchunk < 1) xchunk = 16;
     if (xchunk > nx) xchunk = (int)nx;
     dim3 grid((unsigned)(nz / CL_TZ), (unsigned)((ny + TY - 1) / TY), (unsigned)((nx + xchunk - 1) / xchunk));
     const size_t smem = (size_t)S * (TY + 2 * CL_H) * CL_PITCH * 8 + 8 * S + 4 * S + 128;

@@ -91,7 +91,10 @@ class CurvilinearGrid(Grid):
         """Return (device tensors, host_output?)."""
         on_device = [_device.is_device_array(a) for a in arrays]
         if all(on_device):
-            return [_device.as_device_tensor(a, self.shape) for a in arrays], False
+            xs = [_device.as_device_tensor(a, self.shape) for a in arrays]
+            if len({x.device for x in xs}) > 1:
+                raise ValueError("all arrays of one call must live on the same CUDA device")
+            return xs, False
         _lib.require_gpu()
         out = []
         for a, dev in zip(arrays, on_device):
@@ -103,53 +106,85 @@ class CurvilinearGrid(Grid):
     def _finish(t, to_host):
         return t.cpu().numpy() if to_host else t
 
+    def _complex_split(self, arrays, run):
+        """Complex fields: the operators are real and linear, so they are applied to the real and the
+        imaginary parts separately (the reference's NumPy arithmetic does the same componentwise).  On grids
+        with a periodic axis the reference's FFTDiff keeps only the real part of that axis' terms
+        (numgrids/diff.py:141) -- a mixed result that is refused here rather than reproduced."""
+        if not any(_device.is_complex(a) for a in arrays):
+            return None
+        from .axes import EquidistantAxis
+        if any(isinstance(a, EquidistantAxis) and a.periodic for a in self.axes):
+            raise TypeError("complex fields are not supported on curvilinear grids with a periodic axis "
+                            "(the reference's FFTDiff discards the imaginary part there)")
+        parts = [_device.split_complex(a) if _device.is_complex(a) else (a, None) for a in arrays]
+        re = run(*[p[0] for p in parts])
+        zero = lambda a: a * 0.0
+        im = run(*[p[1] if p[1] is not None else zero(p[0]) for p in parts])
+        if isinstance(re, tuple):
+            return tuple(_device.join_complex(a, b) for a, b in zip(re, im))
+        return _device.join_complex(re, im)
+
     # ------------------------------------------------------------ operators
     def gradient(self, f):
         """(grad f)_i = (1/h_i) d f / d q_i, non-finite values replaced by 0 (curvilinear.py:153-177)."""
+        c = self._complex_split([f], self.gradient)
+        if c is not None:
+            return c
         self._ensure_diff_ops()
         h = self._evaluate_scale_factors()
         (x,), to_host = self._stage([f])
-        plan = self._plan()
-        for i in range(self.ndims):
-            self._register(_lib.NG_COEF_GRAD, i, lambda i=i: 1.0 / h[i])
-        outs = [_device.empty_like_device(x) for _ in range(self.ndims)]
-        ptrs = _lib.ptr_array([o.data_ptr() for o in outs])
-        _lib.check(_lib.load().ng_curv_gradient(plan.handle, x.data_ptr(), ptrs,
-                                                _device.current_stream_ptr()), "ng_curv_gradient")
+        with _device.device_of(x):
+            plan = self._plan()
+            for i in range(self.ndims):
+                self._register(_lib.NG_COEF_GRAD, i, lambda i=i: 1.0 / h[i])
+            outs = [_device.empty_like_device(x) for _ in range(self.ndims)]
+            ptrs = _lib.ptr_array([o.data_ptr() for o in outs])
+            _lib.check(_lib.load().ng_curv_gradient(plan.handle, x.data_ptr(), ptrs,
+                                                    _device.current_stream_ptr()), "ng_curv_gradient")
         return tuple(self._finish(o, to_host) for o in outs)
 
     def divergence(self, *v):
         """(1/J) sum_i d/dq_i (J/h_i v_i) (curvilinear.py:179-215)."""
+        if len(v) == self.ndims:
+            c = self._complex_split(list(v), self.divergence)
+            if c is not None:
+                return c
         if len(v) != self.ndims:
             raise ValueError(f"Expected {self.ndims} vector components, got {len(v)}.")
         self._ensure_diff_ops()
         h = self._evaluate_scale_factors()
         J = self._evaluate_jacobian()
         xs, to_host = self._stage(list(v))
-        plan = self._plan()
-        self._register(_lib.NG_COEF_J, 0, lambda: J)
-        for i in range(self.ndims):
-            self._register(_lib.NG_COEF_DIV, i, lambda i=i: J / h[i])
-        out = _device.empty_like_device(xs[0])
-        ptrs = _lib.ptr_array([x.data_ptr() for x in xs])
-        _lib.check(_lib.load().ng_curv_divergence(plan.handle, ptrs, out.data_ptr(),
-                                                  _device.current_stream_ptr()), "ng_curv_divergence")
+        with _device.device_of(xs[0]):
+            plan = self._plan()
+            self._register(_lib.NG_COEF_J, 0, lambda: J)
+            for i in range(self.ndims):
+                self._register(_lib.NG_COEF_DIV, i, lambda i=i: J / h[i])
+            out = _device.empty_like_device(xs[0])
+            ptrs = _lib.ptr_array([x.data_ptr() for x in xs])
+            _lib.check(_lib.load().ng_curv_divergence(plan.handle, ptrs, out.data_ptr(),
+                                                      _device.current_stream_ptr()), "ng_curv_divergence")
         return self._finish(out, to_host)
 
     def laplacian(self, f):
         """(1/J) sum_i d/dq_i (J/h_i^2 d f/d q_i): a DOUBLE first-derivative apply per axis
         (curvilinear.py:217-244), not a sum of second-derivative operators."""
+        c = self._complex_split([f], self.laplacian)
+        if c is not None:
+            return c
         self._ensure_diff_ops()
         h = self._evaluate_scale_factors()
         J = self._evaluate_jacobian()
         (x,), to_host = self._stage([f])
-        plan = self._plan()
-        self._register(_lib.NG_COEF_J, 0, lambda: J)
-        for i in range(self.ndims):
-            self._register(_lib.NG_COEF_LAP, i, lambda i=i: J / h[i] ** 2)
-        out = _device.empty_like_device(x)
-        _lib.check(_lib.load().ng_curv_laplacian(plan.handle, x.data_ptr(), out.data_ptr(),
-                                                 _device.current_stream_ptr()), "ng_curv_laplacian")
+        with _device.device_of(x):
+            plan = self._plan()
+            self._register(_lib.NG_COEF_J, 0, lambda: J)
+            for i in range(self.ndims):
+                self._register(_lib.NG_COEF_LAP, i, lambda i=i: J / h[i] ** 2)
+            out = _device.empty_like_device(x)
+            _lib.check(_lib.load().ng_curv_laplacian(plan.handle, x.data_ptr(), out.data_ptr(),
+                                                     _device.current_stream_ptr()), "ng_curv_laplacian")
         return self._finish(out, to_host)
 
     def curl(self, *v):
@@ -162,19 +197,23 @@ class CurvilinearGrid(Grid):
         raise ValueError("Curl is only defined for 2D and 3D grids.")
 
     def _curl_common(self, v, pairs):
+        c = self._complex_split(list(v), lambda *w: tuple(self._curl_common(w, pairs)))
+        if c is not None:
+            return list(c)
         self._ensure_diff_ops()
         h = self._evaluate_scale_factors()
         xs, to_host = self._stage(list(v))
-        plan = self._plan()
-        for i in range(self.ndims):
-            self._register(_lib.NG_COEF_H, i, lambda i=i: h[i])
-        for c, (j, k) in enumerate(pairs):
-            self._register(_lib.NG_COEF_CURL, c, lambda j=j, k=k: 1.0 / (h[j] * h[k]))
-        outs = [_device.empty_like_device(xs[0]) for _ in pairs]
-        vin = _lib.ptr_array([x.data_ptr() for x in xs])
-        vout = _lib.ptr_array([o.data_ptr() for o in outs])
-        _lib.check(_lib.load().ng_curv_curl(plan.handle, vin, vout, _device.current_stream_ptr()),
-                   "ng_curv_curl")
+        with _device.device_of(xs[0]):
+            plan = self._plan()
+            for i in range(self.ndims):
+                self._register(_lib.NG_COEF_H, i, lambda i=i: h[i])
+            for c, (j, k) in enumerate(pairs):
+                self._register(_lib.NG_COEF_CURL, c, lambda j=j, k=k: 1.0 / (h[j] * h[k]))
+            outs = [_device.empty_like_device(xs[0]) for _ in pairs]
+            vin = _lib.ptr_array([x.data_ptr() for x in xs])
+            vout = _lib.ptr_array([o.data_ptr() for o in outs])
+            _lib.check(_lib.load().ng_curv_curl(plan.handle, vin, vout, _device.current_stream_ptr()),
+                       "ng_curv_curl")
         return [self._finish(o, to_host) for o in outs]
 
     def _curl_2d(self, v0, v1):

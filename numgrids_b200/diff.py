@@ -24,11 +24,12 @@ from .axes import EquidistantAxis, LogAxis
 class DeviceOperator:
     """Callable ``f -> D f`` backed by an ``ng_plan`` (created on first use)."""
 
-    def __init__(self, shape, plan_factory, flexible_shape=False):
+    def __init__(self, shape, plan_factory, flexible_shape=False, real_result_only=False):
         self.shape = tuple(int(s) for s in shape)
         self._factory = plan_factory
         self._plan = None
         self._flex = flexible_shape
+        self.real_result_only = real_result_only     # FFTDiff: np.real(ifft(..)) drops the imaginary part
 
     # -- plan ----------------------------------------------------------
     @property
@@ -49,10 +50,19 @@ class DeviceOperator:
 
     # -- user level ----------------------------------------------------
     def __call__(self, f):
+        if _device.is_complex(f):
+            # The operator is real and linear.  FD / log / Chebyshev in the reference differentiate complex
+            # fields componentwise (findiff's `w * y`, scipy's sparse matvec); FFTDiff keeps `np.real(...)` of
+            # the result (numgrids/diff.py:141), i.e. the derivative of the real part as a REAL array.
+            re, im = _device.split_complex(f)
+            if self.real_result_only:
+                return self(re)
+            return _device.join_complex(self(re), self(im))
         if _device.is_device_array(f):
             x = _device.as_device_tensor(f, self.shape)
-            out = _device.empty_like_device(x)
-            self.apply_ptr(x.data_ptr(), out.data_ptr())
+            with _device.device_of(x):
+                out = _device.empty_like_device(x)
+                self.apply_ptr(x.data_ptr(), out.data_ptr())
             return out
         a = _device.as_host_array(f, self.shape)
         _lib.require_gpu()
@@ -193,7 +203,7 @@ class FFTDiff(GridDiff):
         self._W_1d = _tables.fft_multiplier(n, self.axis.spacing, order)
         self._dense = None
         self._D = None
-        self.operator = DeviceOperator(grid.shape, self._make_plan)
+        self.operator = DeviceOperator(grid.shape, self._make_plan, real_result_only=True)
 
     def _dense_matrix(self):
         if self._dense is None:
