@@ -321,7 +321,7 @@ template <int R, bool SLAB>
 __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int nz, i64 sx, i64 goff,
                                               const Lap3U& W, const Lap3Side* side,
                                               const double* __restrict__ in, double* __restrict__ out,
-                                              unsigned a_hlo, unsigned a_hhi,
+                                              int dL, int stL, int dR, int stR,
                                               unsigned a_cen, bool rowfix, int ztile, int zfix,
                                               const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
                                               const Rows<R>& D, const Rows<R>& E) {
@@ -353,11 +353,11 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
     for (int r = 0; r < R; ++r) {
         if (y0 + r >= ny) break;                                // ragged last tile (warp-uniform)
         const double2 cc = C.v[r];
-        double2 L = lds2(a_cen + r * PB - 16), Rn = lds2(a_cen + r * PB + 16);
-        if (SLAB) {     // neighbour rank's planes, staged next to the ring by the producer's halo TMAs
-            if (a_hlo) L = lds2(a_hlo + r * 16);        // lane 0 of the first z tile
-            if (a_hhi) Rn = lds2(a_hhi + r * 16);       // lane 31 of the last z tile
-        }
+        // z neighbours: the pairs left and right of the own one in the staged row -- or, for the edge lane of
+        // a slab's first / last z tile, the neighbour rank's pair staged behind the plane in the same slot
+        // (per-lane offset and row stride, so this costs no branch: profiles/r02_slab_edge_tiles.txt)
+        const double2 L = SLAB ? lds2(a_cen + dL + r * stL) : lds2(a_cen + r * PB - 16);
+        const double2 Rn = SLAB ? lds2(a_cen + dR + r * stR) : lds2(a_cen + r * PB + 16);
         // The reference starts every tap sum from +0.0.  `0.0 + p` only differs from `p` when p is
         // -0.0, and a sum that starts from its first product can end as -0.0 only if EVERY product
         // was -0.0; that sign survives to the output only if all three axis sums are -0.0, which the
@@ -431,16 +431,15 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
     constexpr int TY = R * WY;
     constexpr int ROWS = TY + 4;
     constexpr int PLANE = ROWS * RING_PITCH;          // doubles per ring slot
-    constexpr unsigned PLANE_B = PLANE * 8, RING_B = S * PLANE_B, PB = RING_PITCH * 8;
+    // slab mode: every slot carries, behind its plane, the nb=2 neighbour columns of the tile's rows
+    // ([ROWS][2] doubles per side, padded to 256 bytes so that the next slot stays 128-byte aligned)
+    constexpr unsigned HALO_B = SLAB ? ((ROWS * 16 + 255) / 256) * 256 : 0;
+    constexpr unsigned PLANE_B = PLANE * 8, SLOT_B = PLANE_B + 2 * HALO_B, RING_B = S * SLOT_B, PB = RING_PITCH * 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // TMA destinations must be 128-byte aligned (the launch reserves 128 spare bytes)
     double* ring = reinterpret_cast<double*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    // slab mode: per slot, the nb=2 neighbour columns of the tile's rows ([ROWS][2] doubles) per side
-    constexpr int HALO = SLAB ? ((ROWS * 2 + 15) / 16) * 16 : 0;   // doubles per slot and side (128-B slots)
-    constexpr unsigned HALO_B = HALO * 8;
-    double* hlo = ring + (size_t)S * PLANE;
-    double* hhi = hlo + (size_t)S * HALO;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(hhi + (size_t)S * HALO);
+    unsigned char* const ring_b = reinterpret_cast<unsigned char*>(ring);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring_b + RING_B);
     unsigned long long* empty = full + S;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -474,13 +473,14 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
             for (int q = 0; q < nplanes; ++q) {
                 if (q >= S) mbar_wait(&empty[s], eph ^ 1);
                 mbar_arrive_expect_tx(&full[s], tx);   // bytes the TMAs deliver (slots are padded to 128 B)
-                tma_load_3d(ring + (size_t)s * PLANE, &tmap, z0 - 2, yb - 2, p_first + q, &full[s]);
+                unsigned char* const slot = ring_b + (size_t)s * SLOT_B;
+                tma_load_3d(slot, &tmap, z0 - 2, yb - 2, p_first + q, &full[s]);
                 if (SLAB) {
                     // halo planes are [nx][ny][2]: the tile's ROWS x 2 values of one plane are ONE contiguous
                     // 16*ROWS-byte run, fetched as a single-row 2-D box (a {2, ROWS, 1} box would cost ROWS
                     // 16-byte row requests -- as many TMA row operations as the main box)
-                    if (lo_tile) tma_load_2d(hlo + (size_t)s * HALO, &tmap_lo, 2 * (yb - 2), p_first + q, &full[s]);
-                    if (hi_tile) tma_load_2d(hhi + (size_t)s * HALO, &tmap_hi, 2 * (yb - 2), p_first + q, &full[s]);
+                    if (lo_tile) tma_load_2d(slot + PLANE_B, &tmap_lo, 2 * (yb - 2), p_first + q, &full[s]);
+                    if (hi_tile) tma_load_2d(slot + PLANE_B + HALO_B, &tmap_hi, 2 * (yb - 2), p_first + q, &full[s]);
                 }
                 if (++s == S) { s = 0; if (q >= S) eph ^= 1; }
             }
@@ -503,11 +503,12 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
     const bool rowfix = (y0 < 2) || (y0 + R > ny - 2);                            // warp-uniform, rare
     const int ztile = (zfix_lo ? 1 : 0) | (zfix_hi ? 2 : 0);                      // warp-uniform
     const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
-    // this lane's halo pair address in slot 0 (0 = not an edge lane of an edge tile)
-    unsigned a_hlo = (lo_tile && lane == 0) ? smem_u32(hlo) + (unsigned)(j0 + 2) * 16u : 0u;
-    unsigned a_hhi = (hi_tile && lane == 31) ? smem_u32(hhi) + (unsigned)(j0 + 2) * 16u : 0u;
-
     const unsigned my_off = (unsigned)(((j0 + 2) * RING_PITCH + 2 + 2 * lane) * 8);
+    // z neighbours of the own pair, relative to it: 16 bytes to either side in the staged row; the edge lane
+    // of a slab's first / last tile reads the neighbour rank's pair behind the plane instead (row stride 16)
+    int dL = -16, stL = (int)PB, dR = 16, stR = (int)PB;
+    if (lo_tile && lane == 0) { dL = (int)(PLANE_B + (unsigned)(j0 + 2) * 16u) - (int)my_off; stL = 16; }
+    if (hi_tile && lane == 31) { dR = (int)(PLANE_B + HALO_B + (unsigned)(j0 + 2) * 16u) - (int)my_off; stR = 16; }
     const unsigned ring_a = smem_u32(ring) + my_off;
     unsigned a_new = ring_a, bar_new = smem_u32(full), ph = 0;
     unsigned a_cen = ring_a, bar_cen = smem_u32(empty);          // centre = plane q-2 (valid from q = 2)
@@ -517,15 +518,11 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
 
     Rows<R> w0, w1, w2, w3, w4;
 #define NG_ADV_NEW()                                                                   \
-    a_new += PLANE_B; bar_new += 8;                                                    \
+    a_new += SLOT_B; bar_new += 8;                                                     \
     if (++s_new == S) { s_new = 0; a_new -= RING_B; bar_new -= 8 * S; ph ^= 1; }
 #define NG_ADV_CEN()                                                                   \
-    a_cen += PLANE_B; bar_cen += 8;                                                    \
-    if (SLAB) { if (a_hlo) a_hlo += HALO_B; if (a_hhi) a_hhi += HALO_B; }              \
-    if (++s_cen == S) {                                                                \
-        s_cen = 0; a_cen -= RING_B; bar_cen -= 8 * S;                                  \
-        if (SLAB) { if (a_hlo) a_hlo -= S * HALO_B; if (a_hhi) a_hhi -= S * HALO_B; }  \
-    }
+    a_cen += SLOT_B; bar_cen += 8;                                                     \
+    if (++s_cen == S) { s_cen = 0; a_cen -= RING_B; bar_cen -= 8 * S; }
 #define NG_LOAD_NEW(NEW)                                                               \
     mbar_wait_a(bar_new, ph);                                                          \
     _Pragma("unroll") for (int r = 0; r < R; ++r) NEW.v[r] = lds2(a_new + r * PB);     \
@@ -546,7 +543,7 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
 #define NG_RING2_STEP(A, B, C, D, NEW)                                                 \
     {                                                                                  \
         NG_LOAD_NEW(NEW)                                                               \
-        ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, a_hlo, a_hhi, a_cen, \
+        ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, dL, stL, dR, stR, a_cen, \
                                rowfix, ztile, zfix, A, B, C, D, NEW);                         \
         NG_RELEASE_CEN()                                                               \
         ++x; goff += sx;                                                               \
@@ -655,8 +652,8 @@ int launch_ring2(const ng_plan* p, const double* in, double* out, const double* 
                  int xbeg, int xend, int xchunk, int zmode, const Lap3U& WU, cudaStream_t st, bool* launched) {
     constexpr int TY = R * WY, ROWS = TY + 4, plane = ROWS * RING_PITCH;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
-    const size_t smem = (size_t)S * plane * sizeof(double) + 2 * S * sizeof(unsigned long long) +
-                        (SLAB ? (size_t)S * 2 * (((ROWS * 2 + 15) / 16) * 16) * sizeof(double) : 0) + 128;
+    const size_t smem = (size_t)S * (plane * sizeof(double) + (SLAB ? 2 * (((ROWS * 16 + 255) / 256) * 256) : 0)) +
+                        2 * S * sizeof(unsigned long long) + 128;
     NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB>);
     const unsigned ztiles = (unsigned)(nz / RING_TZ);
     const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2)
