@@ -322,7 +322,7 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
                                               const Lap3U& W, const Lap3Side* side,
                                               const double* __restrict__ in, double* __restrict__ out,
                                               int dL, int stL, int dR, int stR,
-                                              unsigned a_cen, bool rowfix, int ztile, int zfix,
+                                              unsigned a_cen, bool rowfix, int ztile, int zfix, int zoff,
                                               const Rows<R>& A, const Rows<R>& B, const Rows<R>& C,
                                               const Rows<R>& D, const Rows<R>& E) {
     constexpr unsigned PB = RING_PITCH * 8;
@@ -340,14 +340,14 @@ __device__ __forceinline__ void ring2_compute(int x, int y0, int nx, int ny, int
     // boundary lane collects them by shuffle -- one sum's latency per step instead of 2R (the
     // single-lane version cost +35 % FP64 issue on every boundary tile, i.e. on half of the
     // tiles of a 256-wide slab).  ztile: 1 = first tile, 2 = last tile, 3 = both (nz == 64).
-    const int lane_ = threadIdx.x & 31;
+    // Each of the two cases is its own copy of the sum: tap direction and weight table are then compile-time
+    // (constant-bank operands) instead of selected per step (+23 thread-instructions per point on the boundary
+    // tiles before, profiles/r02_slab_edge_tiles.txt); `zoff` is the lane's operand offset from its own pair.
     double zsum = 0.0;
-    if (ztile == 1 || ztile == 2) {                             // warp-uniform
-        if (lane_ < 2 * R) {
-            const int rr = lane_ >> 1, cc_ = lane_ & 1;
-            const unsigned edge = ztile == 1 ? a_cen - 16u * lane_ : a_cen + 16u * (31 - lane_);   // the boundary lane's pair
-            zsum = onesided6_z_smem(ztile == 1 ? W.wfz : W.wbz, edge + rr * PB + cc_ * 8, ztile == 1 ? 8 : -8, W.ih[2]);
-        }
+    if (ztile == 1) {                                           // warp-uniform
+        if (zoff != 0x7fffffff) zsum = onesided6_z_smem(W.wfz, a_cen + zoff, 8, W.ih[2]);
+    } else if (ztile == 2) {
+        if (zoff != 0x7fffffff) zsum = onesided6_z_smem(W.wbz, a_cen + zoff, -8, W.ih[2]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -421,7 +421,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
         ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int R, int WY, int S, int MINB, bool SLAB>
+template <int R, int WY, int S, int MINB, bool SLAB, bool ROT = false>
 __global__ void __launch_bounds__(32 * (WY + 1), MINB)
 fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
                      int xchunk, int xbeg, int xend, int zmode, Lap3U W, const Lap3Side* __restrict__ side,
@@ -503,6 +503,11 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
     const bool rowfix = (y0 < 2) || (y0 + R > ny - 2);                            // warp-uniform, rare
     const int ztile = (zfix_lo ? 1 : 0) | (zfix_hi ? 2 : 0);                      // warp-uniform
     const int zfix = (zfix_lo && lane == 0) ? 1 : ((zfix_hi && lane == 31) ? 2 : 0);
+    // global z boundary: lane i < 2R computes the one-sided sum of (row i/2, boundary point i%2); its first operand
+    // sits at this offset from the lane's own pair (the boundary lane's pair is 16 bytes per lane away)
+    int zoff = 0x7fffffff;
+    if (lane < 2 * R && (ztile == 1 || ztile == 2))
+        zoff = (ztile == 1 ? -16 * lane : 16 * (31 - lane)) + (lane >> 1) * (int)PB + (lane & 1) * 8;
     const unsigned my_off = (unsigned)(((j0 + 2) * RING_PITCH + 2 + 2 * lane) * 8);
     // z neighbours of the own pair, relative to it: 16 bytes to either side in the staged row; the edge lane
     // of a slab's first / last tile reads the neighbour rank's pair behind the plane instead (row stride 16)
@@ -544,17 +549,25 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
     {                                                                                  \
         NG_LOAD_NEW(NEW)                                                               \
         ring2_compute<R, SLAB>(x, y0, nx, ny, nz, sx, goff, W, side, in, out, dL, stL, dR, stR, a_cen, \
-                               rowfix, ztile, zfix, A, B, C, D, NEW);                         \
+                               rowfix, ztile, zfix, zoff, A, B, C, D, NEW);                   \
         NG_RELEASE_CEN()                                                               \
         ++x; goff += sx;                                                               \
         if (--left == 0) break;                                                        \
     }
-    for (;;) {
-        NG_RING2_STEP(w0, w1, w2, w3, w4)
-        NG_RING2_STEP(w1, w2, w3, w4, w0)
-        NG_RING2_STEP(w2, w3, w4, w0, w1)
-        NG_RING2_STEP(w3, w4, w0, w1, w2)
-        NG_RING2_STEP(w4, w0, w1, w2, w3)
+    if (ROT) {
+        // one copy of the step, window shifted by register moves (a fifth of the code: instruction-cache experiment)
+        for (;;) {
+            NG_RING2_STEP(w0, w1, w2, w3, w4)
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+        }
+    } else {
+        for (;;) {
+            NG_RING2_STEP(w0, w1, w2, w3, w4)
+            NG_RING2_STEP(w1, w2, w3, w4, w0)
+            NG_RING2_STEP(w2, w3, w4, w0, w1)
+            NG_RING2_STEP(w3, w4, w0, w1, w2)
+            NG_RING2_STEP(w4, w0, w1, w2, w3)
+        }
     }
 #undef NG_RING2_STEP
 #undef NG_RELEASE_CEN
@@ -647,14 +660,14 @@ int cached_tmap(CUtensorMap* tm, const TmapKey& k) {
     return NG_OK;
 }
 
-template <int R, int WY, int S, int MINB, bool SLAB>
+template <int R, int WY, int S, int MINB, bool SLAB, bool ROT = false>
 int launch_ring2(const ng_plan* p, const double* in, double* out, const double* lo, const double* hi,
                  int xbeg, int xend, int xchunk, int zmode, const Lap3U& WU, cudaStream_t st, bool* launched) {
     constexpr int TY = R * WY, ROWS = TY + 4, plane = ROWS * RING_PITCH;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
     const size_t smem = (size_t)S * (plane * sizeof(double) + (SLAB ? 2 * (((ROWS * 16 + 255) / 256) * 256) : 0)) +
                         2 * S * sizeof(unsigned long long) + 128;
-    NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB>);
+    NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB, ROT>);
     const unsigned ztiles = (unsigned)(nz / RING_TZ);
     const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2)
                          : zmode == 3 ? (ztiles >= 4 ? 2 : 0) : ztiles);
@@ -669,7 +682,7 @@ int launch_ring2(const ng_plan* p, const double* in, double* out, const double* 
     if (!rc && SLAB && lo) rc = cached_tmap(&tm_lo, TmapKey{lo, nx, ny, 2, 2 * ROWS, 1, 2});
     if (!rc && SLAB && hi) rc = cached_tmap(&tm_hi, TmapKey{hi, nx, ny, 2, 2 * ROWS, 1, 2});
     if (rc) return rc;
-    fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB><<<grid, 32 * (WY + 1), smem, st>>>(
+    fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB, ROT><<<grid, 32 * (WY + 1), smem, st>>>(
         out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, zmode, WU, (const Lap3Side*)p->d_Mt, in, lo, hi, tm,
         tm_lo, tm_hi);
     NG_TRACE(SLAB ? "fdlap3d_ring2<slab>" : "fdlap3d_ring2");
@@ -733,6 +746,7 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         if (slab && NG_ENV_INT("NG_FDLAP_EDGE_TEST", 0))        // timing experiment (wrong edge columns): boundary tiles with neither halo nor one-sided work
             rc = launch_ring2<2, 4, 8, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slab) rc = launch_ring2<2, 4, 8, 3, true>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
+        else if (NG_ENV_INT("NG_FDLAP_ROT", 0)) rc = launch_ring2<2, 4, 8, 3, false, true>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slots == 10) rc = launch_ring2<2, 4, 10, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slots == 6) rc = launch_ring2<2, 4, 6, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else rc = launch_ring2<2, 4, 8, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);

@@ -67,7 +67,7 @@ class Clock:
 
 
 def env(**kw):
-    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST"):
+    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST", "NG_FDLAP_ROT"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -100,6 +100,8 @@ variants = {
     "whole S=6": whole(NG_FDLAP_S=6),
     "whole S=10": whole(NG_FDLAP_S=10),
     "whole S=8 xc=32": whole(NG_FDLAP_XCHUNK=32),
+    "whole, window rotated by moves": whole(NG_FDLAP_ROT=1),
+    "whole, rotated, xc=128": whole(NG_FDLAP_ROT=1, NG_FDLAP_XCHUNK=128),
     "whole S=8 xc=128": whole(NG_FDLAP_XCHUNK=128),
     "whole S=10 xc=128": whole(NG_FDLAP_S=10, NG_FDLAP_XCHUNK=128),
     "slab: interior + boundary, serial": ({}, parts_serial),
