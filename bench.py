@@ -404,8 +404,16 @@ def per_config_extras(torch, ng, peak_gbs, quick):
                     s.wait_stream(b_)
         torch.cuda.current_stream().wait_stream(s)
         ms_graph8 = timed(graph8.replay, 5, 2) / (5 * nbuf)
+        # the 80 fields as one stack in ONE launch (ng_apply_batch): the streaming kernel at its large-array rate
+        from numgrids_b200 import _lib as _L
+        lib_ = _L.load()
+        st_ptr = torch.cuda.current_stream().cuda_stream
+        ms_batch = timed(lambda: _L.check(lib_.ng_apply_batch(op.plan.handle, ins.data_ptr(), outs.data_ptr(), nbuf, st_ptr)),
+                         10, 3, True) / nbuf
         pts = 512 * 512
         out["cfg1_fd_512x512_order1_axis0"] = {
+            "gpts_batched_80_fields_one_launch": pts / ms_batch / 1e6, "ms_per_apply_batched": ms_batch,
+            "hbm_frac_batched": 16 * pts / ms_batch / 1e6 / peak_gbs,
             "gpts_single_launch_cold_l2": pts / ms_single / 1e6, "ms_single_launch": ms_single,
             "gpts_graph_replay_rotating_320MiB": pts / ms_graph / 1e6, "ms_per_apply_graph": ms_graph,
             "hbm_frac_graph": 16 * pts / ms_graph / 1e6 / peak_gbs,

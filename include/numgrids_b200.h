@@ -117,6 +117,9 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis,
 int ng_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream);
 int ng_apply_fused(const ng_plan* plan, const double* d_in, double* d_out,
                    const ng_fuse* fuse, void* stream);
+/* `count` fields of the plan's shape stacked contiguously ([count][shape...], in and out): one launch for all of
+ * them.  Small grids are launch-bound one field at a time; a stack streams at the large-array rate. */
+int ng_apply_batch(const ng_plan* plan, const double* d_in, double* d_out, int64_t count, void* stream);
 /* Same from host buffers (pinned or pageable): H2D, kernel, D2H, synchronous. */
 int ng_apply_host(ng_plan* plan, const double* h_in, double* h_out);
 /* Slab variant for a finite-difference plan whose `axis` is sharded across ranks: d_lo_halo /

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ng_fft_plan_create": (C.c_int, [C.c_int, _I64, C.c_int, _D, _D, _PP]),
     "ng_apply": (C.c_int, [_P, _P, _P, _P]),
     "ng_apply_fused": (C.c_int, [_P, _P, _P, C.POINTER(NgFuse), _P]),
+    "ng_apply_batch": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "ng_apply_host": (C.c_int, [_P, _P, _P]),
     "ng_fd_apply_slab": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ng_fd_pack_halo": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -36,6 +36,14 @@ class Diff:
     def as_matrix(self):
         return self.operator.as_matrix()
 
+    def as_linear_operator(self):
+        """Matrix-free scipy ``LinearOperator`` (extension; the reference only offers ``as_matrix``)."""
+        return self.operator.as_linear_operator()
+
+    def apply_batch(self, fs):
+        """K stacked device fields of shape (K, *grid.shape) in one launch (extension for launch-bound sizes)."""
+        return self.operator.operator.apply_batch(fs)
+
 
 class AxisType(str, enum.Enum):
     EQUIDISTANT = "equidistant"

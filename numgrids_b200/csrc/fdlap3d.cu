@@ -205,7 +205,8 @@ fdlap3d_march_kernel(const double* __restrict__ in, double* __restrict__ out, in
 //     the centre product w[2]*f is formed once for the three axis sums;
 //   * 32-bit shared addresses advanced incrementally (no div/mod, no generic->shared conversion),
 //     LDS.128 through inline PTX; running global output offset;
-//   * the 4 prologue steps (window fill) are peeled, so the steady-state step has no prologue tests;
+//   * the 4 prologue steps (window fill) are peeled, so the steady-state step has no prologue tests; the
+//     step exists once (window shifted by register moves): the loop fits the instruction cache;
 //   * slab-halo handling (neighbour rank's planes, two more TMAs per plane) compiled in only for
 //     the SLAB instantiation, which runs on the first/last z tile only (zmode 2): interior tiles of
 //     a slab never read a halo and always run the plain instantiation.
@@ -421,7 +422,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
         ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int R, int WY, int S, int MINB, bool SLAB, bool ROT = false>
+template <int R, int WY, int S, int MINB, bool SLAB>
 __global__ void __launch_bounds__(32 * (WY + 1), MINB)
 fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
                      int xchunk, int xbeg, int xend, int zmode, Lap3U W, const Lap3Side* __restrict__ side,
@@ -554,20 +555,12 @@ fdlap3d_ring2_kernel(double* __restrict__ out, int nx, int ny, int nz,
         ++x; goff += sx;                                                               \
         if (--left == 0) break;                                                        \
     }
-    if (ROT) {
-        // one copy of the step, window shifted by register moves (a fifth of the code: instruction-cache experiment)
-        for (;;) {
-            NG_RING2_STEP(w0, w1, w2, w3, w4)
-            w0 = w1; w1 = w2; w2 = w3; w3 = w4;
-        }
-    } else {
-        for (;;) {
-            NG_RING2_STEP(w0, w1, w2, w3, w4)
-            NG_RING2_STEP(w1, w2, w3, w4, w0)
-            NG_RING2_STEP(w2, w3, w4, w0, w1)
-            NG_RING2_STEP(w3, w4, w0, w1, w2)
-            NG_RING2_STEP(w4, w0, w1, w2, w3)
-        }
+    // ONE copy of the step; the 5-plane window is shifted by register moves (4R MOV pairs against ~430
+    // instructions of work).  Unrolling the step five times to rotate the window by renaming made the loop
+    // 34 KB of code -- more than the instruction cache holds: 8-12 % slower (profiles/r02_tune_fdlap.txt).
+    for (;;) {
+        NG_RING2_STEP(w0, w1, w2, w3, w4)
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4;
     }
 #undef NG_RING2_STEP
 #undef NG_RELEASE_CEN
@@ -660,14 +653,14 @@ int cached_tmap(CUtensorMap* tm, const TmapKey& k) {
     return NG_OK;
 }
 
-template <int R, int WY, int S, int MINB, bool SLAB, bool ROT = false>
+template <int R, int WY, int S, int MINB, bool SLAB>
 int launch_ring2(const ng_plan* p, const double* in, double* out, const double* lo, const double* hi,
                  int xbeg, int xend, int xchunk, int zmode, const Lap3U& WU, cudaStream_t st, bool* launched) {
     constexpr int TY = R * WY, ROWS = TY + 4, plane = ROWS * RING_PITCH;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
     const size_t smem = (size_t)S * (plane * sizeof(double) + (SLAB ? 2 * (((ROWS * 16 + 255) / 256) * 256) : 0)) +
                         2 * S * sizeof(unsigned long long) + 128;
-    NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB, ROT>);
+    NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB>);
     const unsigned ztiles = (unsigned)(nz / RING_TZ);
     const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2)
                          : zmode == 3 ? (ztiles >= 4 ? 2 : 0) : ztiles);
@@ -682,7 +675,7 @@ int launch_ring2(const ng_plan* p, const double* in, double* out, const double* 
     if (!rc && SLAB && lo) rc = cached_tmap(&tm_lo, TmapKey{lo, nx, ny, 2, 2 * ROWS, 1, 2});
     if (!rc && SLAB && hi) rc = cached_tmap(&tm_hi, TmapKey{hi, nx, ny, 2, 2 * ROWS, 1, 2});
     if (rc) return rc;
-    fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB, ROT><<<grid, 32 * (WY + 1), smem, st>>>(
+    fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB><<<grid, 32 * (WY + 1), smem, st>>>(
         out, (int)nx, (int)ny, (int)nz, xchunk, xbeg, xend, zmode, WU, (const Lap3Side*)p->d_Mt, in, lo, hi, tm,
         tm_lo, tm_hi);
     NG_TRACE(SLAB ? "fdlap3d_ring2<slab>" : "fdlap3d_ring2");
@@ -746,7 +739,6 @@ int ng_fdlap3d_try_launch(const ng_plan* p, const double* in, double* out, const
         if (slab && NG_ENV_INT("NG_FDLAP_EDGE_TEST", 0))        // timing experiment (wrong edge columns): boundary tiles with neither halo nor one-sided work
             rc = launch_ring2<2, 4, 8, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slab) rc = launch_ring2<2, 4, 8, 3, true>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
-        else if (NG_ENV_INT("NG_FDLAP_ROT", 0)) rc = launch_ring2<2, 4, 8, 3, false, true>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slots == 10) rc = launch_ring2<2, 4, 10, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else if (slots == 6) rc = launch_ring2<2, 4, 6, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);
         else rc = launch_ring2<2, 4, 8, 3, false>(p, in, out, lo, hi, xbeg, xend, xchunk, zmode, WU, st, &launched);

@@ -48,6 +48,18 @@ class DeviceOperator:
             _lib.check(lib.ng_apply_fused(self.plan.handle, d_in, d_out, C.byref(fuse), st),
                        "ng_apply_fused")
 
+    def apply_batch(self, fs):
+        """`fs`: CUDA array of shape (K, *grid.shape) -- K fields stacked; returns the K derivatives in one
+        launch (``ng_apply_batch``).  For grids so small that one apply is launch-bound (BASELINE cfg1)."""
+        x = _device.as_device_tensor(fs)
+        if tuple(x.shape[1:]) != self.shape or x.dim() != len(self.shape) + 1:
+            raise ValueError(f"expected a stack of shape (K, {', '.join(map(str, self.shape))}), got {tuple(x.shape)}")
+        with _device.device_of(x):
+            out = _device.empty_like_device(x)
+            _lib.check(_lib.load().ng_apply_batch(self.plan.handle, x.data_ptr(), out.data_ptr(), int(x.shape[0]),
+                                                  _device.current_stream_ptr()), "ng_apply_batch")
+        return out
+
     # -- user level ----------------------------------------------------
     def __call__(self, f):
         if _device.is_complex(f):
@@ -103,6 +115,25 @@ class GridDiff:
 
     def as_matrix(self):
         raise NotImplementedError
+
+    def as_linear_operator(self):
+        """Matrix-free ``scipy.sparse.linalg.LinearOperator`` of shape (grid.size, grid.size): ``matvec`` runs the
+        device operator on the flattened vector (no Kronecker matrix is ever built -- what makes the reference's
+        ``as_matrix()`` consumers unusable at scale, numgrids/diff.py:90-91, :130-131, :201-202); ``rmatvec`` /
+        dense products fall back to the lazily assembled sparse matrix."""
+        from scipy.sparse.linalg import LinearOperator
+        n = int(np.prod(self.grid.shape))
+        shape = tuple(self.grid.shape)
+
+        def matvec(v):
+            v = np.asarray(v)
+            return np.asarray(self.operator(v.reshape(shape))).reshape(-1)
+
+        def rmatvec(v):
+            return self.as_matrix().T @ np.asarray(v).reshape(-1)
+
+        return LinearOperator((n, n), matvec=matvec, rmatvec=rmatvec,
+                              dtype=np.float64)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -373,3 +373,46 @@ def test_laplacian_z_parts(gpu_ready):
             lap.apply_part(f, out, 1, *halos)
             lap.apply_part(f, out, 2, *halos)
             assert torch.equal(out, ref), (shape, [h is not None for h in halos])
+
+
+def test_apply_batch_equals_single_applies(gpu_ready):
+    """ng_apply_batch: K stacked fields in one launch are bit-identical to K single applies (FD, Chebyshev, FFT
+    axes; contiguous and strided), and a stack of cfg1-size fields takes the streaming kernel."""
+    import torch
+    from numgrids_b200 import _lib
+    torch.manual_seed(11)
+    ax = ng.create_axis(A.EQUIDISTANT, 512, 0.0, 1.0)
+    g = ng.Grid(ax, ax)
+    fs = torch.randn(12, 512, 512, dtype=torch.float64, device="cuda")
+    for order, axis in ((1, 0), (2, 1)):
+        d = ng.Diff(g, order, axis)
+        out = d.apply_batch(fs)
+        assert _lib.last_kernel() in ("fd_march", "fd_row<u4>"), _lib.last_kernel()
+        for k in range(12):
+            assert torch.equal(out[k], d(fs[k])), (order, axis, k)
+    axes = [ng.create_axis(A.CHEBYSHEV, 24, 0.0, 1.0), ng.create_axis(A.EQUIDISTANT_PERIODIC, 64, 0.0, 2 * np.pi),
+            ng.create_axis(A.LOGARITHMIC, 20, 0.1, 10.0)]
+    g3 = ng.Grid(*axes)
+    fs = torch.randn(5, *g3.shape, dtype=torch.float64, device="cuda")
+    for axis in range(3):
+        d = ng.Diff(g3, 1, axis)
+        out = d.apply_batch(fs)
+        for k in range(5):
+            assert torch.equal(out[k], d(fs[k])), (axis, k)
+    with pytest.raises(ValueError):
+        ng.Diff(g3, 1, 0).apply_batch(fs[:, :, :, :10])
+
+
+def test_matrix_free_linear_operator(gpu_ready):
+    """GridDiff.as_linear_operator(): matvec on the device equals the (lazily assembled) sparse matrix product."""
+    axes = [ng.create_axis(A.CHEBYSHEV, 12, 0.0, 1.0), ng.create_axis(A.EQUIDISTANT, 16, 0.0, 2.0)]
+    g = ng.Grid(*axes)
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(g.size)
+    for order, axis in ((1, 0), (2, 1)):
+        d = ng.Diff(g, order, axis)
+        L = d.as_linear_operator()
+        assert L.shape == (g.size, g.size)
+        ref = d.as_matrix() @ v
+        assert rel_linf(L @ v, ref) <= 1e-12
+        assert rel_linf(L.rmatvec(v), d.as_matrix().T @ v) <= 1e-12

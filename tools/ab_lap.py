@@ -100,8 +100,8 @@ variants = {
     "whole S=6": whole(NG_FDLAP_S=6),
     "whole S=10": whole(NG_FDLAP_S=10),
     "whole S=8 xc=32": whole(NG_FDLAP_XCHUNK=32),
-    "whole, window rotated by moves": whole(NG_FDLAP_ROT=1),
-    "whole, rotated, xc=128": whole(NG_FDLAP_ROT=1, NG_FDLAP_XCHUNK=128),
+    "whole S=6 xc=128": whole(NG_FDLAP_S=6, NG_FDLAP_XCHUNK=128),
+    "whole S=8 xc=256": whole(NG_FDLAP_XCHUNK=256),
     "whole S=8 xc=128": whole(NG_FDLAP_XCHUNK=128),
     "whole S=10 xc=128": whole(NG_FDLAP_S=10, NG_FDLAP_XCHUNK=128),
     "slab: interior + boundary, serial": ({}, parts_serial),
