@@ -190,6 +190,11 @@ int ng_check_plan_device(const ng_plan* p, const char* who);
 int ng_plan_bind_device(ng_plan* p);
 void ng_fuse_to_dev(const ng_plan* p, const ng_fuse* f, FuseDev* out);
 
+// mbarrier.try_wait suspend-time hint (ns): a waiting thread is parked by the hardware until the phase completes
+// or the hint expires, instead of polling -- a producer lane that spins issues ~10 thread-instructions per grid
+// point in the plane-ring kernels, slots the consumer warps of the same scheduler then do not get
+#define NG_MBAR_SUSPEND_NS 1000u
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

@@ -38,6 +38,20 @@
 
 namespace {
 
+// suspend-time hint of the mbarrier waits (see NG_MBAR_SUSPEND_NS in common.cuh); NG_MBAR_HINT_NS overrides it for A/B runs
+__constant__ unsigned c_mbar_hint_ns = NG_MBAR_SUSPEND_NS;
+int sync_mbar_hint(cudaStream_t st) {
+    static std::atomic<long long> current{NG_MBAR_SUSPEND_NS};
+    const long long want = NG_ENV_INT("NG_MBAR_HINT_NS", NG_MBAR_SUSPEND_NS);
+    if (want != current.load(std::memory_order_relaxed)) {
+        const unsigned v = (unsigned)want;
+        NG_CUDA_OK(cudaMemcpyToSymbolAsync(c_mbar_hint_ns, &v, sizeof(v), 0, cudaMemcpyHostToDevice, st));
+        current.store(want, std::memory_order_relaxed);
+    }
+    return NG_OK;
+}
+
+
 constexpr int CL_TZ = 64;                    // z points per tile (one double2 per lane)
 constexpr int CL_H = 4;                      // halo on every side
 constexpr int CL_PITCH = CL_TZ + 2 * CL_H;   // doubles per staged row
@@ -69,9 +83,9 @@ __device__ __forceinline__ bool cl_try(unsigned addr, unsigned parity) {
     unsigned done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(c_mbar_hint_ns) : "memory");
     return done != 0;
 }
 __device__ __noinline__ void cl_wait_slow(unsigned addr, unsigned parity) {
@@ -451,6 +465,7 @@ int cl_launch(ng_plan* p, const double* in, double* out, const ClParams& hp, boo
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
     CUtensorMap tm;
     int rc = cl_make_tmap(&tm, in, nx, ny, nz, TY + 2 * CL_H);
+    if (!rc) rc = sync_mbar_hint(st);
     if (rc) return rc;
     // x chunks: 8 planes of every chunk are loaded for the window only, yet SHORT chunks win (B200, 512^3:
     // 16 planes 1.58 ms, 64 planes 1.83 ms, 256 planes 3.1 ms, profiles/r02_tune_curvlap.txt): a warp issues

@@ -24,6 +24,20 @@
 
 namespace {
 
+// suspend-time hint of the mbarrier waits (see NG_MBAR_SUSPEND_NS in common.cuh); NG_MBAR_HINT_NS overrides it for A/B runs
+__constant__ unsigned c_mbar_hint_ns = NG_MBAR_SUSPEND_NS;
+int sync_mbar_hint(cudaStream_t st) {
+    static std::atomic<long long> current{NG_MBAR_SUSPEND_NS};
+    const long long want = NG_ENV_INT("NG_MBAR_HINT_NS", NG_MBAR_SUSPEND_NS);
+    if (want != current.load(std::memory_order_relaxed)) {
+        const unsigned v = (unsigned)want;
+        NG_CUDA_OK(cudaMemcpyToSymbolAsync(c_mbar_hint_ns, &v, sizeof(v), 0, cudaMemcpyHostToDevice, st));
+        current.store(want, std::memory_order_relaxed);
+    }
+    return NG_OK;
+}
+
+
 struct Lap3W {
     double wc[3][5], wf[3][6], wb[3][6], ih[3];
 };
@@ -239,9 +253,9 @@ __device__ __forceinline__ bool mbar_try_a(unsigned addr, unsigned parity) {
     unsigned done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(c_mbar_hint_ns) : "memory");
     return done != 0;
 }
 __device__ __noinline__ void mbar_wait_slow(unsigned addr, unsigned parity) {
@@ -661,6 +675,10 @@ int launch_ring2(const ng_plan* p, const double* in, double* out, const double* 
     const size_t smem = (size_t)S * (plane * sizeof(double) + (SLAB ? 2 * (((ROWS * 16 + 255) / 256) * 256) : 0)) +
                         2 * S * sizeof(unsigned long long) + 128;
     NG_FUNC_SMEM(smem, fdlap3d_ring2_kernel<R, WY, S, MINB, SLAB>);
+    {
+        const int hrc = sync_mbar_hint(st);
+        if (hrc) return hrc;
+    }
     const unsigned ztiles = (unsigned)(nz / RING_TZ);
     const unsigned gxz = zmode == 1 ? (ztiles > 2 ? ztiles - 2 : 0) : (zmode == 2 ? (ztiles < 2 ? ztiles : 2)
                          : zmode == 3 ? (ztiles >= 4 ? 2 : 0) : ztiles);

@@ -67,7 +67,7 @@ class Clock:
 
 
 def env(**kw):
-    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST", "NG_FDLAP_ROT"):
+    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST", "NG_MBAR_HINT_NS"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -99,11 +99,11 @@ variants = {
     "whole S=8 xc=64 (default)": whole(),
     "whole S=6": whole(NG_FDLAP_S=6),
     "whole S=10": whole(NG_FDLAP_S=10),
-    "whole S=8 xc=32": whole(NG_FDLAP_XCHUNK=32),
-    "whole S=6 xc=128": whole(NG_FDLAP_S=6, NG_FDLAP_XCHUNK=128),
-    "whole S=8 xc=256": whole(NG_FDLAP_XCHUNK=256),
+    "whole, mbarrier hint 0 ns": whole(NG_MBAR_HINT_NS=0),
+    "whole, mbarrier hint 200 ns": whole(NG_MBAR_HINT_NS=200),
+    "whole, mbarrier hint 5000 ns": whole(NG_MBAR_HINT_NS=5000),
+    "whole, mbarrier hint 50000 ns": whole(NG_MBAR_HINT_NS=50000),
     "whole S=8 xc=128": whole(NG_FDLAP_XCHUNK=128),
-    "whole S=10 xc=128": whole(NG_FDLAP_S=10, NG_FDLAP_XCHUNK=128),
     "slab: interior + boundary, serial": ({}, parts_serial),
     "slab: interior || boundary (2 streams)": ({}, parts_two_streams),
     "slab: whole with halos (one call)": ({}, lambda: lap.apply_local(f, out, lo, hi)),
