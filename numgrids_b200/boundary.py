@@ -118,6 +118,8 @@ class BoundaryCondition:
             g = _device.as_device_tensor(spec).reshape(-1)
         else:
             g = _device.to_device(np.ascontiguousarray(self._resolve_value(), dtype=np.float64))
+        if g.numel() == 1:                       # `u[mask] = g` broadcasts a one-element value (numgrids/boundary.py:165)
+            return None, float(g.reshape(-1)[0].item()), None
         if g.numel() != n_face:
             raise ValueError(f"boundary value has {g.numel()} entries, the face has {n_face} points")
         return g.data_ptr(), 0.0, g
@@ -140,11 +142,21 @@ class BoundaryCondition:
             _lib.check(lib.ng_bc_apply(len(shape), shp_p, face.axis_index, side, kind, hs, g_ptr, g_scalar,
                                        t.data_ptr(), _device.current_stream_ptr()), "ng_bc_apply")
             return u
-        # host array: only the face and its adjacent layer travel (a 2-layer array along the axis)
-        if not isinstance(u, np.ndarray) or u.dtype != np.float64 or u.shape != tuple(shape):
-            raise ValueError("in-place boundary apply needs a float64 ndarray of the grid's shape")
+        # host array: only the face and its adjacent layer travel (a 2-layer array along the axis).  Like the
+        # reference's `u[mask] = g` / slice assignment (numgrids/boundary.py:165, :232-244), any ndarray of the
+        # grid's shape is accepted -- other float dtypes and non-contiguous views go through a float64 copy of the
+        # two layers and NumPy casts the face back on assignment; complex arrays layer by real / imaginary part
+        if not isinstance(u, np.ndarray) or u.shape != tuple(shape):
+            raise ValueError("in-place boundary apply needs an ndarray of the grid's shape")
+        if np.iscomplexobj(u):
+            if kind == _KIND_DIRICHLET:
+                re = np.ascontiguousarray(u.real, dtype=np.float64)
+                self._apply_device(re, kind, hs)
+                u[face._index()] = re[face._index()]            # Dirichlet: u = g (real g; imaginary part 0)
+                return u
+            raise TypeError("Neumann / Robin conditions on complex host arrays are not supported")
         lo, hi = (face._index(), face._index(True)) if side == 0 else (face._index(True), face._index())
-        two = np.stack((u[lo], u[hi]), axis=face.axis_index)
+        two = np.stack((u[lo], u[hi]), axis=face.axis_index).astype(np.float64, copy=False)
         d_two = _device.to_device(np.ascontiguousarray(two))
         shp, shp_p = _lib.as_i64(list(two.shape))
         _lib.check(lib.ng_bc_apply(two.ndim, shp_p, face.axis_index, side, kind, hs, g_ptr, g_scalar,

@@ -9,6 +9,29 @@ __device__ __forceinline__ double2 ldg128(const double* p) {
     return __ldg(reinterpret_cast<const double2*>(p));
 }
 
+// Fused elementwise work (ng_fuse) as a template parameter MODE: 0 = none; -1 = every step tested at run time
+// (any combination); > 0 = the steps present, as a compile-time bit mask, for the combinations the curvilinear
+// composites of curv.cu issue -- no flag tests, no offset arithmetic for absent operands (the run-time form cost
+// 134 thread-instructions per point against 57 for the plain kernel, profiles/r01_fd_row_fused_ncu_summary.txt).
+enum : int { FM_PRE = 1, FM_MINUEND = 2, FM_POST = 4, FM_ADDEND = 8, FM_ADDZERO = 16, FM_DIV = 32, FM_FINITE = 64 };
+template <int MODE> __device__ __forceinline__ bool fm_pre(const FuseDev& F) { return MODE < 0 ? F.pre.ptr != nullptr : (MODE & FM_PRE) != 0; }
+template <int MODE> __device__ __forceinline__ bool fm_post(const FuseDev& F) { return MODE < 0 ? F.post.ptr != nullptr : (MODE & FM_POST) != 0; }
+template <int MODE> __device__ __forceinline__ bool fm_div(const FuseDev& F) { return MODE < 0 ? F.div.ptr != nullptr : (MODE & FM_DIV) != 0; }
+// correctly rounded divide, out of line: ~40 instructions that would otherwise be inlined 8 x 6 times per kernel
+__device__ __noinline__ double fd_row_div(double a, double b) { return __ddiv_rn(a, b); }
+// the tail of ng_fuse (same steps and order as fuse_tail_off in common.cuh)
+template <int MODE>
+__device__ __forceinline__ double fm_tail(const FuseDev& F, double d, i64 lin, i64 post_off, i64 div_off) {
+    if (MODE < 0) return fuse_tail_off(F, d, lin, post_off, div_off);
+    if (MODE & FM_MINUEND) d = __dsub_rn(F.minuend[lin], d);
+    if (MODE & FM_POST) d = __dmul_rn(F.post.ptr[post_off], d);
+    if (MODE & FM_ADDEND) d = __dadd_rn(F.addend[lin], d);
+    else if (MODE & FM_ADDZERO) d = __dadd_rn(0.0, d);
+    if (MODE & FM_DIV) d = fd_row_div(d, F.div.ptr[div_off]);
+    if (MODE & FM_FINITE) d = ng_nonfinite(d) ? 0.0 : d;
+    return d;
+}
+
 // (b) derivative axis IS the contiguous one: the [rows][n] view is cut into chunks of 64 doubles (lane l
 // holds the aligned pair 2l, 2l+1: one 512-byte load per chunk) and a warp takes a group of U consecutive
 // chunks of one row.  All U loads (plus the two edge pairs the group's first / last lanes need from the
@@ -20,8 +43,9 @@ __device__ __forceinline__ double2 ldg128(const double* p) {
 // (and for TAIL, how) the group touches the low / high end of its row: only then can a position fall outside [0, n) (slab
 // halo or nothing there), a chunk be partial, or a one-sided scheme apply; interior groups run without
 // any of those tests.
-template <int P, bool FUSED, bool HALO>
+template <int P, int MODE, bool HALO>
 struct RowCtx {
+    static constexpr bool FUSED = MODE != 0;
     const double* __restrict__ src;
     double* __restrict__ dst;
     const double* __restrict__ xdiv;
@@ -34,7 +58,7 @@ struct RowCtx {
         if (q < 0) return (HALO && lo_row && q >= -P) ? lo_row[P + q] : 0.0;
         if (q >= n) return (HALO && hi_row && q - n < P) ? hi_row[q - n] : 0.0;
         double x = src[q];
-        if (FUSED && F.pre.ptr) x = __dmul_rn(F.pre.ptr[pre0 + q * pre_a], x);
+        if (FUSED && fm_pre<MODE>(F)) x = __dmul_rn(F.pre.ptr[pre0 + q * pre_a], x);
         return x;
     }
     template <bool CHECK>
@@ -42,7 +66,7 @@ struct RowCtx {
         double2 v = make_double2(0.0, 0.0);
         if (!CHECK || (pos >= 0 && pos < n)) {
             v = ldg128(src + pos);
-            if (FUSED && F.pre.ptr) {
+            if (FUSED && fm_pre<MODE>(F)) {
                 v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
                 v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
             }
@@ -54,8 +78,31 @@ struct RowCtx {
     }
 };
 
-template <int P, bool FUSED, bool HALO, int U, bool HEAD, int TAIL>
-__device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, const FdTables& T,
+// One-sided scheme at position q of the row (global boundary): sum_k w[k] * x(q + off[k]) from 0.0 in stored order.
+// Out of line on purpose: it runs for at most P positions per row end, but inlined into every head / tail variant of
+// the group body (four copies each) it made the kernels 12-14 thousand instructions long -- 200 KB of code that no
+// instruction cache holds (stall_no_instruction 2.1 per issue in profiles/r01_fd_row_fused_ncu_summary.txt).
+template <int P, int MODE, bool HALO>
+__device__ __noinline__ double fd_row_one_sided(const double* __restrict__ src, const double* lo_row, const double* hi_row,
+                                                const double* pre_ptr, i64 pre0, i64 pre_a, int n, int q,
+                                                const double* w, const int* off, int n_side) {
+    double a = 0.0;
+    for (int k = 0; k < n_side; ++k) {
+        const int t = q + off[k];
+        double x;
+        if (t < 0) x = (HALO && lo_row && t >= -P) ? lo_row[P + t] : 0.0;
+        else if (t >= n) x = (HALO && hi_row && t - n < P) ? hi_row[t - n] : 0.0;
+        else {
+            x = src[t];
+            if (MODE != 0 && pre_ptr) x = __dmul_rn(pre_ptr[pre0 + t * pre_a], x);
+        }
+        a = __dadd_rn(a, __dmul_rn(w[k], x));
+    }
+    return a;
+}
+
+template <int P, int MODE, bool HALO, int U, bool HEAD, int TAIL>
+__device__ __forceinline__ void fd_row_group(const RowCtx<P, MODE, HALO>& R, const FdTables& T,
                                              const FuseDev& F, int c0, int lane) {
     constexpr int H = (P + 1) / 2;                           // neighbour lanes needed on each side
     constexpr int C = 2 * H;                                 // window index of this lane's .x
@@ -97,10 +144,9 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, co
         // one-sided schemes on the global boundary: only the first / last chunk of a row can hold them
         // (TAIL == 1: the group ends exactly at the row end, so only its last chunk; HEAD: only its first)
         if ((one_lo && u == 0) || (one_hi && (TAIL == 1 ? u == U - 1 : (c0 + u) * 64 + 64 + P > n))) {
+            const double* pre_ptr = (MODE != 0 && fm_pre<MODE>(F)) ? F.pre.ptr : nullptr;
             auto one_sided = [&](int q, const double* w, const int* off) -> double {
-                double a = 0.0;
-                for (int k = 0; k < T.n_side; ++k) a = __dadd_rn(a, __dmul_rn(w[k], R.value_at(F, q + off[k])));
-                return a;
+                return fd_row_one_sided<P, MODE, HALO>(R.src, R.lo_row, R.hi_row, pre_ptr, R.pre0, R.pre_a, n, q, w, off, T.n_side);
             };
             if (TAIL != 2 || pos < n) {
                 if (one_lo && pos < P) {
@@ -122,20 +168,22 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, FUSED, HALO>& R, co
                 r.x = __ddiv_rn(r.x, xd.x);
                 r.y = __ddiv_rn(r.y, xd.y);
             }
-            if (FUSED) {
-                r.x = fuse_tail_off(F, r.x, R.base + pos, R.post0 + pos * R.post_a, R.div0 + pos * R.div_a);
-                r.y = fuse_tail_off(F, r.y, R.base + pos + 1, R.post0 + (pos + 1) * R.post_a,
-                                    R.div0 + (pos + 1) * R.div_a);
+            if (MODE != 0) {
+                const i64 po = fm_post<MODE>(F) ? R.post0 + pos * R.post_a : 0;
+                const i64 dv = fm_div<MODE>(F) ? R.div0 + pos * R.div_a : 0;
+                r.x = fm_tail<MODE>(F, r.x, R.base + pos, po, dv);
+                r.y = fm_tail<MODE>(F, r.y, R.base + pos + 1, po + R.post_a, dv + R.div_a);
             }
             *reinterpret_cast<double2*>(R.dst + pos) = r;
         }
     }
 }
 
-template <int P, bool FUSED, bool HALO, int U>
+template <int P, int MODE, bool HALO, int U>
 __global__ void __launch_bounds__(256)
 fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows, int n, int axis,
-              FdTables T, const double* __restrict__ xdiv, FuseDev F, const double* __restrict__ lo,
+              const __grid_constant__ FdTables T, const double* __restrict__ xdiv, const __grid_constant__ FuseDev F,
+              const double* __restrict__ lo,
               const double* __restrict__ hi, int gpr /* groups per row */) {
     const int lane = threadIdx.x & 31;
     const i64 g = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -150,7 +198,8 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
         row = g / gpr;
         grp = (int)(g - row * gpr);
     }
-    RowCtx<P, FUSED, HALO> R;
+    constexpr bool FUSED = MODE != 0;
+    RowCtx<P, MODE, HALO> R;
     R.n = n;
     R.base = row * (i64)n;
     R.src = in + R.base;
@@ -161,9 +210,9 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
     R.pre0 = R.pre_a = R.post0 = R.post_a = R.div0 = R.div_a = 0;
     if (FUSED) {
         const Idx4 ix = unravel4(R.base, F.shape);           // coordinate along `axis` (the last one) is 0
-        if (F.pre.ptr) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; }
-        if (F.post.ptr) { R.post0 = coef_off(F.post, ix); R.post_a = F.post.s[axis]; }
-        if (F.div.ptr) { R.div0 = coef_off(F.div, ix); R.div_a = F.div.s[axis]; }
+        if (fm_pre<MODE>(F)) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; }
+        if (fm_post<MODE>(F)) { R.post0 = coef_off(F.post, ix); R.post_a = F.post.s[axis]; }
+        if (fm_div<MODE>(F)) { R.div0 = coef_off(F.div, ix); R.div_a = F.div.s[axis]; }
     }
     const int c0 = grp * U;                                  // first chunk of the group
     const bool head = c0 == 0;
@@ -171,13 +220,13 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
     // end (only the neighbour pair is outside); 2: ragged (partial or missing chunks)
     const int tail = (c0 + U) * 64 + 64 <= n ? 0 : ((c0 + U) * 64 == n ? 1 : 2);
     if (!head) {
-        if (tail == 0) fd_row_group<P, FUSED, HALO, U, false, 0>(R, T, F, c0, lane);
-        else if (tail == 1) fd_row_group<P, FUSED, HALO, U, false, 1>(R, T, F, c0, lane);
-        else fd_row_group<P, FUSED, HALO, U, false, 2>(R, T, F, c0, lane);
+        if (tail == 0) fd_row_group<P, MODE, HALO, U, false, 0>(R, T, F, c0, lane);
+        else if (tail == 1) fd_row_group<P, MODE, HALO, U, false, 1>(R, T, F, c0, lane);
+        else fd_row_group<P, MODE, HALO, U, false, 2>(R, T, F, c0, lane);
     } else {
-        if (tail == 0) fd_row_group<P, FUSED, HALO, U, true, 0>(R, T, F, c0, lane);
-        else if (tail == 1) fd_row_group<P, FUSED, HALO, U, true, 1>(R, T, F, c0, lane);
-        else fd_row_group<P, FUSED, HALO, U, true, 2>(R, T, F, c0, lane);
+        if (tail == 0) fd_row_group<P, MODE, HALO, U, true, 0>(R, T, F, c0, lane);
+        else if (tail == 1) fd_row_group<P, MODE, HALO, U, true, 1>(R, T, F, c0, lane);
+        else fd_row_group<P, MODE, HALO, U, true, 2>(R, T, F, c0, lane);
     }
 }
 
@@ -202,12 +251,36 @@ int launch_row(const ng_plan* p, const double* in, double* out, const FuseDev& F
         // U = 4 0.80 / 0.92, U = 8 0.69 / 0.58 of the HBM peak
         const int uu = ue ? ue : (!deep ? 1 : 4);
 #define NG_FD_ROW2(FU, HA) do { if (uu >= 4) NG_FD_ROW(FU, HA, 4); else NG_FD_ROW(FU, HA, 1); } while (0)
-        if (F.any) { if (halo) NG_FD_ROW2(true, true); else NG_FD_ROW2(true, false); }
-        else       { if (halo) NG_FD_ROW2(false, true); else NG_FD_ROW2(false, false); }
+        if (F.any) { if (halo) NG_FD_ROW2(-1, true); else NG_FD_ROW2(-1, false); }
+        else       { if (halo) NG_FD_ROW2(0, true); else NG_FD_ROW2(0, false); }
 #undef NG_FD_ROW2
 #undef NG_FD_ROW
         NG_TRACE(uu >= 4 ? "fd_row<u4>" : "fd_row<u1>");
     }
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+// the compile-time fuse patterns of the curvilinear composites (curv.cu) for the acc = 4 stencils (P = 2), no halo
+int fuse_mask(const FuseDev& F) {
+    return (F.pre.ptr ? FM_PRE : 0) | (F.minuend ? FM_MINUEND : 0) | (F.post.ptr ? FM_POST : 0) | (F.addend ? FM_ADDEND : 0) |
+           (!F.addend && F.add_zero ? FM_ADDZERO : 0) | (F.div.ptr ? FM_DIV : 0) | (F.finite ? FM_FINITE : 0);
+}
+
+template <int MODE>
+int launch_row_mode(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st, int uu) {
+    const int n = (int)p->n;
+    const i64 rows = p->outer;
+    const int nchunk = (n + 63) / 64;
+    if (uu >= 4) {
+        const int gpr = (nchunk + 3) / 4;
+        fd_row_kernel<2, MODE, false, 4><<<(unsigned)((rows * gpr + 7) / 8), 256, 0, st>>>(
+            in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, nullptr, nullptr, gpr);
+    } else {
+        fd_row_kernel<2, MODE, false, 1><<<(unsigned)((rows * nchunk + 7) / 8), 256, 0, st>>>(
+            in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, nullptr, nullptr, nchunk);
+    }
+    NG_TRACE(uu >= 4 ? "fd_row<u4,mode>" : "fd_row<u1,mode>");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -221,9 +294,46 @@ int launch_row(const ng_plan* p, const double* in, double* out, const FuseDev& F
 #endif
 int ng_fd_row_launch_wide(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
                           const double* lo, const double* hi, cudaStream_t st);
-#if NG_ROW_PSET == 0
+int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
+                           bool* handled);
+#if NG_ROW_PSET == 2
+// third object: P = 2 with the fuse pattern known at compile time (12 patterns x 2 chunk depths)
+int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
+                           bool* handled) {
+    *handled = true;
+    const i64 rows = p->outer;
+    const int nchunk = ((int)p->n + 63) / 64;
+    const bool deep = rows * nchunk >= 148LL * 8 * 4 * 4 && nchunk >= 3;
+    const int ue = (int)NG_ENV_INT("NG_FD_ROW_U", 0);
+    const int uu = ue ? ue : (!deep ? 1 : 4);
+    switch (fuse_mask(F)) {
+#define NG_MODE(M) case (M): return launch_row_mode<(M)>(p, in, out, F, st, uu);
+        NG_MODE(FM_POST)                                                  // laplacian: work = (J/h^2) * D f
+        NG_MODE(FM_ADDZERO)                                               //            out = 0.0 + D work
+        NG_MODE(FM_ADDEND)                                                //            out = out + D work
+        NG_MODE(FM_ADDZERO | FM_DIV | FM_FINITE)                          //            ... / J, finite (1-D grids)
+        NG_MODE(FM_ADDEND | FM_DIV | FM_FINITE)
+        NG_MODE(FM_POST | FM_FINITE)                                      // gradient
+        NG_MODE(FM_PRE | FM_ADDZERO)                                      // divergence
+        NG_MODE(FM_PRE | FM_ADDEND)
+        NG_MODE(FM_PRE | FM_ADDZERO | FM_DIV | FM_FINITE)
+        NG_MODE(FM_PRE | FM_ADDEND | FM_DIV | FM_FINITE)
+        NG_MODE(FM_PRE)                                                   // curl: out = D(h v)
+        NG_MODE(FM_PRE | FM_MINUEND | FM_POST | FM_FINITE)                //       out = finite(c * (out - D(h v)))
+#undef NG_MODE
+        default: break;
+    }
+    *handled = false;
+    return NG_OK;
+}
+#elif NG_ROW_PSET == 0
 int ng_fd_row_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
                      const double* lo, const double* hi, cudaStream_t st) {
+    if (P == 2 && F.any && !lo && !hi && NG_ENV_INT("NG_FD_ROW_MODES", 1) != 0) {
+        bool handled = false;
+        const int rc = ng_fd_row_launch_modes(p, in, out, F, st, &handled);
+        if (rc || handled) return rc;
+    }
     switch (P) {
         case 1: return launch_row<1>(p, in, out, F, lo, hi, st);
         case 2: return launch_row<2>(p, in, out, F, lo, hi, st);

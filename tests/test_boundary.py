@@ -179,3 +179,34 @@ def test_heat_step_stays_on_device(gpu_ready):
             else:
                 u_ref = bp.neumann_apply(u_ref, bc.face.axis_index, bc.face.side, g, coords[bc.face.axis_index])
     assert np.array_equal(u.cpu().numpy(), u_ref)
+
+
+@pytest.mark.gpu
+def test_apply_accepts_what_the_reference_accepts(gpu_ready):
+    """`u[mask] = g` in the reference takes any ndarray of the grid's shape (other float dtypes, non-contiguous views,
+    complex) and broadcasts a one-element value (numgrids/boundary.py:157-166)."""
+    import numgrids_b200 as ng
+    from numgrids_b200.boundary import DirichletBC, NeumannBC
+    ax = ng.create_axis(ng.AxisType.EQUIDISTANT, 9, 0.0, 1.0)
+    ay = ng.create_axis(ng.AxisType.EQUIDISTANT, 7, 0.0, 2.0)
+    g = ng.Grid(ax, ay)
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal(g.shape)
+    face = g.faces["0_low"]
+    # float32
+    u32 = base.astype(np.float32)
+    DirichletBC(face, lambda c: 2.5).apply(u32)                  # callable returning ONE value: broadcast
+    assert u32.dtype == np.float32 and np.all(u32[0] == np.float32(2.5)) and np.array_equal(u32[1:], base.astype(np.float32)[1:])
+    # non-contiguous view of a larger array
+    big = rng.standard_normal((9, 14))
+    view = big[:, ::2]
+    want = view.copy()
+    h = ax.coords[1] - ax.coords[0]
+    want[0] = want[1] + (h * -1.0) * 0.75
+    NeumannBC(face, 0.75).apply(view)
+    assert np.array_equal(view, want)
+    # complex Dirichlet
+    uc = base + 1j * rng.standard_normal(g.shape)
+    keep = uc.copy()
+    DirichletBC(g.faces["1_high"], 1.5).apply(uc)
+    assert np.all(uc[:, -1] == 1.5 + 0j) and np.array_equal(uc[:, :-1], keep[:, :-1])
