@@ -32,6 +32,24 @@ __device__ __forceinline__ double fm_tail(const FuseDev& F, double d, i64 lin, i
     return d;
 }
 
+// the same with the operands of the pair already in registers (compile-time modes): coefficient pairs come from one
+// hoisted scalar when the table is constant along the row (spherical / cylindrical metrics along z), full-shape
+// operands (minuend / addend) from one aligned 128-bit load per pair
+template <int MODE>
+__device__ __forceinline__ double fm_tail_vals(double d, double mn, double pc, double ad, double dc) {
+    if (MODE & FM_MINUEND) d = __dsub_rn(mn, d);
+    if (MODE & FM_POST) d = __dmul_rn(pc, d);
+    if (MODE & FM_ADDEND) d = __dadd_rn(ad, d);
+    else if (MODE & FM_ADDZERO) d = __dadd_rn(0.0, d);
+    if (MODE & FM_DIV) d = fd_row_div(d, dc);
+    if (MODE & FM_FINITE) d = ng_nonfinite(d) ? 0.0 : d;
+    return d;
+}
+__device__ __forceinline__ double2 coef_pair(const double* base, i64 off, i64 stride, double hoisted) {
+    if (stride == 0) return make_double2(hoisted, hoisted);
+    return make_double2(__ldg(base + off), __ldg(base + off + stride));
+}
+
 // (b) derivative axis IS the contiguous one: the [rows][n] view is cut into chunks of 64 doubles (lane l
 // holds the aligned pair 2l, 2l+1: one 512-byte load per chunk) and a warp takes a group of U consecutive
 // chunks of one row.  All U loads (plus the two edge pairs the group's first / last lanes need from the
@@ -52,6 +70,7 @@ struct RowCtx {
     const double* lo_row;                                    // this row's P halo values, or nullptr
     const double* hi_row;
     i64 base, pre0, pre_a, post0, post_a, div0, div_a;
+    double pre_c;                                            // the pre coefficient when it is constant along the row
     int n;
 
     __device__ __forceinline__ double value_at(const FuseDev& F, int q) const {
@@ -67,8 +86,13 @@ struct RowCtx {
         if (!CHECK || (pos >= 0 && pos < n)) {
             v = ldg128(src + pos);
             if (FUSED && fm_pre<MODE>(F)) {
-                v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
-                v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
+                if (pre_a == 0) {
+                    v.x = __dmul_rn(pre_c, v.x);
+                    v.y = __dmul_rn(pre_c, v.y);
+                } else {
+                    v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
+                    v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
+                }
             }
         } else if (HALO) {
             v.x = value_at(F, pos);
@@ -116,6 +140,12 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, MODE, HALO>& R, con
     if (lane >= 32 - H) pcl = R.template pair_at<HEAD>(F, p0 - 64);
     if (lane < H) ncr = R.template pair_at<TAIL != 0>(F, p0 + 64 * U);
     const bool one_lo = HEAD && !(HALO && R.lo_row), one_hi = TAIL != 0 && !(HALO && R.hi_row);
+    // compile-time modes: coefficients that do not vary along the row are read once per group
+    double post_c = 0.0, div_c = 0.0;
+    if (MODE > 0) {
+        if ((MODE & FM_POST) && R.post_a == 0) post_c = __ldg(F.post.ptr + R.post0);
+        if ((MODE & FM_DIV) && R.div_a == 0) div_c = __ldg(F.div.ptr + R.div0);
+    }
 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -168,7 +198,15 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, MODE, HALO>& R, con
                 r.x = __ddiv_rn(r.x, xd.x);
                 r.y = __ddiv_rn(r.y, xd.y);
             }
-            if (MODE != 0) {
+            if (MODE > 0) {
+                double2 mn = make_double2(0.0, 0.0), ad = mn, pc = mn, dc = mn;
+                if (MODE & FM_MINUEND) mn = *reinterpret_cast<const double2*>(F.minuend + R.base + pos);   // may alias out: plain load
+                if (MODE & FM_ADDEND) ad = *reinterpret_cast<const double2*>(F.addend + R.base + pos);
+                if (MODE & FM_POST) pc = coef_pair(F.post.ptr, R.post0 + pos * R.post_a, R.post_a, post_c);
+                if (MODE & FM_DIV) dc = coef_pair(F.div.ptr, R.div0 + pos * R.div_a, R.div_a, div_c);
+                r.x = fm_tail_vals<MODE>(r.x, mn.x, pc.x, ad.x, dc.x);
+                r.y = fm_tail_vals<MODE>(r.y, mn.y, pc.y, ad.y, dc.y);
+            } else if (MODE != 0) {
                 const i64 po = fm_post<MODE>(F) ? R.post0 + pos * R.post_a : 0;
                 const i64 dv = fm_div<MODE>(F) ? R.div0 + pos * R.div_a : 0;
                 r.x = fm_tail<MODE>(F, r.x, R.base + pos, po, dv);
@@ -208,9 +246,10 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
     R.lo_row = (HALO && lo) ? lo + row * P : nullptr;
     R.hi_row = (HALO && hi) ? hi + row * P : nullptr;
     R.pre0 = R.pre_a = R.post0 = R.post_a = R.div0 = R.div_a = 0;
+    R.pre_c = 0.0;
     if (FUSED) {
         const Idx4 ix = unravel4(R.base, F.shape);           // coordinate along `axis` (the last one) is 0
-        if (fm_pre<MODE>(F)) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; }
+        if (fm_pre<MODE>(F)) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; R.pre_c = R.pre_a == 0 ? __ldg(F.pre.ptr + R.pre0) : 0.0; }
         if (fm_post<MODE>(F)) { R.post0 = coef_off(F.post, ix); R.post_a = F.post.s[axis]; }
         if (fm_div<MODE>(F)) { R.div0 = coef_off(F.div, ix); R.div_a = F.div.s[axis]; }
     }
