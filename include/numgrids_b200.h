@@ -112,6 +112,15 @@ int ng_cheb_plan_create(int ndim, const int64_t* shape, int axis,
 int ng_fft_plan_create(int ndim, const int64_t* shape, int axis,
                        const double* h_W_re_im, const double* h_D, ng_plan** out);
 
+/* The same for an axis of ANY length n in O(n log n): the operator is a circular convolution with the real kernel
+ * d = ifft(W); the host lays d out on a circle of m points (m a power of two, 2n-1 <= m <= 8192: d[k] at k, d[n-k] at
+ * m-k, zeros between) and passes its m-point transform h_Wm_re_im (m complex values, interleaved).  The kernels transform
+ * zero-padded pencils with m points and store the first n outputs; arrays keep n samples along `axis`.  Rounding differs
+ * from numpy.fft's n-point transform by a few 1e-14 for first derivatives; higher orders amplify it (the host layer
+ * keeps the dense contraction there). */
+int ng_fft_plan_create_padded(int ndim, const int64_t* shape, int axis, int64_t m, const double* h_Wm_re_im,
+                              ng_plan** out);
+
 /* ---- apply ------------------------------------------------------------------------------------
  * GridDiff.__call__ (numgrids/diff.py:48-61).  d_out must not alias d_in. */
 int ng_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream);

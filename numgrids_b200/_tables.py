@@ -175,3 +175,23 @@ def compact_coefficient(a: np.ndarray, shape: tuple[int, ...]):
             strides[ax] = s
             s *= values.shape[ax]
     return values.reshape(-1), strides
+
+
+def fft_padded_multiplier(W: np.ndarray):
+    """Zero-padded power-of-two form of the periodic derivative for an axis of ANY length n.
+
+    ``real(ifft(W * fft(f)))`` (numgrids/diff.py:133-143) is the circular convolution of f with the real kernel
+    ``d = ifft(W)``.  Laid out on a circle of ``m >= 2n-1`` points (``d[k]`` at ``k``, ``d[n-k]`` at ``m-k``, zeros
+    between), ``ifft_m(fft_m(d_circle) * fft_m(f zero-padded))`` reproduces it on the first n outputs.  Returns
+    ``(m, fft_m(d_circle))`` with m the next power of two, or ``None`` when m would exceed the kernels' 8192."""
+    n = len(W)
+    m = 1
+    while m < 2 * n - 1:
+        m *= 2
+    if m > 8192:
+        return None
+    d = np.real(np.fft.ifft(W))
+    circle = np.zeros(m)
+    circle[:n] = d
+    circle[m - (n - 1):] = d[1:]
+    return m, np.fft.fft(circle)

@@ -261,6 +261,72 @@ int ng_cheb_plan_create(int ndim, const int64_t* shape, int axis, const double* 
     return NG_OK;
 }
 
+// Device tables of an m-point power-of-two transform (m = the axis length, or the padded length of
+// ng_fft_plan_create_padded): multipliers / m in bit-reversed order + half twiddle circle (radix-2 kernel, fft.cu),
+// multipliers / m in natural order + full twiddle circle (two-pass register kernels, fft2.cu).
+static int build_fft_tables(ng_plan* p, i64 m, const double* h_W_re_im) {
+    p->fft_pow2 = 1;
+    p->fft_len = (int)m;
+    int l = 0;
+    while ((1LL << l) < m) ++l;
+    p->log2n = l;
+    std::vector<double> Wbr((size_t)(2 * m)), tw((size_t)m);   // tw: m/2 complex
+    for (i64 k = 0; k < m; ++k) {
+        i64 r = 0;
+        for (int b = 0; b < l; ++b) if (k & (1LL << b)) r |= 1LL << (l - 1 - b);
+        // position r of the DIF output holds bin k
+        Wbr[(size_t)(2 * r)] = h_W_re_im[2 * k] / (double)m;
+        Wbr[(size_t)(2 * r + 1)] = h_W_re_im[2 * k + 1] / (double)m;
+    }
+    // twiddles exp(-2 pi i j / m), j < m/2, evaluated in long double and rounded once
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (i64 j = 0; j < m / 2; ++j) {
+        const long double a = two_pi * (long double)j / (long double)m;
+        tw[(size_t)(2 * j)] = (double)cosl(a);
+        tw[(size_t)(2 * j + 1)] = (double)(-sinl(a));
+    }
+    int rc = upload(p, &p->d_W, Wbr.data(), 2 * m);
+    if (!rc) rc = upload(p, &p->d_tw, tw.data(), m);
+    std::vector<double> Wn((size_t)(2 * m)), twn((size_t)(2 * m));
+    for (i64 k = 0; k < m; ++k) {
+        Wn[(size_t)(2 * k)] = h_W_re_im[2 * k] / (double)m;
+        Wn[(size_t)(2 * k + 1)] = h_W_re_im[2 * k + 1] / (double)m;
+        const long double a = two_pi * (long double)k / (long double)m;
+        twn[(size_t)(2 * k)] = (double)cosl(a);
+        twn[(size_t)(2 * k + 1)] = (double)(-sinl(a));
+    }
+    if (!rc) rc = upload(p, &p->d_Wn, Wn.data(), 2 * m);
+    if (!rc) rc = upload(p, &p->d_twn, twn.data(), 2 * m);
+    return rc;
+}
+
+// Periodic axis of ANY length n as a zero-padded power-of-two transform: the operator is a circular convolution with
+// the real kernel d = ifft(W); laid out on a circle of m >= 2n-1 points (d[k] at k, d[n-k] at m-k) its m-point
+// transform times the transform of the zero-padded pencil gives, on the first n outputs, exactly the n-point circular
+// convolution.  h_Wm_re_im = fft_m(d on the circle), computed by the host; rows in memory keep n samples.
+int ng_fft_plan_create_padded(int ndim, const int64_t* shape, int axis, int64_t m, const double* h_Wm_re_im,
+                              ng_plan** out) {
+    NG_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    NG_REQUIRE(h_Wm_re_im != nullptr, "multiplier table is NULL");
+    ng_plan* p = new (std::nothrow) ng_plan();
+    if (!p) { ng_set_error("out of host memory"); return NG_ENOMEM; }
+    int rc = set_shape(p, ndim, shape, axis);
+    if (!rc) rc = require_device();
+    if (rc) { delete p; return rc; }
+    p->kind = PK_FFT;
+    if (!(m >= 2 && (m & (m - 1)) == 0 && m <= 8192 && m >= 2 * p->n - 1)) {
+        ng_set_error("padded transform length %lld must be a power of two in [2n-1, 8192] for n = %lld", (long long)m,
+                     (long long)p->n);
+        delete p;
+        return NG_EINVAL;
+    }
+    rc = build_fft_tables(p, m, h_Wm_re_im);
+    if (rc) { ng_plan_destroy(p); return rc; }
+    *out = p;
+    return NG_OK;
+}
+
 int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h_W_re_im,
                        const double* h_D, ng_plan** out) {
     NG_REQUIRE(out != nullptr, "out is NULL");
@@ -276,38 +342,7 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h
     const bool pow2 = n >= 2 && (n & (n - 1)) == 0 && n <= 8192;
     const bool force_dense = NG_ENV_INT("NG_FFT_DENSE", 0) != 0;
     if (pow2 && !(force_dense && h_D)) {
-        p->fft_pow2 = 1;
-        int l = 0;
-        while ((1LL << l) < n) ++l;
-        p->log2n = l;
-        std::vector<double> Wbr((size_t)(2 * n)), tw((size_t)n);   // tw: n/2 complex
-        for (i64 k = 0; k < n; ++k) {
-            i64 r = 0;
-            for (int b = 0; b < l; ++b) if (k & (1LL << b)) r |= 1LL << (l - 1 - b);
-            // position r of the DIF output holds bin k
-            Wbr[(size_t)(2 * r)] = h_W_re_im[2 * k] / (double)n;
-            Wbr[(size_t)(2 * r + 1)] = h_W_re_im[2 * k + 1] / (double)n;
-        }
-        // twiddles exp(-2 pi i j / n), j < n/2, evaluated in long double and rounded once
-        const long double two_pi = 6.283185307179586476925286766559005768L;
-        for (i64 j = 0; j < n / 2; ++j) {
-            const long double a = two_pi * (long double)j / (long double)n;
-            tw[(size_t)(2 * j)] = (double)cosl(a);
-            tw[(size_t)(2 * j + 1)] = (double)(-sinl(a));
-        }
-        rc = upload(p, &p->d_W, Wbr.data(), 2 * n);
-        if (!rc) rc = upload(p, &p->d_tw, tw.data(), n);
-        // tables of the two-pass register kernel: natural-order multipliers / n, full twiddle circle
-        std::vector<double> Wn((size_t)(2 * n)), twn((size_t)(2 * n));
-        for (i64 k = 0; k < n; ++k) {
-            Wn[(size_t)(2 * k)] = h_W_re_im[2 * k] / (double)n;
-            Wn[(size_t)(2 * k + 1)] = h_W_re_im[2 * k + 1] / (double)n;
-            const long double a = two_pi * (long double)k / (long double)n;
-            twn[(size_t)(2 * k)] = (double)cosl(a);
-            twn[(size_t)(2 * k + 1)] = (double)(-sinl(a));
-        }
-        if (!rc) rc = upload(p, &p->d_Wn, Wn.data(), 2 * n);
-        if (!rc) rc = upload(p, &p->d_twn, twn.data(), 2 * n);
+        rc = build_fft_tables(p, n, h_W_re_im);
     } else {
         if (!h_D) {
             ng_set_error("n = %lld is not a power of two <= 8192: the dense spectral matrix is required",

@@ -147,6 +147,7 @@ struct ng_plan {
     // PK_FFT
     int fft_pow2 = 0;
     int log2n = 0;
+    int fft_len = 0;          // transform length: n, or the power of two >= 2n-1 of a zero-padded plan (ng_fft_plan_create_padded)
     double* d_W = nullptr;    // [n][2]
     double* d_tw = nullptr;   // [n/2][2] forward twiddles exp(-2 pi i k / n) (radix-2 kernel)
     double* d_Wn = nullptr;   // [n][2] multipliers / n in natural order (two-pass kernel, fft2.cu)

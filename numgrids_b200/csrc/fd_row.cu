@@ -45,8 +45,9 @@ __device__ __forceinline__ double fm_tail_vals(double d, double mn, double pc, d
     if (MODE & FM_FINITE) d = ng_nonfinite(d) ? 0.0 : d;
     return d;
 }
-__device__ __forceinline__ double2 coef_pair(const double* base, i64 off, i64 stride, double hoisted) {
-    if (stride == 0) return make_double2(hoisted, hoisted);
+__device__ __forceinline__ double2 coef_pair(const double* base, i64 off0, int pos, i64 stride, double hoisted) {
+    if (stride == 0) return make_double2(hoisted, hoisted);          // (no offset arithmetic on this path)
+    const i64 off = off0 + pos * stride;
     return make_double2(__ldg(base + off), __ldg(base + off + stride));
 }
 
@@ -202,8 +203,8 @@ __device__ __forceinline__ void fd_row_group(const RowCtx<P, MODE, HALO>& R, con
                 double2 mn = make_double2(0.0, 0.0), ad = mn, pc = mn, dc = mn;
                 if (MODE & FM_MINUEND) mn = *reinterpret_cast<const double2*>(F.minuend + R.base + pos);   // may alias out: plain load
                 if (MODE & FM_ADDEND) ad = *reinterpret_cast<const double2*>(F.addend + R.base + pos);
-                if (MODE & FM_POST) pc = coef_pair(F.post.ptr, R.post0 + pos * R.post_a, R.post_a, post_c);
-                if (MODE & FM_DIV) dc = coef_pair(F.div.ptr, R.div0 + pos * R.div_a, R.div_a, div_c);
+                if (MODE & FM_POST) pc = coef_pair(F.post.ptr, R.post0, pos, R.post_a, post_c);
+                if (MODE & FM_DIV) dc = coef_pair(F.div.ptr, R.div0, pos, R.div_a, div_c);
                 r.x = fm_tail_vals<MODE>(r.x, mn.x, pc.x, ad.x, dc.x);
                 r.y = fm_tail_vals<MODE>(r.y, mn.y, pc.y, ad.y, dc.y);
             } else if (MODE != 0) {

@@ -25,7 +25,8 @@ template <bool LAST, bool FUSED>
 __global__ void __launch_bounds__(FFT_NT)
 fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
                 const double2* __restrict__ W_br, const double2* __restrict__ tw, i64 outer, int n,
-                int log2n, i64 inner, int P, FuseDev F) {
+                int log2n, i64 inner, int P, int nv /* samples per pencil in memory (<= n; the rest is zero padding) */,
+                FuseDev F) {
     extern __shared__ double smem[];
     double* sre = smem;                // [P][n]
     double* sim = smem + (i64)P * n;   // [P][n]
@@ -47,10 +48,10 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
         else      { k = e / (2 * P); pl = e - k * (2 * P); }
         const i64 q = q0 + pl;
         double v = 0.0;
-        if (q < npencil) {
+        if (q < npencil && k < nv) {
             const i64 o = LAST ? q : q / inner;
             const i64 c = LAST ? 0 : q - o * inner;
-            const i64 lin = (o * n + k) * inner + c;
+            const i64 lin = (o * nv + k) * inner + c;
             v = in[lin];
             if (FUSED && F.pre.ptr) {
                 const Idx4 ix = unravel4(lin, F.shape);
@@ -113,10 +114,10 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
         if (LAST) { pl = e / n; k = e - pl * n; }
         else      { k = e / (2 * P); pl = e - k * (2 * P); }
         const i64 q = q0 + pl;
-        if (q >= npencil) continue;
+        if (q >= npencil || k >= nv) continue;
         const i64 o = LAST ? q : q / inner;
         const i64 c = LAST ? 0 : q - o * inner;
-        const i64 lin = (o * n + k) * inner + c;
+        const i64 lin = (o * nv + k) * inner + c;
         double d = ((pl & 1) ? sim : sre)[(pl >> 1) * n + k];
         if (sbad[pl]) d = ng_nan();
         if (FUSED) {
@@ -138,7 +139,7 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
         const int rc = ng_fft2_try_launch(p, in, out, F, st, &handled);
         if (rc != NG_OK || handled) return rc;
     }
-    const int n = (int)p->n;
+    const int n = p->fft_len;                            // transform length (== p->n unless the plan is zero-padded)
     const i64 npencil = p->outer * p->inner;
     // pencil pairs per CTA: enough butterflies for 256 threads, bounded by shared memory
     int P = 1;
@@ -151,12 +152,12 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
         NG_FUNC_SMEM(200 * 1024, fft_diff_kernel<LA, FU>);                                       \
         fft_diff_kernel<LA, FU><<<(unsigned)nblk, FFT_NT, smem, st>>>(                           \
             in, out, (const double2*)p->d_W, (const double2*)p->d_tw, p->outer, n, p->log2n,     \
-            p->inner, P, F);                                                                     \
+            p->inner, P, (int)p->n, F);                                                          \
     } while (0)
     if (last) { if (F.any) NG_FFT_GO(true, true); else NG_FFT_GO(true, false); }
     else      { if (F.any) NG_FFT_GO(false, true); else NG_FFT_GO(false, false); }
 #undef NG_FFT_GO
-    NG_TRACE("fft_radix2");
+    NG_TRACE(p->fft_len != p->n ? "fft_radix2<padded>" : "fft_radix2");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }

@@ -105,14 +105,14 @@ template <bool FUSED>
 __device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, double* __restrict__ out, i64 base,
                                              i64 step, int ax, int N, int log2n, double2* S,
                                              const double2* __restrict__ Wn, const double2* __restrict__ tw,
-                                             const FuseDev& F) {
+                                             const FuseDev& F, int nv /* samples in memory (zero padding above) */) {
     // sample k of the pencil sits at base + k*step and has coordinate k along grid axis `ax`
     const int lane = threadIdx.x & 31;
     Idx4 ix;
     if (FUSED) ix = unravel4(base, F.shape);
     bool bad = false;
     for (int k = lane; k < N; k += 32) {
-        double v = in[base + k * step];
+        double v = k < nv ? in[base + k * step] : 0.0;
         if (FUSED && F.pre.ptr) {
             ix.i[ax] = k;
             v = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], v);
@@ -153,7 +153,7 @@ __device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, doub
             __syncwarp();
         }
     }
-    for (int k = lane; k < N; k += 32) {
+    for (int k = lane; k < nv; k += 32) {
         double d = bad ? ng_nan() : S[k].x;
         if (FUSED) {
             ix.i[ax] = k;
@@ -221,13 +221,17 @@ __device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0, int
 // starts at o*n*inner + c and its samples are `inner` elements apart.  The pair (2*pair, 2*pair+1) and the
 // 2*TPW*8 pencils of a CTA are adjacent columns, so the 8-byte accesses of the lanes fall into sectors /
 // lines that the neighbouring thread groups and warps of the CTA touch at the same time (L1 / L2 reuse).
-template <int RT, int R2, bool FUSED, int MINB, bool STR>
+// PAD: zero-padded plan (ng_fft_plan_create_padded): a pencil has `nv` <= N samples in memory, the rest of the
+// N-point transform is zero; only the first nv outputs are stored.  Plain applies only (FUSED must be false).
+template <int RT, int R2, bool FUSED, int MINB, bool STR, bool PAD = false>
 __global__ void __launch_bounds__(256, MINB)
 fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
                 const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, i64 inner, int axis,
                 int pair16,   // STR: the two pencils of a pair are one aligned 16-byte element of every row
-                     const __grid_constant__ FuseDev F) {   // (address taken for the rare slow path: no local copy)
+                     const __grid_constant__ FuseDev F, int nv) {   // (address taken for the rare slow path: no local copy)
+    static_assert(!(PAD && FUSED), "padded transforms are plain applies");
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
+    const int NV = PAD ? nv : N;                       // samples per pencil in memory
     constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
     constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
     extern __shared__ double2 fsm[];
@@ -241,9 +245,9 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     const i64 step = STR ? inner : 1;
     const int ax = STR ? axis : F.vec_axis;
     auto pencil_base = [&](i64 p) -> i64 {
-        if (!STR) return p * N;
+        if (!STR) return p * NV;
         const i64 o = p / inner;
-        return o * N * inner + (p - o * inner);
+        return o * NV * inner + (p - o * inner);
     };
     const i64 ba = va ? pencil_base(pa) : 0, bb = vb ? pencil_base(pb) : 0;
 
@@ -259,11 +263,13 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
             double a = 0.0, b = 0.0;
-            if (STR && pair16) {
-                if (va) { const double2 v = *reinterpret_cast<const double2*>(in + ba + idx * step); a = v.x; b = v.y; }
-            } else {
-                if (va) a = in[ba + idx * step];
-                if (vb) b = in[bb + idx * step];
+            if (!PAD || idx < NV) {
+                if (STR && pair16) {
+                    if (va) { const double2 v = *reinterpret_cast<const double2*>(in + ba + idx * step); a = v.x; b = v.y; }
+                } else {
+                    if (va) a = in[ba + idx * step];
+                    if (vb) b = in[bb + idx * step];
+                }
             }
             if (pre) {                               // (an absent pencil must stay exactly zero)
                 if (va) a = __dmul_rn(ca.at(r), a);
@@ -321,7 +327,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         for (int q = 0; q < 2 * TPW; ++q)
             if (p0 + q < npencil)
                 fft_slow_pencil<FUSED>(in, out, pencil_base(p0 + q), step, ax, N, LRT + LR2,
-                                       fsm + (size_t)(warp * TPW + (q >> 1)) * UNITS, Wn, tw, F);
+                                       fsm + (size_t)(warp * TPW + (q >> 1)) * UNITS, Wn, tw, F, NV);
         return;
     }
     PencilTail ta, tb;
@@ -334,6 +340,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
             if (va) a = ta.apply(F, a, r, R2);
             if (vb) b = tb.apply(F, b, r, R2);
         }
+        if (PAD && idx >= NV) continue;
         if (STR && pair16) {
             if (va) *reinterpret_cast<double2*>(out + ba + idx * step) = make_double2(a, b);
         } else {
@@ -500,7 +507,7 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
                 if (p0 + q < npencil)
                     fft_slow_pencil<FUSED>(in, out, (p0 + q) * N, 1, F.vec_axis, N, LRT + LR2,
                                            reinterpret_cast<double2*>(Sall + (size_t)(warp * TPW + (q >> 1)) * N * 16),
-                                           Wn, tw, F);
+                                           Wn, tw, F, N);
             continue;
         }
         PencilTail ta, tb;
@@ -562,11 +569,29 @@ int launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cu
         NG_FUNC_SMEM(smem, fft2pass_kernel<RT, R2, FU, MINB, STR>);                               \
         fft2pass_kernel<RT, R2, FU, MINB, STR><<<grid, 32 * WARPS, smem, st>>>(                         \
             in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, p->inner, p->axis,    \
-            (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F);       \
+            (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F, RT * R2);   \
     } while (0)
     if (F.any) NG_FFT2_GO(true); else NG_FFT2_GO(false);
 #undef NG_FFT2_GO
     NG_TRACE(STR ? "fft2pass<strided>" : "fft2pass");
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+// zero-padded plan, plain apply: the (RT*R2)-point transform on pencils of p->n samples
+template <int RT, int R2, bool STR>
+int launch_padded(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    constexpr int T = R2, TPW = 32 / T, WARPS = 8;
+    const i64 npencil = p->outer * p->inner;
+    const i64 pairs = (npencil + 1) / 2;
+    const i64 per_block = (i64)WARPS * TPW;
+    const unsigned grid = (unsigned)((pairs + per_block - 1) / per_block);
+    const size_t smem = (size_t)WARPS * TPW * RT * (R2 + 1) * sizeof(double2);
+    NG_FUNC_SMEM(smem, fft2pass_kernel<RT, R2, false, 1, STR, true>);
+    fft2pass_kernel<RT, R2, false, 1, STR, true><<<grid, 32 * WARPS, smem, st>>>(
+        in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, p->inner, p->axis,
+        (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F, (int)p->n);
+    NG_TRACE(STR ? "fft2pass<strided,padded>" : "fft2pass<padded>");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -580,6 +605,19 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
     if (!p->d_Wn || !p->d_twn) return NG_OK;
     if (NG_ENV_INT("NG_FFT_TWOPASS", 1) == 0) return NG_OK;
     int rc = NG_OK;
+    if (p->fft_len != p->n) {
+        // zero-padded plan (any axis length): plain applies on the two-pass kernel, fused ones on the radix-2 kernel
+        if (F.any) return NG_OK;
+        const bool str = p->inner != 1;
+        switch (p->fft_len) {
+            case 1024: rc = str ? launch_padded<32, 32, true>(p, in, out, F, st) : launch_padded<32, 32, false>(p, in, out, F, st); break;
+            case 512: rc = str ? launch_padded<32, 16, true>(p, in, out, F, st) : launch_padded<32, 16, false>(p, in, out, F, st); break;
+            case 256: rc = str ? launch_padded<16, 16, true>(p, in, out, F, st) : launch_padded<16, 16, false>(p, in, out, F, st); break;
+            default: return NG_OK;
+        }
+        *handled = (rc == NG_OK);
+        return rc;
+    }
     if (p->inner != 1) {
         // transform axis not contiguous: the one-shot kernel with strided pencils (adjacent columns per CTA)
         if (NG_ENV_INT("NG_FFT_STRIDED", 1) == 0) return NG_OK;   // A/B: 0 = radix-2 shared-memory fallback (fft.cu)

@@ -223,6 +223,8 @@ class LogDiff(_StencilMixin, GridDiff):
 class FFTDiff(GridDiff):
     """Spectral derivative on a periodic equidistant axis (reference numgrids/diff.py:109-171)."""
 
+    PADDED_MIN_POINTS = 65          # non-power-of-two axes from this length on: zero-padded transform (order 1)
+
     def __init__(self, grid, order, axis_index, acc=6):
         super().__init__(grid, order, axis_index)
         if not isinstance(self.axis, EquidistantAxis):
@@ -247,8 +249,20 @@ class FFTDiff(GridDiff):
         W = np.ascontiguousarray(self._W_1d, dtype=np.complex128).view(np.float64)
         Wk, W_p = _lib.as_f64(W)
         n = len(self.axis)
-        Dk, D_p = (None, None) if _tables.is_pow2(n) and n <= 8192 else _lib.as_f64(self._dense_matrix())
         out = C.c_void_p()
+        pow2 = _tables.is_pow2(n) and n <= 8192
+        # Any other length: first derivatives run as a zero-padded power-of-two transform (O(n log n) like the
+        # reference's pocketfft, within a few 1e-14 of it); higher orders amplify the padded transform's rounding
+        # beyond the 1e-11 contract (order 2: 1e-11 at n = 1000), so they keep the dense O(n^2) contraction, as do
+        # short axes, where it is faster.
+        padded = None if pow2 or self.order != 1 or n < self.PADDED_MIN_POINTS else _tables.fft_padded_multiplier(self._W_1d)
+        if padded is not None:
+            m, Wm = padded
+            Wmk, Wm_p = _lib.as_f64(np.ascontiguousarray(Wm, dtype=np.complex128).view(np.float64))
+            _lib.check(lib.ng_fft_plan_create_padded(len(shp), shp_p, self.axis_index, m, Wm_p, C.byref(out)),
+                       "ng_fft_plan_create_padded")
+            return _lib.Plan(out.value)
+        Dk, D_p = (None, None) if pow2 else _lib.as_f64(self._dense_matrix())
         _lib.check(lib.ng_fft_plan_create(len(shp), shp_p, self.axis_index, W_p, D_p, C.byref(out)),
                    "ng_fft_plan_create")
         return _lib.Plan(out.value)

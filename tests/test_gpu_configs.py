@@ -416,3 +416,43 @@ def test_matrix_free_linear_operator(gpu_ready):
         ref = d.as_matrix() @ v
         assert rel_linf(L @ v, ref) <= 1e-12
         assert rel_linf(L.rmatvec(v), d.as_matrix().T @ v) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [65, 96, 100, 200, 360, 500, 1000, 1536, 3000])
+def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
+    """Periodic axes whose length is not a power of two: first derivatives run as a zero-padded power-of-two
+    transform (two-pass register kernel up to n = 512, radix-2 kernel above), not the O(n^2) dense contraction;
+    <= 1e-11 against numpy.fft (oracle) on the last axis and on a strided one, plain and fused (polar Laplacian)."""
+    import torch
+    from numgrids_b200 import _lib
+    p = ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi)
+    e = ng.create_axis(A.EQUIDISTANT, 10, 0.0, 1.0)
+    rng = np.random.default_rng(n)
+    for axes, axis in (((e, p), 1), ((p, e), 0)):
+        g = ng.Grid(*axes)
+        X = g.meshed_coords[axis]
+        f = np.exp(np.sin(X)) * np.cos(2 * X) + 0.05 * rng.standard_normal(g.shape)
+        out = ng.Diff(g, 1, axis)(torch.from_numpy(f).cuda())
+        kernel = _lib.last_kernel()
+        assert "padded" in kernel, kernel
+        assert ("fft2pass" in kernel) == (n <= 512), (n, kernel)
+        ref = pencil.fft_apply(f, axis, pencil.fft_multiplier(n, p.spacing, 1))
+        err = rel_linf(out.cpu().numpy(), ref)
+        assert err <= TOL_FFT, (n, axis, err)
+    # order 2 keeps the dense contraction (the padded transform's rounding would exceed the contract at large n)
+    if n <= 500:
+        g = ng.Grid(e, p)
+        f = rng.standard_normal(g.shape)
+        out = ng.Diff(g, 2, 1)(f)
+        assert _lib.last_kernel().startswith("dense"), _lib.last_kernel()
+        assert rel_linf(out, pencil.fft_apply(f, 1, pencil.fft_multiplier(n, p.spacing, 2))) <= TOL_FFT
+    # fused: polar Laplacian with n points in phi (Chebyshev r), through the radix-2 kernel's fused path
+    if n in (100, 360):
+        r = ng.create_axis(A.CHEBYSHEV, 12, 0.5, 2.0)
+        pg = ng.PolarGrid(r, p)
+        R, P = pg.meshed_coords
+        f = R ** 2 * np.cos(2 * P) + np.exp(-R) * np.sin(P)
+        pax = [pencil.make_axis("chebyshev", 12, 0.5, 2.0), pencil.make_axis("periodic", n, 0.0, 2 * np.pi)]
+        D = [pencil.make_diff(pax, 1, i) for i in range(2)]
+        ref = pencil.laplacian(f, (np.ones_like(R), R), D)
+        assert rel_linf(pg.laplacian(f), ref) <= TOL_FFT
