@@ -316,7 +316,7 @@ __device__ __forceinline__ void cl_output(int x, int y0, int z0, int lane, int n
 // the LAST warp to finish an iteration re-arms the slot's mbarrier and issues the TMA for the plane that
 // takes its place at once, so the ring stays S-5 planes ahead without anybody waiting for a producer.
 template <int R, int WY, int S, bool GEN>
-__global__ void __launch_bounds__(32 * WY, 256 / (32 * WY))
+__global__ void __launch_bounds__(32 * WY, (R * WY >= 32 ? 1 : 2))
 curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx, int ny, int nz, int xchunk,
                  const __grid_constant__ ClTabs T, const __grid_constant__ ClGen G, const ClParams* __restrict__ P,
                  const __grid_constant__ CUtensorMap tmap) {
@@ -534,6 +534,7 @@ int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStrea
     int rc;
     switch ((int)NG_ENV_INT("NG_CURV_CFG", 0)) {    // tuning: tile rows / ring depth (profiles/r02_tune_curvlap.txt)
         case 1: rc = cl_launch<4, 8, 9>(p, in, out, hp, gen, st); break;      // 32 x 64 tiles, one CTA of 8 warps per SM
+        case 2: rc = cl_launch<2, 8, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, 2 rows per warp: two CTAs of 8 warps
         default: rc = cl_launch<4, 4, 8>(p, in, out, hp, gen, st); break;     // 16 x 64 tiles, two CTAs of 4 warps per SM
     }
     if (rc) return rc;

@@ -71,7 +71,6 @@ struct RowCtx {
     const double* lo_row;                                    // this row's P halo values, or nullptr
     const double* hi_row;
     i64 base, pre0, pre_a, post0, post_a, div0, div_a;
-    double pre_c;                                            // the pre coefficient when it is constant along the row
     int n;
 
     __device__ __forceinline__ double value_at(const FuseDev& F, int q) const {
@@ -86,14 +85,9 @@ struct RowCtx {
         double2 v = make_double2(0.0, 0.0);
         if (!CHECK || (pos >= 0 && pos < n)) {
             v = ldg128(src + pos);
-            if (FUSED && fm_pre<MODE>(F)) {
-                if (pre_a == 0) {
-                    v.x = __dmul_rn(pre_c, v.x);
-                    v.y = __dmul_rn(pre_c, v.y);
-                } else {
-                    v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
-                    v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
-                }
+            if (FUSED && fm_pre<MODE>(F)) {      // (a row-constant table is the same address twice: one L1 line, no branch)
+                v.x = __dmul_rn(F.pre.ptr[pre0 + pos * pre_a], v.x);
+                v.y = __dmul_rn(F.pre.ptr[pre0 + (pos + 1) * pre_a], v.y);
             }
         } else if (HALO) {
             v.x = value_at(F, pos);
@@ -247,10 +241,9 @@ fd_row_kernel(const double* __restrict__ in, double* __restrict__ out, i64 rows,
     R.lo_row = (HALO && lo) ? lo + row * P : nullptr;
     R.hi_row = (HALO && hi) ? hi + row * P : nullptr;
     R.pre0 = R.pre_a = R.post0 = R.post_a = R.div0 = R.div_a = 0;
-    R.pre_c = 0.0;
     if (FUSED) {
         const Idx4 ix = unravel4(R.base, F.shape);           // coordinate along `axis` (the last one) is 0
-        if (fm_pre<MODE>(F)) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; R.pre_c = R.pre_a == 0 ? __ldg(F.pre.ptr + R.pre0) : 0.0; }
+        if (fm_pre<MODE>(F)) { R.pre0 = coef_off(F.pre, ix); R.pre_a = F.pre.s[axis]; }
         if (fm_post<MODE>(F)) { R.post0 = coef_off(F.post, ix); R.post_a = F.post.s[axis]; }
         if (fm_div<MODE>(F)) { R.div0 = coef_off(F.div, ix); R.div_a = F.div.s[axis]; }
     }
