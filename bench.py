@@ -692,6 +692,27 @@ def run_gpu_arm(args):
     ms_per_step = elapsed_ms / args.steps
     value = global_pts / ms_per_step / 1e6
 
+    # ---- sustained number (N = 1): >= 2 s of back-to-back applies; the part settles at its 1000 W cap
+    sustained = None
+    if world == 1 and not args.no_extras:
+        nrun = 640
+        sampler2 = NvmlSampler(local_rank)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(nrun + 1)]
+        torch.cuda.synchronize()
+        sampler2.start()
+        ts0 = time.perf_counter()
+        ev[0].record()
+        for i in range(nrun):
+            slab.apply_local(f, out)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ts1 = time.perf_counter()
+        tail = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(nrun // 2, nrun))
+        ms_s = tail[len(tail) // 2]
+        sustained = {"applies": nrun, "seconds": ts1 - ts0, "ms_per_apply_median_second_half": ms_s,
+                     "gpts": local_pts / ms_s / 1e6, "hbm_frac": 16.0 * local_pts / ms_s / 1e6 / peak_gbs,
+                     "clocks_nvml_1khz": sampler2.stop(ts0 + 0.5 * (ts1 - ts0), ts1)}
+
     # ---- parity: every rank checks the array it just timed against the oracle (bit for bit)
     try:
         p_equal, p_err, p_pts = parity_check(torch, gshape, hs, slab.z0, slab.z1, out, dev)
@@ -807,7 +828,7 @@ def run_gpu_arm(args):
                                        "NCCL send/recv: " + str(getattr(slab, "_symm_error", "disabled"))))},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "parity": parity, "parity_checked": bool(parity.get("parity_checked") and parity.get("bit_exact")),
-        "step_parts": parts, "per_config": extras if extras is not None else multi,
+        "step_parts": parts, "sustained": sustained, "per_config": extras if extras is not None else multi,
     }
     print(json.dumps(line))
     if world > 1:

@@ -20,3 +20,11 @@ def test_fast_kernels_equal_simple_kernels(gpu_ready, tool, cases, seed):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "0 mismatches" in r.stdout
+
+
+def test_fused_laplacian_kernels_equal_the_simple_kernel(gpu_ready):
+    """Plane-ring kernel (every ring depth, several x chunks), register-march fallback, slab halos and the interior /
+    boundary split, all against the thread-per-point kernel: tools/check_fdlap.py."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_fdlap.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bad 0" in r.stdout
