@@ -625,7 +625,7 @@ def run_gpu_arm(args):
                 b.record()
                 kernel_ms.append((a, b))
             return
-        slab.stencil_events = stencil_ev if (record and not args.no_overlap) else None
+        slab.stencil_events = stencil_ev if (record == "parts" and not args.no_overlap) else None
         if record and args.no_overlap:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -663,6 +663,13 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         clocks["nvml_1khz"] = nvml.stop(t_host0, t_host1)
+    if world > 1 and not args.no_overlap:
+        # the timed steps above ran the product path (ng_slab_lap_apply: the whole step behind the C ABI); the per-part
+        # times come from a few extra steps of the same sequence driven from Python with CUDA events between the parts
+        for _ in range(min(args.steps, 5)):
+            step(record="parts")
+        barrier()
+        slab.stencil_events = None
     k_ms = [a.elapsed_time(b) for a, b in kernel_ms]
     parts = None
     if stencil_ev:
@@ -822,10 +829,13 @@ def run_gpu_arm(args):
         "config": workload_config(n_gpus, scale),
         "details": {"local_shape": local_shape,
                     "halo_exchange": ("none (1 GPU)" if world == 1 else
-                                      ("NVLink peer stores from the pack kernel (symmetric memory) + per-neighbour signals; "
-                                       "interior z tiles on the main stream, boundary z tiles behind the signals on a side stream"
-                                       if getattr(slab, "_symm", None) is not None else
-                                       "NCCL send/recv: " + str(getattr(slab, "_symm_error", "disabled"))))},
+                                      ("ng_slab_lap_apply (C ABI): " if getattr(slab, "_cabi_plan", None) is not None else
+                                       "slab.py (per-part events): ") +
+                                      ("NVLink peer stores from the pack kernel (symmetric memory) + per-neighbour flags; "
+                                       "interior z tiles on the main stream, boundary z tiles behind the flags on a side stream"
+                                       if getattr(slab, "_symm", None) is not None or getattr(slab, "_cabi_plan", None) is not None
+                                       else "NCCL send/recv: " + str(getattr(slab, "_symm_error", "disabled")) + " / "
+                                            + str(getattr(slab, "_cabi_error", ""))))},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "parity": parity, "parity_checked": bool(parity.get("parity_checked") and parity.get("bit_exact")),
         "step_parts": parts, "sustained": sustained, "per_config": extras if extras is not None else multi,

@@ -195,6 +195,29 @@ int ng_fdlap_apply_host(ng_plan* plan, const double* h_in, double* h_out);
 int ng_fdlap_pack_halo_range(const ng_plan* plan, const double* d_in, double* d_lo_planes,
                              double* d_hi_planes, int64_t x_begin, int64_t x_end, void* stream);
 
+/* ---- one multi-GPU step of the fused Cartesian Laplacian (one process per GPU, last axis sharded) ------------------
+ * pack kernel (stores this rank's first / last nb columns straight into the neighbours' halo buffers) -> one 8-byte flag
+ * per neighbour -> interior z tiles on `stream` || boundary z tiles on the plan's side stream once both neighbours'
+ * flags have arrived -> join on `stream`.  The library maps no peer memory: every pointer below must be valid in THIS
+ * process -- the neighbours' buffers through CUDA IPC, fabric handles, or torch symmetric memory (numgrids_b200/slab.py).
+ * Halo buffers hold [rows][nb] doubles (rows = product of the unsharded local extents), two sets that alternate per
+ * step.  Flags are step counters stored with release / read with acquire at system scope; they must start at 0. */
+typedef struct ng_slab_comm {
+    int32_t rank, nranks;
+    double* my_halo[2][2];        /* [set][0 = from the lower neighbour, 1 = from the upper one]: this rank's buffers */
+    double* peer_lo_halo[2];      /* [set] the LOWER neighbour's my_halo[set][1], mapped here (NULL on rank 0)         */
+    double* peer_hi_halo[2];      /* [set] the UPPER neighbour's my_halo[set][0], mapped here (NULL on the last rank)  */
+    uint64_t* my_flags;           /* 2 words in this rank's memory: [0] written by the lower, [1] by the upper neighbour */
+    uint64_t* peer_lo_flag;       /* the lower neighbour's my_flags + 1, mapped here                                   */
+    uint64_t* peer_hi_flag;       /* the upper neighbour's my_flags + 0, mapped here                                   */
+} ng_slab_comm;
+/* local_shape = this rank's slab; axis_plans = the ndim second-derivative FD plans of that shape (global spacings). */
+int ng_slab_plan_create(const ng_slab_comm* comm, int ndim, const int64_t* local_shape, ng_plan* const* axis_plans,
+                        ng_plan** out);
+int ng_slab_lap_apply(ng_plan* plan, const double* d_f, double* d_out, void* stream);
+/* 1 after a wait gave up (~10 s without a neighbour's flag: crashed rank, mismatched step counts); synchronises. */
+int ng_slab_timed_out(ng_plan* plan);
+
 /* ---- curvilinear composites: CurvilinearGrid.gradient/divergence/laplacian/curl ---------------
  * numgrids/curvilinear.py:153-317.  axis_plans[i] is the first-derivative plan of axis i
  * (curvilinear.py:142-149).  Coefficients are evaluated on the host exactly as the reference does

@@ -31,6 +31,12 @@ class NgFuse(C.Structure):
                 ("add_zero", C.c_int32), ("divisor", NgCoef), ("finite", C.c_int32)]
 
 
+class NgSlabComm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("my_halo", (C.c_void_p * 2) * 2),
+                ("peer_lo_halo", C.c_void_p * 2), ("peer_hi_halo", C.c_void_p * 2), ("my_flags", C.c_void_p),
+                ("peer_lo_flag", C.c_void_p), ("peer_hi_flag", C.c_void_p)]
+
+
 class NgCopyBlock(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("row_len", C.c_int64),
                 ("src_stride", C.c_int64), ("dst_stride", C.c_int64), ("local_offset", C.c_int64)]
@@ -72,6 +78,9 @@ SIGNATURES = {
     "ng_fdlap_apply_slab_part": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "ng_fdlap_apply_host": (C.c_int, [_P, _P, _P]),
     "ng_fdlap_pack_halo_range": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "ng_slab_plan_create": (C.c_int, [C.POINTER(NgSlabComm), C.c_int, _I64, _PP, _PP]),
+    "ng_slab_lap_apply": (C.c_int, [_P, _P, _P, _P]),
+    "ng_slab_timed_out": (C.c_int, [_P]),
     "ng_curv_plan_create": (C.c_int, [C.c_int, _I64, _PP, _PP]),
     "ng_curv_set_coef": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int64, _I64]),
     "ng_curv_laplacian": (C.c_int, [_P, _P, _P, _P]),

@@ -601,6 +601,7 @@ int ng_plan_destroy(ng_plan* p) {
     fr(p->d_xdiv); fr(p->d_M); fr(p->d_Mt); fr(p->d_Mtp); fr(p->d_W); fr(p->d_tw); fr(p->d_Wn); fr(p->d_twn); fr(p->d_work);
     fr(p->d_stage_in); fr(p->d_stage_out);
     if (p->d_curvlap) cudaFree(p->d_curvlap);
+    if (p->slab) ng_slab_state_destroy(p->slab);
     fr(p->cJ.d_ptr);
     for (int a = 0; a < NG_MAX_DIM; ++a) {
         fr(p->cLap[a].d_ptr); fr(p->cDiv[a].d_ptr); fr(p->cGrad[a].d_ptr);

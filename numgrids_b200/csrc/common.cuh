@@ -113,7 +113,8 @@ struct FuseDev {
     i64 shape[NG_MAX_DIM];
 };
 
-enum PlanKind { PK_FD = 1, PK_CHEB = 2, PK_FFT = 3, PK_FDLAP = 4, PK_CURV = 5 };
+enum PlanKind { PK_FD = 1, PK_CHEB = 2, PK_FFT = 3, PK_FDLAP = 4, PK_CURV = 5, PK_SLAB = 6 };
+void ng_slab_state_destroy(void* state);     // slab.cu
 
 struct CoefHost {           // device-resident compact coefficient table owned by a curv plan
     double* d_ptr = nullptr;
@@ -163,6 +164,9 @@ struct ng_plan {
     double* d_work = nullptr;
     void* d_curvlap = nullptr;   // parameter block of the single-pass Laplacian (curvlap3d.cu)
 
+    // PK_SLAB
+    void* slab = nullptr;        // SlabState (slab.cu): local Laplacian plan, peer pointers, side stream, events
+
     // host-call staging (ng_apply_host / ng_fdlap_apply_host)
     double* d_stage_in = nullptr;
     double* d_stage_out = nullptr;
@@ -181,6 +185,8 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
                   cudaStream_t st);
 int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                        cudaStream_t st, bool* handled);
+int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
+                           cudaStream_t st, bool* handled);
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,
                     const double* hi, i64 xbeg, i64 xend, int zmode, cudaStream_t st);
 int ng_apply_any(const ng_plan* p, const double* in, double* out, const FuseDev& F,

@@ -1,0 +1,235 @@
+// fft_net.cuh -- pieces shared by the periodic-derivative kernels (fft2.cu: contiguous axis, fft_tile.cu: strided
+// axis through shared-memory tiles): compile-time radix networks held in registers, the per-pencil coefficient
+// helpers of the fused applies, the rare non-finite slow path, and the mbarrier / bulk-copy wrappers.
+// Reference: numgrids/diff.py:133-143 (out = real(ifft(W * fft(f)))).
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double cos32(int k) {      // cos(2 pi k / 32), k = 0..15, correctly rounded
+    switch (k) {
+        case 0: return 1.0;
+        case 1: return 0.9807852804032304;
+        case 2: return 0.9238795325112867;
+        case 3: return 0.8314696123025452;
+        case 4: return 0.7071067811865476;
+        case 5: return 0.5555702330196022;
+        case 6: return 0.3826834323650898;
+        case 7: return 0.19509032201612828;
+        case 8: return 0.0;
+        case 9: return -0.19509032201612828;
+        case 10: return -0.3826834323650898;
+        case 11: return -0.5555702330196022;
+        case 12: return -0.7071067811865476;
+        case 13: return -0.8314696123025452;
+        case 14: return -0.9238795325112867;
+        default: return -0.9807852804032304;
+    }
+}
+__device__ __forceinline__ double sin32(int k) { return cos32(k < 8 ? 8 - k : k - 8); }
+// sin(2 pi k/32) = cos(2 pi (8-k)/32) for k <= 8 and cos(2 pi (k-8)/32) for k >= 8 (both non-negative)
+
+__device__ __forceinline__ double2 cmul(double2 a, double c, double s) {     // a * (c + i s)
+    return make_double2(fma(a.x, c, -(a.y * s)), fma(a.x, s, a.y * c));
+}
+
+// multiply by exp(SIGN * 2 pi i k / 32), k in [0, 16), with the trivial cases folded at compile time
+template <int SIGN>
+__device__ __forceinline__ double2 rot32(double2 a, int k) {
+    if (k == 0) return a;
+    if (k == 8) return SIGN < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+    return cmul(a, cos32(k), SIGN < 0 ? -sin32(k) : sin32(k));
+}
+
+__host__ __device__ __forceinline__ constexpr int bitrev(int v, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) if (v & (1 << b)) r |= 1 << (bits - 1 - b);
+    return r;
+}
+template <int R> struct Log2 { static constexpr int v = 1 + Log2<R / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// Forward DIF network on x[0..R): natural order in, X[k] ends in x[bitrev(k)].
+template <int R>
+__device__ __forceinline__ void dif_forward(double2* x) {
+#pragma unroll
+    for (int s = R / 2; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if ((i & s) == 0) {
+                const double2 u = x[i], v = x[i + s];
+                x[i] = make_double2(u.x + v.x, u.y + v.y);
+                const double2 d = make_double2(u.x - v.x, u.y - v.y);
+                x[i + s] = rot32<-1>(d, (i & (s - 1)) * (16 / s));       // exp(-2 pi i j / (2s))
+            }
+        }
+    }
+}
+// Inverse DIT network: x[bitrev(k)] = X[k] in, natural order out (unnormalised).
+template <int R>
+__device__ __forceinline__ void dit_inverse(double2* x) {
+#pragma unroll
+    for (int s = 1; s <= R / 2; s <<= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if ((i & s) == 0) {
+                const double2 u = x[i];
+                const double2 v = rot32<+1>(x[i + s], (i & (s - 1)) * (16 / s));
+                x[i] = make_double2(u.x + v.x, u.y + v.y);
+                x[i + s] = make_double2(u.x - v.x, u.y - v.y);
+            }
+        }
+    }
+}
+
+// Non-finite samples (the reference's inf/nan rows on coordinate singularities before its final
+// isfinite select, numgrids/curvilinear.py:236-244).  Two real pencils share one complex transform,
+// so one bad pencil would poison its partner.  inf/nan survive every +, -, * of the transform and
+// every output depends on every input of both pencils, so ONE test of a finished output per lane
+// detects a poisoned pair at no cost to the clean path; the pair is then redone one pencil at a
+// time by this warp-cooperative radix-2 routine (rare, slow): a pencil with a non-finite sample
+// comes out all-NaN (what numpy.fft makes of it), a clean one gets its derivative.
+template <bool FUSED>
+__device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, double* __restrict__ out, i64 base,
+                                             i64 step, int ax, int N, int log2n, double2* S,
+                                             const double2* __restrict__ Wn, const double2* __restrict__ tw,
+                                             const FuseDev& F, int nv /* samples in memory (zero padding above) */) {
+    // sample k of the pencil sits at base + k*step and has coordinate k along grid axis `ax`
+    const int lane = threadIdx.x & 31;
+    Idx4 ix;
+    if (FUSED) ix = unravel4(base, F.shape);
+    bool bad = false;
+    for (int k = lane; k < N; k += 32) {
+        double v = k < nv ? in[base + k * step] : 0.0;
+        if (FUSED && F.pre.ptr) {
+            ix.i[ax] = k;
+            v = __dmul_rn(F.pre.ptr[coef_off(F.pre, ix)], v);
+        }
+        if (ng_nonfinite(v)) { bad = true; v = 0.0; }
+        S[k] = make_double2(v, 0.0);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (!bad) {
+        const int half = N >> 1;
+        for (int st = log2n - 1; st >= 0; --st) {            // forward DIF: natural in, bit-reversed out
+            const int m = 1 << st;
+            for (int e = lane; e < half; e += 32) {
+                const int j = e & (m - 1);
+                const int i0 = ((e >> st) << (st + 1)) + j, i1 = i0 + m;
+                const double2 w = tw[j << (log2n - 1 - st)];
+                const double2 u = S[i0], v = S[i1];
+                S[i0] = make_double2(u.x + v.x, u.y + v.y);
+                S[i1] = cmul(make_double2(u.x - v.x, u.y - v.y), w.x, w.y);
+            }
+            __syncwarp();
+        }
+        for (int k = lane; k < N; k += 32) {
+            const double2 w = Wn[__brev((unsigned)k) >> (32 - log2n)];
+            S[k] = cmul(S[k], w.x, w.y);
+        }
+        __syncwarp();
+        for (int st = 0; st < log2n; ++st) {                 // inverse DIT: bit-reversed in, natural out
+            const int m = 1 << st;
+            for (int e = lane; e < half; e += 32) {
+                const int j = e & (m - 1);
+                const int i0 = ((e >> st) << (st + 1)) + j, i1 = i0 + m;
+                const double2 w = tw[j << (log2n - 1 - st)];
+                const double2 u = S[i0], v = cmul(S[i1], w.x, -w.y);
+                S[i0] = make_double2(u.x + v.x, u.y + v.y);
+                S[i1] = make_double2(u.x - v.x, u.y - v.y);
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = lane; k < nv; k += 32) {
+        double d = bad ? ng_nan() : S[k].x;
+        if (FUSED) {
+            ix.i[ax] = k;
+            d = fuse_tail(F, d, base + k * step, ix);
+        }
+        out[base + k * step] = d;
+    }
+    __syncwarp();
+}
+
+// ng_fuse along a contiguous pencil, for a lane that owns samples idx = t + r*R2 (r compile-time):
+// the coefficient offsets of the pencil are found once (one unravel per pencil), every operand
+// becomes a per-lane base pointer plus r times a per-pencil step, and a coefficient that does
+// not vary along the pencil (spherical J/h^2 tables depend on (r, theta) only) is loaded once --
+// instead of an unravel + 4-term 64-bit offset per sample, which cost more instructions than the
+// transform itself.
+struct PencilCoef {
+    const double* p;      // table entry of this lane's sample r = 0 (nullptr = absent)
+    i64 step;             // elements between this lane's consecutive samples (0: constant along the pencil)
+    double c;             // the value when step == 0
+    __device__ __forceinline__ void init(const CoefDev& C, const Idx4& ix0, int vec_axis, int t, int R2) {
+        const i64 s = C.s[vec_axis];
+        p = C.ptr ? C.ptr + coef_off(C, ix0) + t * s : nullptr;
+        step = s * R2;
+        c = (p && step == 0) ? *p : 0.0;
+    }
+    __device__ __forceinline__ double at(int r) const { return step == 0 ? c : p[r * step]; }
+};
+struct PencilTail {
+    PencilCoef post, div;
+    const double *minuend, *addend;
+    i64 mstep;            // elements between this lane's consecutive samples in the full-shape operands
+    // the pencil's sample k sits at lin0 + k*step and has coordinate k along grid axis `ax`
+    // (contiguous pencils: step 1, ax = the innermost axis)
+    __device__ __forceinline__ void init(const FuseDev& F, i64 lin0, i64 step, int ax, int t, int R2) {
+        Idx4 ix = unravel4(lin0, F.shape);
+        ix.i[ax] = 0;
+        post.init(F.post, ix, ax, t, R2);
+        div.init(F.div, ix, ax, t, R2);
+        minuend = F.minuend ? F.minuend + lin0 + t * step : nullptr;
+        addend = F.addend ? F.addend + lin0 + t * step : nullptr;
+        mstep = step * R2;
+    }
+    // same steps and order as fuse_tail (common.cuh); sample r of this lane sits at offset r*mstep
+    __device__ __forceinline__ double apply(const FuseDev& F, double d, int r, int R2) const {
+        if (minuend) d = __dsub_rn(minuend[r * mstep], d);
+        if (post.p) d = __dmul_rn(post.at(r), d);
+        if (addend) d = __dadd_rn(addend[r * mstep], d);
+        else if (F.add_zero) d = __dadd_rn(0.0, d);
+        if (div.p) d = __ddiv_rn(d, div.at(r));
+        if (F.finite) d = ng_nonfinite(d) ? 0.0 : d;
+        return d;
+    }
+};
+__device__ __forceinline__ PencilCoef pencil_pre(const FuseDev& F, i64 lin0, int ax, int t, int R2) {
+    PencilCoef c;
+    Idx4 ix = unravel4(lin0, F.shape);
+    ix.i[ax] = 0;
+    c.init(F.pre, ix, ax, t, R2);
+    return c;
+}
+
+// mbarrier / bulk-copy helpers of the ring kernel
+__device__ __forceinline__ unsigned pf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pf_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pf_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pf_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pf_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pf_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = pf_smem_u32(bar);
+    unsigned done, spins = 0;
+    do {
+        if (++spins > (1u << 24)) __trap();          // bounded: a protocol bug must not hang the GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void pf_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(pf_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pf_smem_u32(bar)) : "memory");
+}
+
+}  // namespace

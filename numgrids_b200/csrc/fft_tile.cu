@@ -1,0 +1,286 @@
+// fft_tile.cu -- periodic spectral derivative along an axis that is NOT the contiguous one
+// (cylindrical phi in the middle, doubly periodic boxes; reference numgrids/diff.py:133-143 applies
+// numpy.fft along any axis).  n = 64 .. 1024 a power of two, array viewed as [outer][n][inner].
+//
+// Why a second kernel: with strided pencils every lane of the register kernel (fft2.cu) touches its
+// own 32-byte sector -- 32 L1 wavefronts for 512 useful bytes per load instruction -- and the LSU, not
+// HBM, sets the pace (0.27-0.31 of the copy peak, profiles/r01_tune_fft.txt).  Here no lane ever
+// loads from or stores to global memory:
+//   * a tile = all n rows of C = 8 or 16 adjacent columns (64 / 128 contiguous bytes per row) is
+//     brought in by TMA (cp.async.bulk.tensor, 256-row boxes) into a hardware-swizzled slot;
+//   * a warp owns the column PAIRS of its transforms: the 16-byte chunk c of every row.  The swizzle
+//     (chunk index XOR row bits) makes a quarter-warp's 8 consecutive rows hit 8 distinct 16-byte bank
+//     groups, so the column loads are conflict-free;
+//   * the pair's n x 16 B column is also its exchange buffer between the two register passes (same
+//     XOR-by-row trick as fft2.cu's ring kernel, mapped into the column) and finally receives the
+//     derivative in the input's own positions;
+//   * the finished tile leaves by ONE TMA store per 256 rows (full 64 / 128-byte row segments).
+// A CTA runs 8 warps as NG groups of WPT warps (one tile per group at a time) over NSLOT slots: tile s
+// of the CTA sits in slot s % NSLOT, is worked by group s % NG, and the group's leader refills the
+// slot with tile s + NSLOT once the store has drained it.  A slot's mbarrier completes phase k+1 only
+// after every warp of the group that waited for phase k has passed the group barrier behind it, so a
+// parity wait can never observe a stale phase.
+// Plain applies only (fused composites keep the strided register kernel); HBM traffic 16 B/point.
+#include "fft_net.cuh"
+
+#include <cuda.h>
+
+namespace {
+
+__device__ __forceinline__ void ft_tma_load_3d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ft_tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
+}
+__device__ __forceinline__ void ft_group_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// C columns per tile (row = C*8 bytes: 64 -> SWIZZLE_64B, 128 -> SWIZZLE_128B), NSLOT slots, 8 warps
+template <int RT, int R2, int C, int NSLOT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ Wn,
+                const double2* __restrict__ tw, i64 ntiles, int tiles_per_outer, i64 inner, int axis,
+                const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                const __grid_constant__ FuseDev F) {
+    constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T, NW = 8;
+    constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
+    constexpr int RS = C * 8;                            // bytes per tile row
+    constexpr int WPT = C / (2 * TPW);                   // warps per tile
+    constexpr int NG = NW / WPT;                         // groups per CTA
+    constexpr int BR = N < 256 ? N : 256;                // rows per TMA box
+    constexpr int SLOT_B = N * RS;
+    static_assert(RS == 64 || RS == 128, "tile rows are one swizzle span");
+    static_assert(WPT >= 1 && NW % WPT == 0, "groups tile the CTA");
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    unsigned char* slots = tsm;                                                       // [NSLOT][N][RS], swizzled
+    double2* TWS = reinterpret_cast<double2*>(tsm + (size_t)NSLOT * SLOT_B);          // [RT][T]  exp(-2 pi i kr t / n)
+    double2* WNS = TWS + N;                                                           // [N]      (ik)^order / n
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(WNS + N);        // [NSLOT]
+    int* poison = reinterpret_cast<int*>(full + NSLOT);                               // [NG][2]: flag of a group's even / odd tiles
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tr = lane / T, t = lane - tr * T;
+    const int grp = warp / WPT, wg = warp - grp * WPT;   // group, warp within the group
+    const int cp = wg * TPW + tr;                        // this lane's column pair = 16-byte chunk of every row
+    const bool leader = (wg == 0 && lane == 0);
+
+    for (int e = threadIdx.x; e < N; e += 32 * NW) {
+        TWS[e] = tw[(e / T) * (e % T)];
+        WNS[e] = Wn[e];
+    }
+    if (threadIdx.x < NSLOT) pf_mbar_init(full + threadIdx.x, 1);
+    if (threadIdx.x < 2 * NG) poison[threadIdx.x] = 0;
+    if ((pf_smem_u32(tsm) & 1023u) != 0) __trap();     // the swizzle formula below assumes 1 KB-aligned slots
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const i64 nmine = (ntiles - (i64)blockIdx.x + gridDim.x - 1) / gridDim.x;         // tiles of this CTA
+    auto issue = [&](i64 s) {                            // one lane: tile s of this CTA -> slot s % NSLOT
+        const i64 id = s * gridDim.x + blockIdx.x;
+        const int o = (int)(id / tiles_per_outer);
+        const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
+        const int sl = (int)(s % NSLOT);
+        unsigned long long* bar = full + sl;
+        pf_mbar_expect_tx(bar, (unsigned)SLOT_B);
+#pragma unroll
+        for (int b = 0; b < N / BR; ++b)
+            ft_tma_load_3d(pf_smem_u32(slots + (size_t)sl * SLOT_B + (size_t)b * BR * RS), &tm_in, c0, b * BR, o,
+                           pf_smem_u32(bar));
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < NSLOT && s < nmine; ++s) issue(s);
+
+    // byte offset of row e of this lane's pair column inside a slot (hardware swizzle: 16-byte chunk ^= row bits)
+    auto col = [&](int e) -> unsigned {
+        const int sw = RS == 128 ? (e & 7) : ((e >> 1) & 3);
+        return (unsigned)e * RS + (unsigned)((cp ^ sw) << 4);
+    };
+
+    int par = 0;
+    for (i64 s = grp; s < nmine; s += NG, par ^= 1) {
+        // the flag alternates per tile: a warp that runs ahead into the group's next tile never touches the flag a
+        // slower warp is about to read
+        int* myflag = poison + 2 * grp + par;
+        const int sl = (int)(s % NSLOT);
+        unsigned char* slot = slots + (size_t)sl * SLOT_B;
+        pf_mbar_wait(full + sl, (unsigned)((s / NSLOT) & 1));
+        double2 x[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) x[r] = *reinterpret_cast<const double2*>(slot + col(r * R2 + t));
+        __syncwarp();                              // the column becomes the exchange buffer
+        dif_forward<RT>(x);
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const int kr = bitrev(q, LRT);
+            double2 v = x[q];
+            if (kr != 0) {
+                const double2 w = TWS[kr * T + t];
+                v = cmul(v, w.x, w.y);
+            }
+            *reinterpret_cast<double2*>(slot + col(kr * R2 + (t ^ (kr & (R2 - 1))))) = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int kr = t + T * g;
+            double2* y = x + g * R2;
+#pragma unroll
+            for (int j = 0; j < R2; ++j) y[j] = *reinterpret_cast<const double2*>(slot + col(kr * R2 + (j ^ t)));
+            dif_forward<R2>(y);
+#pragma unroll
+            for (int q = 0; q < R2; ++q) {
+                const int k2 = bitrev(q, LR2);
+                const double2 w = WNS[kr + RT * k2];
+                y[q] = cmul(y[q], w.x, w.y);
+            }
+            dit_inverse<R2>(y);
+#pragma unroll
+            for (int j = 0; j < R2; ++j) *reinterpret_cast<double2*>(slot + col(kr * R2 + (j ^ t))) = y[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < RT; ++q) {
+            const int kr = bitrev(q, LRT);
+            double2 v = *reinterpret_cast<const double2*>(slot + col(kr * R2 + (t ^ (kr & (R2 - 1)))));
+            if (kr != 0) {
+                const double2 w = TWS[kr * T + t];
+                v = cmul(v, w.x, -w.y);
+            }
+            x[q] = v;
+        }
+        dit_inverse<RT>(x);
+        __syncwarp();                              // every lane has its rows back: the column takes the result
+#pragma unroll
+        for (int r = 0; r < RT; ++r) *reinterpret_cast<double2*>(slot + col(r * R2 + t)) = x[r];
+        const bool bad = __any_sync(0xffffffffu, ng_nonfinite(x[0].x) || ng_nonfinite(x[0].y));
+        if (bad && lane == 0) atomicOr(myflag, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        ft_group_bar(1 + grp, 32 * WPT);
+        const i64 id = s * gridDim.x + blockIdx.x;
+        const int o = (int)(id / tiles_per_outer);
+        const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
+        if (leader) {
+#pragma unroll
+            for (int b = 0; b < N / BR; ++b)
+                ft_tma_store_3d(&tm_out, c0, b * BR, o, pf_smem_u32(slot + (size_t)b * BR * RS));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (*reinterpret_cast<volatile int*>(myflag)) {
+            // Rare: a non-finite sample poisoned a pair (see fft_slow_pencil).  Once the tile's store has landed, the
+            // pencils of the poisoned warps are redone one at a time straight from / to global memory; the drained
+            // slot is the scratch space.
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            ft_group_bar(1 + grp, 32 * WPT);
+            if (bad) {
+                for (int q = 0; q < 2 * TPW; ++q) {
+                    const i64 cc = c0 + (i64)(wg * TPW) * 2 + q;
+                    if (cc < inner)
+                        fft_slow_pencil<false>(in, out, (i64)o * N * inner + cc, inner, axis, N, LRT + LR2,
+                                               reinterpret_cast<double2*>(slot + (size_t)(wg * TPW + (q >> 1)) * N * 16),
+                                               Wn, tw, F, N);
+                }
+            }
+            ft_group_bar(1 + grp, 32 * WPT);
+            if (leader) *myflag = 0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            ft_group_bar(1 + grp, 32 * WPT);
+        }
+        if (leader) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (s + NSLOT < nmine) issue(s + NSLOT);
+        }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+typedef CUresult (*ft_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D map over the [outer][n][inner] view (inner fastest), box = C x rows x 1, swizzle = the row size
+int ft_make_tmap(CUtensorMap* tm, const double* base, i64 outer, i64 n, i64 inner, int cols, int rows) {
+    static std::atomic<ft_encode_fn> encode{nullptr};
+    ft_encode_fn e = encode.load(std::memory_order_acquire);
+    if (!e) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NG_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
+        if (!fp || qres != cudaDriverEntryPointSuccess) {
+            ng_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return NG_ECUDA;
+        }
+        e = (ft_encode_fn)fp;
+        encode.store(e, std::memory_order_release);
+    }
+    struct Key { const void* p; i64 o, n, i; int c, r; };
+    struct Cache { Key k[8]; CUtensorMap m[8]; int used = 0, next = 0; };
+    thread_local Cache cache;
+    for (int i = 0; i < cache.used; ++i) {
+        const Key& k = cache.k[i];
+        if (k.p == base && k.o == outer && k.n == n && k.i == inner && k.c == cols && k.r == rows) { *tm = cache.m[i]; return NG_OK; }
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)n, (cuuint64_t)outer};
+    const cuuint64_t gstr[2] = {(cuuint64_t)inner * 8, (cuuint64_t)n * inner * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)cols, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = e(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, cols * 8 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ng_set_error("cuTensorMapEncodeTiled (fft tile) failed with CUresult %d", (int)r);
+        return NG_ECUDA;
+    }
+    const int slot = cache.used < 8 ? cache.used++ : (cache.next = (cache.next + 1) % 8);
+    cache.k[slot] = Key{base, outer, n, inner, cols, rows};
+    cache.m[slot] = *tm;
+    return NG_OK;
+}
+
+template <int RT, int R2, int C, int NSLOT, int MINB>
+int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+    constexpr int N = RT * R2, BR = N < 256 ? N : 256;
+    constexpr int NG = 8 / (C / (2 * (32 / R2)));
+    const i64 tpo = (p->inner + C - 1) / C;
+    const i64 ntiles = p->outer * tpo;
+    CUtensorMap tmi, tmo;
+    int rc = ft_make_tmap(&tmi, in, p->outer, N, p->inner, C, BR);
+    if (!rc) rc = ft_make_tmap(&tmo, out, p->outer, N, p->inner, C, BR);
+    if (rc) return rc;
+    const size_t smem = (size_t)NSLOT * N * C * 8 + (size_t)2 * N * 16 + NSLOT * 8 + NG * 8 + 16;
+    NG_FUNC_SMEM(smem, fft_tile_kernel<RT, R2, C, NSLOT, MINB>);
+    i64 g = (ntiles + NG - 1) / NG;                      // at least one tile per group
+    if (g > (i64)148 * MINB) g = (i64)148 * MINB;
+    fft_tile_kernel<RT, R2, C, NSLOT, MINB><<<(unsigned)g, 256, smem, st>>>(
+        in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, ntiles, (int)tpo, p->inner, p->axis, tmi, tmo, F);
+    NG_TRACE("fft_tile");
+    NG_LAUNCH_CHECK();
+    return NG_OK;
+}
+
+}  // namespace
+
+// Plain applies along a non-contiguous axis.  Needs 16-byte aligned arrays and an even inner extent (TMA strides
+// are multiples of 16 bytes) of at least one tile width; everything else stays on the strided register kernel.
+int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
+                           bool* handled) {
+    *handled = false;
+    if (F.any || p->inner == 1 || p->fft_len != p->n || !p->d_Wn || !p->d_twn) return NG_OK;
+    if (NG_ENV_INT("NG_FFT_TILE", 1) == 0) return NG_OK;        // A/B: 0 = strided register kernel
+    if ((p->inner & 1) || p->inner < 16 || ((((uintptr_t)in | (uintptr_t)out) & 15) != 0)) return NG_OK;
+    if (p->outer > 0x7fffffff || p->inner > 0x7fffffff) return NG_OK;
+    int rc = NG_OK;
+    switch (p->n) {
+        case 1024: rc = launch_tile<32, 32, 8, 3, 1>(p, in, out, F, st); break;
+        case 512: rc = launch_tile<32, 16, 16, 3, 1>(p, in, out, F, st); break;
+        case 256: rc = launch_tile<16, 16, 16, 3, 2>(p, in, out, F, st); break;
+        case 128: rc = launch_tile<16, 8, 16, 6, 2>(p, in, out, F, st); break;
+        case 64: rc = launch_tile<8, 8, 16, 12, 2>(p, in, out, F, st); break;
+        default: return NG_OK;
+    }
+    *handled = (rc == NG_OK);
+    return rc;
+}

@@ -127,6 +127,41 @@ class SymmetricHalo:
             self.hdl.wait_signal(self.hi_n, 2 * q + 1, timeout_ms)
 
 
+class SymmetricSlabComm:
+    """The peer-memory record of ``ng_slab_plan_create`` (include/numgrids_b200.h) from ONE torch symmetric-memory
+    allocation per rank: two halo sets [set][side][rows][nb] followed by the two flag words.  torch is used to
+    allocate and map the buffers only; pack, signals, stencil launches, streams and events are the C library's."""
+
+    def __init__(self, rows, nb, device, rank, nranks, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.nranks = rank, nranks
+        halo = rows * nb                                   # doubles per halo buffer
+        self.elems = 4 * halo + 2                          # + 2 flag words (8 bytes each, start at 0)
+        self.buf = symm.empty((self.elems,), dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        lo_n, hi_n = neighbours(rank, nranks)
+        base = self.buf.data_ptr()
+        peer = lambda r: self.hdl.get_buffer(r, (self.elems,), torch.float64).data_ptr()
+        off = lambda q, side: 8 * ((2 * q + side) * halo)
+        flags = 8 * 4 * halo
+        c = _lib.NgSlabComm()
+        c.rank, c.nranks = rank, nranks
+        for q in range(2):
+            for side in range(2):
+                c.my_halo[q][side] = base + off(q, side)
+            c.peer_lo_halo[q] = peer(lo_n) + off(q, 1) if lo_n is not None else None
+            c.peer_hi_halo[q] = peer(hi_n) + off(q, 0) if hi_n is not None else None
+        c.my_flags = base + flags
+        c.peer_lo_flag = peer(lo_n) + flags + 8 if lo_n is not None else None
+        c.peer_hi_flag = peer(hi_n) + flags if hi_n is not None else None
+        self.record = c
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=0)
+
+
 class SlabLaplacian:
     """Fused Cartesian Laplacian on this rank's last-axis slab of a global equidistant grid."""
 
@@ -217,6 +252,10 @@ class SlabLaplacian:
         out = t.empty_like(f) if out is None else out
         if self.nranks == 1:
             return self.apply_local(f, out)
+        if self._use_cabi(f):
+            _lib.check(_lib.load().ng_slab_lap_apply(self._cabi_plan.handle, f.data_ptr(), out.data_ptr(),
+                                                     _device.current_stream_ptr()), "ng_slab_lap_apply")
+            return out
         if self._use_symm(f):
             return self._call_symm(f, out)
         b = self.pack(f)
@@ -251,11 +290,37 @@ class SlabLaplacian:
             tm.append(ev)
         return out
 
+    # -- the whole step behind the C ABI (ng_slab_plan_create / ng_slab_lap_apply) ---------------------
+    def _use_cabi(self, f):
+        """Default multi-GPU path: torch symmetric memory only allocates and maps the halo / flag buffers; the step
+        itself (pack, flags, the two stencil launches, side stream, events) is ``ng_slab_lap_apply``.
+        NG_SLAB_EXCHANGE = cabi (default) | symm (the same sequence driven from Python, with per-part events) | nccl."""
+        import os
+        if os.environ.get("NG_SLAB_EXCHANGE", "cabi") != "cabi" or len(self.local_shape) != 3 \
+                or getattr(self, "_cabi_failed", False) or getattr(self, "stencil_events", None) is not None:
+            return False
+        if getattr(self, "_cabi_plan", None) is None:
+            try:
+                self._cabi_comm = SymmetricSlabComm(self.rows, self.nb, f.device, self.rank, self.nranks, self.group)
+                lib = _lib.load()
+                children = [make_fd_plan(self.local_shape, a, 2, self.acc, self.spacings[a]) for a in range(3)]
+                arr = _lib.ptr_array([p.handle.value for p in children])
+                shp, shp_p = _lib.as_i64(list(self.local_shape))
+                out = C.c_void_p()
+                _lib.check(lib.ng_slab_plan_create(C.byref(self._cabi_comm.record), 3, shp_p, arr, C.byref(out)),
+                           "ng_slab_plan_create")
+                self._cabi_plan = _lib.Plan(out.value, keepalive=children)
+            except Exception as e:          # no symmetric memory: the torch.distributed paths below
+                self._cabi_failed = True
+                self._cabi_error = repr(e)
+                return False
+        return True
+
     # -- NVLink peer-memory exchange (pack kernel stores straight into the neighbours' halos) -------
     def _use_symm(self, f):
         import os
-        mode = os.environ.get("NG_SLAB_EXCHANGE", "symm")
-        if mode != "symm" or len(self.local_shape) != 3 or getattr(self, "_symm_failed", False):
+        mode = os.environ.get("NG_SLAB_EXCHANGE", "cabi")
+        if mode not in ("symm", "cabi") or len(self.local_shape) != 3 or getattr(self, "_symm_failed", False):
             return False
         if getattr(self, "_symm", None) is None:
             try:

@@ -9,6 +9,10 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# test_slab_step_behind_the_c_abi runs several ranks' streams (with spinning flag waits) on one GPU: give every
+# stream its own hardware queue so that no wait kernel sits in front of the kernel it waits for (read at context creation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

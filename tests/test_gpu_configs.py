@@ -83,6 +83,47 @@ def test_cfg3_fft_ring_kernel_vs_oracle(gpu_ready, n):
         assert err <= (3e-11 if (order == 2 and n == 1024) else TOL_FFT), (n, order, err)
 
 
+@pytest.mark.parametrize("n", [1024, 512, 256, 128, 64])
+@pytest.mark.parametrize("shape_kind", ["middle", "first", "ragged"])
+def test_fft_strided_axis_tile_kernel_vs_oracle(gpu_ready, n, shape_kind):
+    """Periodic axis that is not the contiguous one (cylindrical phi in the middle, doubly periodic boxes): the TMA
+    tile kernel (csrc/fft_tile.cu), orders 1 and 2 against numpy.fft (oracle), 1e-11.  `ragged`: an inner extent
+    that is no multiple of the tile width (the last tile hangs over the array: zero-filled loads, clipped stores)
+    and more tiles than slots; one pencil carries an inf (the reference's singular rows): it must come out all-NaN
+    and leave its pair partner and every other pencil untouched."""
+    import torch
+    from numgrids_b200 import _lib
+    p = ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi)
+    if shape_kind == "middle":
+        axes, ax = [ng.create_axis(A.EQUIDISTANT, 5, 0.0, 1.0), p, ng.create_axis(A.CHEBYSHEV, 48, 0.0, 1.0)], 1
+    elif shape_kind == "first":
+        axes, ax = [p, ng.create_axis(A.EQUIDISTANT, 160, 0.0, 1.0)], 0
+    else:
+        axes, ax = [ng.create_axis(A.EQUIDISTANT, 3, 0.0, 1.0), p, ng.create_axis(A.EQUIDISTANT, 7, 0.0, 1.0),
+                    ng.create_axis(A.EQUIDISTANT, 6, 0.0, 1.0)], 1           # inner = 42
+    g = ng.Grid(*axes)
+    M = g.meshed_coords
+    P = M[ax]
+    others = [m for i, m in enumerate(M) if i != ax]
+    f = np.exp(np.sin(P)) * np.cos(2 * others[0]) + others[-1] * np.sin(3 * P)
+    if shape_kind == "ragged":
+        f[1, 5, 2, 3] = np.inf
+    fd = torch.from_numpy(f).cuda()
+    for order in (1, 2):
+        out = ng.Diff(g, order, ax)(fd)
+        assert _lib.last_kernel() == "fft_tile", _lib.last_kernel()
+        got = out.cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            ref = pencil.fft_apply(f, ax, pencil.fft_multiplier(n, p.spacing, order))
+        if shape_kind == "ragged":
+            assert np.all(np.isnan(got[1, :, 2, 3])) and np.all(np.isnan(ref[1, :, 2, 3]))
+            got[1, :, 2, 3] = ref[1, :, 2, 3] = 0.0
+        assert np.all(np.isfinite(got))
+        err = rel_linf(got, ref)
+        print(f"tile kernel n={n} {shape_kind} order {order}: rel Linf {err:.3e}")
+        assert err <= (3e-11 if (order == 2 and n == 1024) else TOL_FFT), (n, shape_kind, order, err)
+
+
 def test_cfg3_full_size_512x512x1024(gpu_ready):
     """BASELINE cfg3 at its stated size (2 GiB array, 262 144 pencils): pencils are independent, so three
     8-plane blocks of the full-size result are compared with numpy.fft on the same blocks."""

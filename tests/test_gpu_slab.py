@@ -136,3 +136,73 @@ def test_block_copy_argument_checks(gpu_ready):
     assert lib.ng_slab_block_copy(1, arr, 0, None, None, 0, None) != 0
     assert lib.ng_slab_block_copy(17, arr, 0, None, None, 0, None) != 0
     assert lib.ng_slab_block_copy(1, arr, 0, None, None, 1, None) != 0      # fused without fuse record
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_step_behind_the_c_abi(gpu_ready, nranks):
+    """ng_slab_plan_create / ng_slab_lap_apply (include/numgrids_b200.h): the whole multi-GPU step -- pack into the
+    neighbours' halo buffers, flags, interior || boundary tiles, join -- with every rank's plan living in THIS process:
+    the library takes plain device pointers, so the "peer" buffers are local tensors and the flags travel between the
+    ranks' side streams of the one GPU.  Several steps (the halo sets alternate); every slab bit for bit."""
+    import ctypes as C
+    import torch
+    from numgrids_b200 import _lib
+    from numgrids_b200.slab import SlabLaplacian, make_fd_plan
+    lib = _lib.load()
+    gshape = (40, 33, 48 * nranks + 5)
+    hs = [float(np.linspace(0, 1, n)[1]) for n in gshape]
+    torch.manual_seed(11)
+    fg = torch.randn(*gshape, dtype=torch.float64, device="cuda")
+    ref = SlabLaplacian(gshape, hs).apply_local(fg, torch.empty_like(fg))
+    ranks = [SlabLaplacian(gshape, hs, rank=r, nranks=nranks) for r in range(nranks)]
+    rows, nb = ranks[0].rows, ranks[0].nb
+    halo = [torch.zeros(2, 2, rows, nb, dtype=torch.float64, device="cuda") for _ in range(nranks)]
+    flags = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(nranks)]
+    plans, keep = [], []
+    for r, s in enumerate(ranks):
+        c = _lib.NgSlabComm()
+        c.rank, c.nranks = r, nranks
+        for q in range(2):
+            for side in range(2):
+                c.my_halo[q][side] = halo[r][q, side].data_ptr()
+            c.peer_lo_halo[q] = halo[r - 1][q, 1].data_ptr() if r > 0 else None
+            c.peer_hi_halo[q] = halo[r + 1][q, 0].data_ptr() if r < nranks - 1 else None
+        c.my_flags = flags[r].data_ptr()
+        c.peer_lo_flag = flags[r - 1].data_ptr() + 8 if r > 0 else None
+        c.peer_hi_flag = flags[r + 1].data_ptr() if r < nranks - 1 else None
+        children = [make_fd_plan(s.local_shape, a, 2, 4, hs[a]) for a in range(3)]
+        arr = _lib.ptr_array([p.handle.value for p in children])
+        shp, shp_p = _lib.as_i64(list(s.local_shape))
+        out = C.c_void_p()
+        _lib.check(lib.ng_slab_plan_create(C.byref(c), 3, shp_p, arr, C.byref(out)), "ng_slab_plan_create")
+        plans.append(_lib.Plan(out.value, keepalive=children))
+        keep.append(c)
+    streams = [torch.cuda.Stream() for _ in range(nranks)]
+    local = [fg[..., s.z0:s.z1].contiguous() for s in ranks]
+    outs = [torch.empty_like(x) for x in local]
+    # every kernel instance a step launches is loaded before the first flag wait spins: CUDA loads kernels lazily, and
+    # loading one synchronises the context -- across the ranks' streams when all ranks share ONE context as they do here
+    for r, s in enumerate(ranks):
+        b = s.pack(local[r])
+        s.apply_part(local[r], outs[r], 1)
+        s.apply_part(local[r], outs[r], 2, b["lo_halo"] if r > 0 else None, b["hi_halo"] if r < nranks - 1 else None)
+    torch.cuda.synchronize()
+    for step in range(4):
+        for o in outs:
+            o.fill_(float("nan"))
+        torch.cuda.synchronize()
+        for r in range(nranks):
+            _lib.check(lib.ng_slab_lap_apply(plans[r].handle, local[r].data_ptr(), outs[r].data_ptr(),
+                                             streams[r].cuda_stream), "ng_slab_lap_apply")
+        torch.cuda.synchronize()
+        for r, s in enumerate(ranks):
+            assert lib.ng_slab_timed_out(plans[r].handle) == 0
+            assert torch.equal(outs[r], ref[..., s.z0:s.z1]), ("step", step, "rank", r)
+    # argument checks: a rank with a neighbour but no buffers is refused
+    bad = _lib.NgSlabComm()
+    bad.rank, bad.nranks = 0, 2
+    out = C.c_void_p()
+    shp, shp_p = _lib.as_i64(list(ranks[0].local_shape))
+    children = [make_fd_plan(ranks[0].local_shape, a, 2, 4, hs[a]) for a in range(3)]
+    arr = _lib.ptr_array([p.handle.value for p in children])
+    assert lib.ng_slab_plan_create(C.byref(bad), 3, shp_p, arr, C.byref(out)) != 0

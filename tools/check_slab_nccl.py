@@ -40,7 +40,8 @@ for gshape in ((96, 80, 64 * world), (130, 64, 192 * world), (33, 47, 70 * world
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"global {gshape} on {world} ranks: bit-exact={bool(t.item())}")
+        path = "cabi" if getattr(s, "_cabi_plan", None) is not None else ("symm" if getattr(s, "_symm", None) is not None else "nccl")
+        print(f"global {gshape} on {world} ranks: bit-exact={bool(t.item())} path={path} {getattr(s, '_cabi_error', '')}")
     ok_all &= bool(t.item())
 dist.barrier()
 dist.destroy_process_group()
