@@ -17,9 +17,12 @@
 //   * the finished tile leaves by ONE TMA store per 256 rows (full 64 / 128-byte row segments).
 // A CTA runs 8 warps as NG groups of WPT warps (one tile per group at a time) over NSLOT slots: tile s
 // of the CTA sits in slot s % NSLOT, is worked by group s % NG, and the group's leader refills the
-// slot with tile s + NSLOT once the store has drained it.  A slot's mbarrier completes phase k+1 only
-// after every warp of the group that waited for phase k has passed the group barrier behind it, so a
-// parity wait can never observe a stale phase.
+// slot with tile s + NSLOT once the store has drained it.  Consecutive uses of a slot belong to
+// DIFFERENT groups, and a parity wait cannot tell "the load before mine has not landed yet" from "mine
+// has landed" -- so a slot has TWO mbarriers, for its even and its odd uses: (2 NSLOT) % NG == 0 makes
+// every phase of one mbarrier a tile of the same group, which waits for them in order (the usual
+// single-consumer argument), and a phase is re-armed only after that group has passed the group barrier
+// behind its wait.
 // Plain applies only (fused composites keep the strided register kernel); HBM traffic 16 B/point.
 #include "fft_net.cuh"
 
@@ -54,14 +57,15 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
     constexpr int NG = NW / WPT;                         // groups per CTA
     constexpr int BR = N < 256 ? N : 256;                // rows per TMA box
     constexpr int SLOT_B = N * RS;
-    static_assert(RS == 64 || RS == 128, "tile rows are one swizzle span");
+    static_assert(RS == 32 || RS == 64 || RS == 128, "tile rows are one swizzle span");
     static_assert(WPT >= 1 && NW % WPT == 0, "groups tile the CTA");
+    static_assert((2 * NSLOT) % NG == 0, "every other use of a slot belongs to the same group (see the header)");
     extern __shared__ __align__(1024) unsigned char tsm[];
     unsigned char* slots = tsm;                                                       // [NSLOT][N][RS], swizzled
     double2* TWS = reinterpret_cast<double2*>(tsm + (size_t)NSLOT * SLOT_B);          // [RT][T]  exp(-2 pi i kr t / n)
     double2* WNS = TWS + N;                                                           // [N]      (ik)^order / n
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(WNS + N);        // [NSLOT]
-    int* poison = reinterpret_cast<int*>(full + NSLOT);                               // [NG][2]: flag of a group's even / odd tiles
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(WNS + N);        // [NSLOT][2]
+    int* poison = reinterpret_cast<int*>(full + 2 * NSLOT);                               // [NG][2]: flag of a group's even / odd tiles
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tr = lane / T, t = lane - tr * T;
     const int grp = warp / WPT, wg = warp - grp * WPT;   // group, warp within the group
@@ -72,7 +76,7 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         TWS[e] = tw[(e / T) * (e % T)];
         WNS[e] = Wn[e];
     }
-    if (threadIdx.x < NSLOT) pf_mbar_init(full + threadIdx.x, 1);
+    if (threadIdx.x < 2 * NSLOT) pf_mbar_init(full + threadIdx.x, 1);
     if (threadIdx.x < 2 * NG) poison[threadIdx.x] = 0;
     if ((pf_smem_u32(tsm) & 1023u) != 0) __trap();     // the swizzle formula below assumes 1 KB-aligned slots
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -84,7 +88,7 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         const int o = (int)(id / tiles_per_outer);
         const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
         const int sl = (int)(s % NSLOT);
-        unsigned long long* bar = full + sl;
+        unsigned long long* bar = full + 2 * sl + (int)((s / NSLOT) & 1);
         pf_mbar_expect_tx(bar, (unsigned)SLOT_B);
 #pragma unroll
         for (int b = 0; b < N / BR; ++b)
@@ -96,7 +100,7 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
 
     // byte offset of row e of this lane's pair column inside a slot (hardware swizzle: 16-byte chunk ^= row bits)
     auto col = [&](int e) -> unsigned {
-        const int sw = RS == 128 ? (e & 7) : ((e >> 1) & 3);
+        const int sw = RS == 128 ? (e & 7) : RS == 64 ? ((e >> 1) & 3) : ((e >> 2) & 1);
         return (unsigned)e * RS + (unsigned)((cp ^ sw) << 4);
     };
 
@@ -107,7 +111,7 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         int* myflag = poison + 2 * grp + par;
         const int sl = (int)(s % NSLOT);
         unsigned char* slot = slots + (size_t)sl * SLOT_B;
-        pf_mbar_wait(full + sl, (unsigned)((s / NSLOT) & 1));
+        pf_mbar_wait(full + 2 * sl + (int)((s / NSLOT) & 1), (unsigned)((s / (2 * NSLOT)) & 1));
         double2 x[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) x[r] = *reinterpret_cast<const double2*>(slot + col(r * R2 + t));
@@ -228,7 +232,8 @@ int ft_make_tmap(CUtensorMap* tm, const double* base, i64 outer, i64 n, i64 inne
     const cuuint32_t box[3] = {(cuuint32_t)cols, (cuuint32_t)rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = e(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, cols * 8 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         cols * 8 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : cols * 8 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         ng_set_error("cuTensorMapEncodeTiled (fft tile) failed with CUresult %d", (int)r);
@@ -250,12 +255,13 @@ int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& 
     int rc = ft_make_tmap(&tmi, in, p->outer, N, p->inner, C, BR);
     if (!rc) rc = ft_make_tmap(&tmo, out, p->outer, N, p->inner, C, BR);
     if (rc) return rc;
-    const size_t smem = (size_t)NSLOT * N * C * 8 + (size_t)2 * N * 16 + NSLOT * 8 + NG * 8 + 16;
+    const size_t smem = (size_t)NSLOT * N * C * 8 + (size_t)2 * N * 16 + 2 * NSLOT * 8 + NG * 8 + 16;
     NG_FUNC_SMEM(smem, fft_tile_kernel<RT, R2, C, NSLOT, MINB>);
     i64 g = (ntiles + NG - 1) / NG;                      // at least one tile per group
     if (g > (i64)148 * MINB) g = (i64)148 * MINB;
     fft_tile_kernel<RT, R2, C, NSLOT, MINB><<<(unsigned)g, 256, smem, st>>>(
-        in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, ntiles, (int)tpo, p->inner, p->axis, tmi, tmo, F);
+        in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, ntiles, (int)tpo, p->inner, p->axis,
+        tmi, tmo, F);
     NG_TRACE("fft_tile");
     NG_LAUNCH_CHECK();
     return NG_OK;

@@ -25,8 +25,10 @@ def timed(fn, steps=10, warm=3):
     return statistics.median(ts)
 
 
-for shape in ((256, 256, 256), (512, 1024, 512), (128, 256, 128)):
-    for axis in range(3):
+SHAPES = {(256, 256, 256): (0, 1, 2), (512, 1024, 512): (0, 1, 2), (128, 256, 128): (0, 1, 2),
+          (1024, 256, 1024): (1,), (2048, 128, 1024): (1,), (4096, 64, 1024): (1,)}
+for shape, which in SHAPES.items():
+    for axis in which:
         axes = [ng.create_axis(A.EQUIDISTANT_PERIODIC if a == axis else A.EQUIDISTANT, n, 0.0, 2 * np.pi if a == axis else 1.0)
                 for a, n in enumerate(shape)]
         g = ng.Grid(*axes)
