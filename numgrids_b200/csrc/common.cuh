@@ -104,6 +104,12 @@ struct CoefDev {
 
 struct FuseDev {
     CoefDev pre, post, div;
+    // Double apply (internal, not part of ng_fuse): out = tail(D(mid * D(pre * in))) in ONE launch -- the
+    // D_i((J/h_i^2) D_i f) term of the curvilinear Laplacian with the inner array never leaving the SM.
+    // Honoured by the register FFT kernels only (ng_fft_twice_supported, fft2.cu); same arithmetic in the
+    // same order as the two launches it replaces (pencil pairs poisoned by a non-finite value are redone by the slow
+    // routine in both cases, but then for both transforms: agreement to rounding there).
+    CoefDev mid;
     const double* minuend;
     const double* addend;
     int add_zero;
@@ -185,6 +191,7 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
                   cudaStream_t st);
 int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                        cudaStream_t st, bool* handled);
+bool ng_fft_twice_supported(const ng_plan* p);
 int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                            cudaStream_t st, bool* handled);
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,

@@ -5,6 +5,7 @@
 //   laplacian : for i: work = (J/h_i^2) * D_i f            [post]
 //                      out  = (0.0 | out) + D_i work        [add_zero | addend]
 //               last axis also: out / J, isfinite select    [divisor, finite]
+//               (periodic axes: both applies in ONE launch, `work` stays in registers [mid])
 //   divergence: for i: out = (0.0 | out) + D_i((J/h_i) * v_i)   [pre, add_zero | addend], last: /J, finite
 //   gradient  : out_i = finite((1/h_i) * D_i f)
 //   curl      : out_i = D_j(h_k v_k);  out_i = finite(1/(h_j h_k) * (out_i - D_k(h_j v_j)))
@@ -144,13 +145,20 @@ int ng_curv_laplacian(ng_plan* p, const double* d_f, double* d_out, void* stream
     if (rc) return rc;
     for (int i = 0; i < p->ndim; ++i) {
         const ng_plan* D = p->axis_plans[i];
+        FuseDev F2 = base_fuse(D);
+        if (i == 0) F2.add_zero = 1; else F2.addend = d_out;
+        if (i == p->ndim - 1) { F2.div = to_dev(p->cJ); F2.finite = 1; }
+        if (ng_fft_twice_supported(D)) {
+            // periodic axis: D_i, the multiply and D_i again in one launch -- the pencil pair stays in registers
+            F2.mid = to_dev(p->cLap[i]);
+            rc = ng_apply_any(D, d_f, d_out, F2, st);
+            if (rc) return rc;
+            continue;
+        }
         FuseDev F1 = base_fuse(D);
         F1.post = to_dev(p->cLap[i]);
         rc = ng_apply_any(D, d_f, p->d_work, F1, st);
         if (rc) return rc;
-        FuseDev F2 = base_fuse(D);
-        if (i == 0) F2.add_zero = 1; else F2.addend = d_out;
-        if (i == p->ndim - 1) { F2.div = to_dev(p->cJ); F2.finite = 1; }
         rc = ng_apply_any(D, p->d_work, d_out, F2, st);
         if (rc) return rc;
     }

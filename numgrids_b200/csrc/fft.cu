@@ -133,12 +133,16 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
 int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                   cudaStream_t st) {
     if (p->size == 0) return NG_OK;
-    if (!p->fft_pow2) return ng_dense_launch(p, in, out, F, st);
+    if (!p->fft_pow2) {
+        NG_REQUIRE(!F.mid.ptr, "double apply requested from a kernel that does not implement it (ng_fft_twice_supported)");
+        return ng_dense_launch(p, in, out, F, st);
+    }
     {   // contiguous axis, 64 <= n <= 1024: two-pass register kernel (fft2.cu)
         bool handled = false;
         const int rc = ng_fft2_try_launch(p, in, out, F, st, &handled);
         if (rc != NG_OK || handled) return rc;
     }
+    NG_REQUIRE(!F.mid.ptr, "double apply requested from a kernel that does not implement it (ng_fft_twice_supported)");
     const int n = p->fft_len;                            // transform length (== p->n unless the plan is zero-padded)
     const i64 npencil = p->outer * p->inner;
     // pencil pairs per CTA: enough butterflies for 256 threads, bounded by shared memory

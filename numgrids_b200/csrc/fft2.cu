@@ -73,12 +73,18 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
                     if (vb) b = in[bb + idx * step];
                 }
             }
-            if (pre) {                               // (an absent pencil must stay exactly zero)
-                if (va) a = __dmul_rn(ca.at(r), a);
-                if (vb) b = __dmul_rn(cb.at(r), b);
-            }
             x[r] = make_double2(a, b);
         }
+        if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb);
+    }
+    // double apply (FuseDev::mid): the transform runs twice with the pointwise multiply between, the pair stays
+    // in registers; a run-time loop, so the unrolled body exists once
+    const int nrep = (FUSED && F.mid.ptr) ? 2 : 1;
+#pragma unroll 1
+    for (int rep = 0; rep < nrep; ++rep) {
+    if (FUSED && rep == 1) {
+        const PencilCoef ma = pencil_coef(F, F.mid, ba, ax, t, R2), mb = pencil_coef(F, F.mid, bb, ax, t, R2);
+        pencil_mul_all<RT>(x, ma, mb, va, vb);
     }
     dif_forward<RT>(x);
 #pragma unroll
@@ -123,6 +129,8 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         x[q] = v;
     }
     dit_inverse<RT>(x);
+    __syncwarp();                                  // the exchange buffer is rewritten by the second transform
+    }
     if (__any_sync(0xffffffffu, ng_nonfinite(x[0].x) || ng_nonfinite(x[0].y))) {   // poisoned pair: redo
         __syncwarp();
         const i64 p0 = ((i64)blockIdx.x * (blockDim.x >> 5) + warp) * TPW * 2;
@@ -132,16 +140,16 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
                                        fsm + (size_t)(warp * TPW + (q >> 1)) * UNITS, Wn, tw, F, NV);
         return;
     }
-    PencilTail ta, tb;
-    if (FUSED) { ta.init(F, ba, step, ax, t, R2); tb.init(F, bb, step, ax, t, R2); }
+    if (FUSED) {
+        PencilTail ta, tb;
+        ta.init(F, ba, step, ax, t, R2);
+        tb.init(F, bb, step, ax, t, R2);
+        pencil_tail_all<RT>(F, ta, tb, x);
+    }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         const int idx = r * R2 + t;
-        double a = x[r].x, b = x[r].y;
-        if (FUSED) {
-            if (va) a = ta.apply(F, a, r, R2);
-            if (vb) b = tb.apply(F, b, r, R2);
-        }
+        const double a = x[r].x, b = x[r].y;
         if (PAD && idx >= NV) continue;
         if (STR && pair16) {
             if (va) *reinterpret_cast<double2*>(out + ba + idx * step) = make_double2(a, b);
@@ -221,17 +229,21 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
-            double a = va ? raw[idx] : 0.0, b = vb ? raw[N + idx] : 0.0;
-            if (pre) {                               // (an absent pencil must stay exactly zero)
-                if (va) a = __dmul_rn(ca.at(r), a);
-                if (vb) b = __dmul_rn(cb.at(r), b);
-            }
-            x[r] = make_double2(a, b);
+            x[r] = make_double2(va ? raw[idx] : 0.0, vb ? raw[N + idx] : 0.0);
         }
+        if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb);
         __syncwarp();                              // the stage is drained
         if (lane == 0 && jl + NSTAGE < njl) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(jl + NSTAGE);                    // refill it for the partner warp
+        }
+        const int nrep = (FUSED && F.mid.ptr) ? 2 : 1;     // double apply (FuseDev::mid), see fft2pass_kernel
+#pragma unroll 1
+        for (int rep = 0; rep < nrep; ++rep) {
+        if (FUSED && rep == 1) {
+            const PencilCoef ma = pencil_coef(F, F.mid, va ? pa * N : 0, F.vec_axis, t, R2),
+                             mb = pencil_coef(F, F.mid, vb ? pb * N : 0, F.vec_axis, t, R2);
+            pencil_mul_all<RT>(x, ma, mb, va, vb);
         }
         dif_forward<RT>(x);
 #pragma unroll
@@ -275,7 +287,8 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             x[q] = v;
         }
         dit_inverse<RT>(x);
-        __syncwarp();                              // the exchange buffer is rewritten by the next unit
+        __syncwarp();                              // the exchange buffer is rewritten by the next unit / transform
+        }
         if (__any_sync(0xffffffffu, ng_nonfinite(x[0].x) || ng_nonfinite(x[0].y))) {   // poisoned pair: redo
             const i64 p0 = (jl * gridDim.x + blockIdx.x) * PPU;
             for (int q = 0; q < PPU; ++q)
@@ -285,20 +298,19 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
                                            Wn, tw, F, N);
             continue;
         }
-        PencilTail ta, tb;
-        if (FUSED) { ta.init(F, va ? pa * N : 0, 1, F.vec_axis, t, R2); tb.init(F, vb ? pb * N : 0, 1, F.vec_axis, t, R2); }
+        if (FUSED) {
+            PencilTail ta, tb;
+            ta.init(F, va ? pa * N : 0, 1, F.vec_axis, t, R2);
+            tb.init(F, vb ? pb * N : 0, 1, F.vec_axis, t, R2);
+            pencil_tail_all<RT>(F, ta, tb, x);
+        }
         double* const oa = out + pa * N;
         double* const ob = oa + N;
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
-            double a = x[r].x, b = x[r].y;
-            if (FUSED) {
-                if (va) a = ta.apply(F, a, r, R2);
-                if (vb) b = tb.apply(F, b, r, R2);
-            }
-            if (va) oa[idx] = a;
-            if (vb) ob[idx] = b;
+            if (va) oa[idx] = x[r].x;
+            if (vb) ob[idx] = x[r].y;
         }
     }
 }
@@ -372,6 +384,14 @@ int launch_padded(const ng_plan* p, const double* in, double* out, const FuseDev
 }
 
 }  // namespace
+
+// A fused apply with FuseDev::mid (double apply) is honoured exactly when ng_fft2_try_launch takes the plan.
+bool ng_fft_twice_supported(const ng_plan* p) {
+    if (p->kind != PK_FFT || !p->fft_pow2 || !p->d_Wn || !p->d_twn || p->fft_len != p->n) return false;
+    if (NG_ENV_INT("NG_FFT_TWOPASS", 1) == 0 || NG_ENV_INT("NG_FFT_TWICE", 1) == 0) return false;
+    if (p->inner != 1 && NG_ENV_INT("NG_FFT_STRIDED", 1) == 0) return false;
+    return p->n == 64 || p->n == 128 || p->n == 256 || p->n == 512 || p->n == 1024;
+}
 
 // Returns NG_OK and sets *handled when this kernel family covers the plan.
 int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,

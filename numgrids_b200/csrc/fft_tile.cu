@@ -7,14 +7,16 @@
 // HBM, sets the pace (0.27-0.31 of the copy peak, profiles/r01_tune_fft.txt).  Here no lane ever
 // loads from or stores to global memory:
 //   * a tile = all n rows of C = 8 or 16 adjacent columns (64 / 128 contiguous bytes per row) is
-//     brought in by TMA (cp.async.bulk.tensor, 256-row boxes) into a hardware-swizzled slot;
+//     brought in by TMA (cp.async.bulk.tensor) into a hardware-swizzled slot;
 //   * a warp owns the column PAIRS of its transforms: the 16-byte chunk c of every row.  The swizzle
 //     (chunk index XOR row bits) makes a quarter-warp's 8 consecutive rows hit 8 distinct 16-byte bank
 //     groups, so the column loads are conflict-free;
 //   * the pair's n x 16 B column is also its exchange buffer between the two register passes (same
 //     XOR-by-row trick as fft2.cu's ring kernel, mapped into the column) and finally receives the
 //     derivative in the input's own positions;
-//   * the finished tile leaves by ONE TMA store per 256 rows (full 64 / 128-byte row segments).
+//   * the finished tile leaves by TMA stores (full 64 / 128-byte row segments): every warp of the
+//     group stores its own quarter / half of the rows and refills it with the same rows of the slot's
+//     next tile as soon as its store has read them, so no single warp carries the whole drain.
 // A CTA runs 8 warps as NG groups of WPT warps (one tile per group at a time) over NSLOT slots: tile s
 // of the CTA sits in slot s % NSLOT, is worked by group s % NG, and the group's leader refills the
 // slot with tile s + NSLOT once the store has drained it.  Consecutive uses of a slot belong to
@@ -55,8 +57,8 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
     constexpr int RS = C * 8;                            // bytes per tile row
     constexpr int WPT = C / (2 * TPW);                   // warps per tile
     constexpr int NG = NW / WPT;                         // groups per CTA
-    constexpr int BR = N < 256 ? N : 256;                // rows per TMA box
-    constexpr int SLOT_B = N * RS;
+    constexpr int BR = N / WPT;                          // rows per TMA box: every warp of a group moves its own
+    constexpr int SLOT_B = N * RS, BOX_B = BR * RS;      // row range of the tile, in and out
     static_assert(RS == 32 || RS == 64 || RS == 128, "tile rows are one swizzle span");
     static_assert(WPT >= 1 && NW % WPT == 0, "groups tile the CTA");
     static_assert((2 * NSLOT) % NG == 0, "every other use of a slot belongs to the same group (see the header)");
@@ -76,27 +78,25 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         TWS[e] = tw[(e / T) * (e % T)];
         WNS[e] = Wn[e];
     }
-    if (threadIdx.x < 2 * NSLOT) pf_mbar_init(full + threadIdx.x, 1);
+    if (threadIdx.x < 2 * NSLOT) pf_mbar_init(full + threadIdx.x, WPT);
     if (threadIdx.x < 2 * NG) poison[threadIdx.x] = 0;
     if ((pf_smem_u32(tsm) & 1023u) != 0) __trap();     // the swizzle formula below assumes 1 KB-aligned slots
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     const i64 nmine = (ntiles - (i64)blockIdx.x + gridDim.x - 1) / gridDim.x;         // tiles of this CTA
-    auto issue = [&](i64 s) {                            // one lane: tile s of this CTA -> slot s % NSLOT
+    auto issue = [&](i64 s, int b) {                     // one lane: row box b of tile s of this CTA -> slot s % NSLOT
         const i64 id = s * gridDim.x + blockIdx.x;
         const int o = (int)(id / tiles_per_outer);
         const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
         const int sl = (int)(s % NSLOT);
         unsigned long long* bar = full + 2 * sl + (int)((s / NSLOT) & 1);
-        pf_mbar_expect_tx(bar, (unsigned)SLOT_B);
-#pragma unroll
-        for (int b = 0; b < N / BR; ++b)
-            ft_tma_load_3d(pf_smem_u32(slots + (size_t)sl * SLOT_B + (size_t)b * BR * RS), &tm_in, c0, b * BR, o,
-                           pf_smem_u32(bar));
+        pf_mbar_expect_tx(bar, (unsigned)BOX_B);
+        ft_tma_load_3d(pf_smem_u32(slots + (size_t)sl * SLOT_B + (size_t)b * BOX_B), &tm_in, c0, b * BR, o, pf_smem_u32(bar));
     };
     if (threadIdx.x == 0)
-        for (int s = 0; s < NSLOT && s < nmine; ++s) issue(s);
+        for (int s = 0; s < NSLOT && s < nmine; ++s)
+            for (int b = 0; b < WPT; ++b) issue(s, b);
 
     // byte offset of row e of this lane's pair column inside a slot (hardware swizzle: 16-byte chunk ^= row bits)
     auto col = [&](int e) -> unsigned {
@@ -167,17 +167,15 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         const i64 id = s * gridDim.x + blockIdx.x;
         const int o = (int)(id / tiles_per_outer);
         const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
-        if (leader) {
-#pragma unroll
-            for (int b = 0; b < N / BR; ++b)
-                ft_tma_store_3d(&tm_out, c0, b * BR, o, pf_smem_u32(slot + (size_t)b * BR * RS));
+        if (lane == 0) {                           // every warp stores (and below refills) its own rows of the tile
+            ft_tma_store_3d(&tm_out, c0, wg * BR, o, pf_smem_u32(slot + (size_t)wg * BOX_B));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (*reinterpret_cast<volatile int*>(myflag)) {
             // Rare: a non-finite sample poisoned a pair (see fft_slow_pencil).  Once the tile's store has landed, the
             // pencils of the poisoned warps are redone one at a time straight from / to global memory; the drained
             // slot is the scratch space.
-            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             ft_group_bar(1 + grp, 32 * WPT);
             if (bad) {
                 for (int q = 0; q < 2 * TPW; ++q) {
@@ -193,12 +191,12 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             ft_group_bar(1 + grp, 32 * WPT);
         }
-        if (leader) {
+        if (lane == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (s + NSLOT < nmine) issue(s + NSLOT);
+            if (s + NSLOT < nmine) issue(s + NSLOT, wg);
         }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 typedef CUresult (*ft_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -247,8 +245,8 @@ int ft_make_tmap(CUtensorMap* tm, const double* base, i64 outer, i64 n, i64 inne
 
 template <int RT, int R2, int C, int NSLOT, int MINB>
 int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
-    constexpr int N = RT * R2, BR = N < 256 ? N : 256;
-    constexpr int NG = 8 / (C / (2 * (32 / R2)));
+    constexpr int N = RT * R2, WPT = C / (2 * (32 / R2)), NG = 8 / WPT, BR = N / WPT;
+    static_assert(BR <= 256, "TMA box extent");
     const i64 tpo = (p->inner + C - 1) / C;
     const i64 ntiles = p->outer * tpo;
     CUtensorMap tmi, tmo;

@@ -28,3 +28,49 @@ def test_fused_laplacian_kernels_equal_the_simple_kernel(gpu_ready):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_fdlap.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "bad 0" in r.stdout
+
+
+@pytest.mark.parametrize("kind", ["spherical", "spherical_singular", "cylindrical", "polar"])
+def test_laplacian_double_apply_equals_two_launches(gpu_ready, kind):
+    """Periodic axes of the curvilinear Laplacian run D, the (J/h^2) multiply and D again in ONE launch (FuseDev::mid,
+    csrc/fft2.cu); NG_FFT_TWICE=0 restores the two launches through the workspace array.  Same arithmetic in the same
+    order, so the results must agree bit for bit.  On a grid whose coefficient table is non-finite on an axis (theta = 0:
+    the reference's inf / nan rows before its isfinite select, numgrids/curvilinear.py:236-244) the partner pencil of a
+    poisoned pair is redone by the warp-cooperative radix-2 routine -- twice in one launch, once with two launches --
+    so there the agreement is to rounding (<= 1e-13 of the result's L-inf norm; the path's tolerance is 1e-11)."""
+    import numpy as np
+    import torch
+    import numgrids_b200 as ng
+    from numgrids_b200 import _lib
+    A = ng.AxisType
+    if kind.startswith("spherical"):
+        th0 = 0.0 if kind.endswith("singular") else 0.3
+        g = ng.SphericalGrid(ng.create_axis(A.CHEBYSHEV, 20, 0.5, 2.0), ng.create_axis(A.CHEBYSHEV, 18, th0, np.pi - th0),
+                             ng.create_axis(A.EQUIDISTANT_PERIODIC, 256, 0, 2 * np.pi))
+    elif kind == "cylindrical":           # phi in the middle: strided pencils
+        g = ng.CylindricalGrid(ng.create_axis(A.CHEBYSHEV, 16, 0.2, 2.0), ng.create_axis(A.EQUIDISTANT_PERIODIC, 128, 0, 2 * np.pi),
+                               ng.create_axis(A.EQUIDISTANT, 22, 0.0, 1.0))
+    else:
+        g = ng.PolarGrid(ng.create_axis(A.CHEBYSHEV, 40, 0.0, 2.0), ng.create_axis(A.EQUIDISTANT_PERIODIC, 64, 0, 2 * np.pi))
+    M = g.meshed_coords
+    f = np.sin(M[0]) * np.cos(2 * M[1]) + (M[-1] if len(M) == 3 else M[0]) ** 2
+    f[(3,) * f.ndim] = np.inf
+    fd = torch.from_numpy(f).cuda()
+    lib = _lib.load()
+    outs = {}
+    try:
+        for mode in ("1", "0"):
+            os.environ["NG_FFT_TWICE"] = mode
+            lib.ng_tuning_reload()
+            n0 = _lib.launch_count()
+            outs[mode] = g.laplacian(fd).cpu().numpy()
+            outs[mode + "n"] = _lib.launch_count() - n0
+    finally:
+        os.environ.pop("NG_FFT_TWICE", None)
+        lib.ng_tuning_reload()
+    assert outs["1n"] == outs["0n"] - 1, (outs["1n"], outs["0n"])
+    assert np.all(np.isfinite(outs["1"])) and np.all(np.isfinite(outs["0"]))
+    if kind.endswith("singular"):
+        assert float(np.max(np.abs(outs["1"] - outs["0"]))) <= 1e-13 * float(np.max(np.abs(outs["0"])))
+    else:
+        assert np.array_equal(outs["1"], outs["0"])

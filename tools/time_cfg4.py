@@ -1,4 +1,4 @@
-"""cfg4 (SphericalGrid 128x128x256) composite timings on device tensors, sweeping NG_DENSE_STAGGER_NS."""
+"""cfg4 (SphericalGrid 128x128x256): per-axis Diff and composite timings on device tensors (L2 flushed between calls)."""
 import os
 import sys
 import statistics
@@ -36,17 +36,14 @@ def timed(fn, steps=15, warm=3):
     return statistics.median(ts)
 
 
-ref = None
-for ns in sys.argv[1:] or ["0", "4000", "8000", "12000", "16000"]:
-    os.environ["NG_DENSE_STAGGER_NS"] = ns
-    a0 = timed(lambda: d0.apply_ptr(f.data_ptr(), o.data_ptr()))
-    a1 = timed(lambda: d1.apply_ptr(f.data_ptr(), o.data_ptr()))
-    lap = timed(lambda: g.laplacian(f))
-    grad = timed(lambda: g.gradient(f))
-    div = timed(lambda: g.divergence(f, f, f))
-    curl = timed(lambda: g.curl(f, f, f))
-    out = g.laplacian(f)
-    if ref is None:
-        ref = out.clone()
-    print(f"stagger={ns:>6s} ns: Diff axis0 {a0 * 1e3:.1f} us  axis1 {a1 * 1e3:.1f} us  laplacian {lap:.3f} ms  gradient {grad:.3f}  "
-          f"divergence {div:.3f}  curl {curl:.3f}  bit-equal={torch.equal(out, ref)}", flush=True)
+d2 = ng.Diff(g, 1, 2).operator.operator
+a0 = timed(lambda: d0.apply_ptr(f.data_ptr(), o.data_ptr()))
+a1 = timed(lambda: d1.apply_ptr(f.data_ptr(), o.data_ptr()))
+a2 = timed(lambda: d2.apply_ptr(f.data_ptr(), o.data_ptr()))
+lap = timed(lambda: g.laplacian(f))
+grad = timed(lambda: g.gradient(f))
+div = timed(lambda: g.divergence(f, f, f))
+curl = timed(lambda: g.curl(f, f, f))
+tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("NG_"))
+print(f"[{tag}] Diff axis0 {a0 * 1e3:.1f} us  axis1 {a1 * 1e3:.1f} us  axis2 {a2 * 1e3:.1f} us  laplacian {lap:.3f} ms  "
+      f"gradient {grad:.3f}  divergence {div:.3f}  curl {curl:.3f}", flush=True)
