@@ -334,6 +334,11 @@ def time_events(torch, fn, steps, warmup):
     return ts
 
 
+def _lib_last_kernel():
+    from numgrids_b200 import _lib
+    return _lib.last_kernel()
+
+
 def per_config_extras(torch, ng, peak_gbs, quick):
     """cfg1-cfg4 at N=1: device-resident timings (median over a few launches)."""
     A = ng.AxisType
@@ -444,9 +449,9 @@ def per_config_extras(torch, ng, peak_gbs, quick):
 
     try:
         # cfg5 in the reference's second idiom: CurvilinearGrid(..., scale_factors = ones).laplacian(f)
-        # = sum_i D_i(D_i f) with first-derivative stencils: six streaming FD applies with fused elementwise
-        # work (no fused single-pass kernel for this form), at 512^3 because the reference API evaluates the
-        # scale factors on the full meshgrid (24 GiB of host arrays at 1024^3)
+        # = sum_i D_i(D_i f) with first-derivative stencils: the single-pass kernel (csrc/curvlap3d.cu; `inner`
+        # never leaves the SM), at 512^3 because the reference API evaluates the scale factors on the full
+        # meshgrid (24 GiB of host arrays at 1024^3)
         nii = 128 if quick else 512
         ax = ng.create_axis(A.EQUIDISTANT, nii, 0.0, 1.0)
         one = lambda c: np.ones_like(c[0])
@@ -454,7 +459,7 @@ def per_config_extras(torch, ng, peak_gbs, quick):
         f = torch.rand(nii, nii, nii, dtype=torch.float64, device=dev)
         ms = timed(lambda: gc.laplacian(f), 5, 2, nii < 512)
         out[f"cfg5_idiom_ii_unit_curvilinear_laplacian_{nii}cubed"] = {
-            "gpts": nii ** 3 / ms / 1e6, "ms": ms, "passes": 6,
+            "gpts": nii ** 3 / ms / 1e6, "ms": ms, "passes": 1, "kernel": _lib_last_kernel(),
             "hbm_frac_algorithmic_16B": 16 * nii ** 3 / ms / 1e6 / peak_gbs}
         del f, gc
     except Exception as e:  # pragma: no cover
@@ -496,6 +501,27 @@ def per_config_extras(torch, ng, peak_gbs, quick):
         del f, o
     except Exception as e:  # pragma: no cover
         out["cfg3_fft"] = {"error": repr(e)}
+
+    try:
+        # the same operator along an axis that is NOT the contiguous one (cylindrical phi in the middle, doubly
+        # periodic boxes): TMA tile kernel (csrc/fft_tile.cu)
+        b = 128 if quick else 512
+        res = {}
+        for shape, axis in (((b, 1024, b), 1), ((2 * b, 256, 2 * b), 1)):
+            axes = [ng.create_axis(A.EQUIDISTANT_PERIODIC if a == axis else A.EQUIDISTANT, m, 0.0,
+                                   2 * np.pi if a == axis else 1.0) for a, m in enumerate(shape)]
+            g = ng.Grid(*axes)
+            f = torch.randn(*shape, dtype=torch.float64, device=dev)
+            o = torch.empty_like(f)
+            op = ng.Diff(g, 1, axis).operator.operator
+            ms = timed(lambda: op.apply_ptr(f.data_ptr(), o.data_ptr()), 10, 3, b < 512)
+            pts = int(np.prod(shape))
+            res["x".join(map(str, shape)) + f"_axis{axis}"] = {"gpts": pts / ms / 1e6, "ms": ms,
+                                                               "hbm_frac": 16 * pts / ms / 1e6 / peak_gbs}
+            del f, o
+        out["fft_strided_axis_order1"] = res
+    except Exception as e:  # pragma: no cover
+        out["fft_strided_axis"] = {"error": repr(e)}
 
     try:
         # cfg4: SphericalGrid(Cheb 128, Cheb 128, periodic 256): laplacian / gradient / divergence

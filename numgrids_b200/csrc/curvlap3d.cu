@@ -532,10 +532,13 @@ int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStrea
         NG_CUDA_OK(cudaMemcpyAsync(p->d_curvlap, &hp, sizeof(ClParams), cudaMemcpyHostToDevice, st));
     }
     int rc;
-    switch ((int)NG_ENV_INT("NG_CURV_CFG", 0)) {    // tuning: tile rows / ring depth (profiles/r02_tune_curvlap.txt)
+    // tuning: tile rows / ring depth.  Two rows per warp recompute more of the y inner derivative ((R+4)/R rows per own
+    // row) but put four warps on every scheduler instead of two, and the kernel is latency-bound (dependent FP64 chains):
+    // 512^3 unit scale 1.45 ms against 1.64 ms (profiles/r02_tune_curvlap.txt)
+    switch ((int)NG_ENV_INT("NG_CURV_CFG", 2)) {
+        case 0: rc = cl_launch<4, 4, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, two CTAs of 4 warps per SM
         case 1: rc = cl_launch<4, 8, 9>(p, in, out, hp, gen, st); break;      // 32 x 64 tiles, one CTA of 8 warps per SM
-        case 2: rc = cl_launch<2, 8, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, 2 rows per warp: two CTAs of 8 warps
-        default: rc = cl_launch<4, 4, 8>(p, in, out, hp, gen, st); break;     // 16 x 64 tiles, two CTAs of 4 warps per SM
+        default: rc = cl_launch<2, 8, 8>(p, in, out, hp, gen, st); break;     // 16 x 64 tiles, 2 rows per warp: two CTAs of 8 warps
     }
     if (rc) return rc;
     *handled = true;
