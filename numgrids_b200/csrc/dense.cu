@@ -163,12 +163,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // k panels past n are zero-filled (0 * 0 adds +-0 to a sum that started at +0.0: the bits do not change),
 // column tiles are cut per outer index with their tail columns zero-filled, rows / columns past the array
 // are not stored and row groups of 32 past n are not computed.  !GEN is the exact-shape kernel unchanged.
-template <bool DESC, bool FMA, bool FUSED, int NCP, bool LASTAX, bool GEN>
-__global__ void __launch_bounds__(256, NCP == 4 ? 1 : NG_DENSE_MINB)
+// THR = threads per CTA: 256 (16 threads across the columns), or 128 (8 across: with NCP = 2 the same 128 x 32 tile
+// as <NCP = 1, 256> but 8 x 4 outputs per thread -- 6 LDS.128 per 64 FP64 instructions instead of 5 per 32).
+template <bool DESC, bool FMA, bool FUSED, int NCP, bool LASTAX, bool GEN, int THR = 256>
+__global__ void __launch_bounds__(THR, NCP == 4 ? 1 : (THR == 128 ? 3 : NG_DENSE_MINB))
 dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
                   const double* __restrict__ Mt, int n, i64 inner, int axis, FuseDev F,
                   int npitch, i64 npencil_last, int tiles_per_o) {
-    constexpr int TFN = 32 * NCP, HALF = TFN / 2;
+    constexpr int TXN = THR / 16, CS = 2 * TXN;       // threads across the columns, column stride between a thread's pairs
+    constexpr int TFN = CS * NCP, HALF = TFN / 2;
+    constexpr int MQ = 4 * FKS * (256 / THR);         // 16-byte M-panel chunks per thread
     // LASTAX stages F by 8-byte copies with consecutive threads walking k: rows one pitch apart.  A
     // pitch of TFN doubles puts all 16 k of a column in one bank (16-way conflict on every copy);
     // two doubles of padding spread them over 8 banks and keep rows 16-byte aligned for the LDS.128.
@@ -192,7 +196,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     const int jmax = GEN ? ((n - row0 + 31) / 32 < 4 ? (n - row0 + 31) / 32 : 4) : 4;   // 32-row groups with rows < n
     // element (k, c): fbase + k*inner + c;  LASTAX: pencil r = col0 + c, element (k, c) at fbase + c*n + k
     const double* fbase = LASTAX ? in + col0 * (i64)n : in + o * (i64)n * inner + c0;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
 
     double acc[8][2 * NCP];
 #pragma unroll
@@ -216,8 +220,8 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         if (FUSED && !LASTAX && F.pre.ptr) {
 #pragma unroll
             for (int q = 0; q < NCP * FKS; ++q) {
-                const int kk = (tid + q * 256) / HALF;
-                if (GEN && (k0 + kk >= n || ((tid + q * 256) % HALF) * 2 >= ncv)) {   // zero-filled chunk
+                const int kk = (tid + q * THR) / HALF;
+                if (GEN && (k0 + kk >= n || ((tid + q * THR) % HALF) * 2 >= ncv)) {   // zero-filled chunk
                     pcn[2 * q] = pcn[2 * q + 1] = 0.0;
                     continue;
                 }
@@ -230,8 +234,8 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         }
         // M panel: 16 x 128 doubles = 1024 16-byte chunks (4 per thread); F panel: 16 x TFN (NCP per thread)
 #pragma unroll
-        for (int q = 0; q < 4 * FKS; ++q) {
-            const int e = tid + q * 256;
+        for (int q = 0; q < MQ; ++q) {
+            const int e = tid + q * THR;
             const int kk = e >> 6, ch = (e & 63) * 2;
             cp_async16(&Ms[buf][kk][ch], Mt + (i64)(k0 + kk) * npitch + row0 + ch);
         }
@@ -239,7 +243,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             // 16 x TFN doubles as 8-byte copies: consecutive threads walk k (128 B contiguous per pencil)
 #pragma unroll
             for (int q = 0; q < 2 * NCP * FKS; ++q) {
-                const int e = tid + q * 256;
+                const int e = tid + q * THR;
                 const int kk = e % FK, c = e / FK;
                 if (GEN) {
                     const bool ok = k0 + kk < n && c < ncv;
@@ -251,7 +255,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         } else {
 #pragma unroll
             for (int q = 0; q < NCP * FKS; ++q) {
-                const int e = tid + q * 256;
+                const int e = tid + q * THR;
                 const int kk = e / HALF, ch = (e % HALF) * 2;
                 if (GEN) {
                     const bool ok = k0 + kk < n && ch < ncv;
@@ -286,7 +290,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             if (LASTAX) {
 #pragma unroll
                 for (int q = 0; q < 2 * NCP * FKS; ++q) {
-                    const int e = tid + q * 256;
+                    const int e = tid + q * THR;
                     const int kk = e % FK, c = e / FK;
                     if (GEN && (k0 + kk >= n || c >= ncv)) continue;      // zero-filled element stays zero
                     const Idx4 ix = unravel4((col0 + c) * (i64)n + k0 + kk, F.shape);
@@ -295,7 +299,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             } else {
 #pragma unroll
                 for (int q = 0; q < NCP * FKS; ++q) {
-                    const int e = tid + q * 256;
+                    const int e = tid + q * THR;
                     const int kk = e / HALF, ch = (e % HALF) * 2;
                     Fs[buf][kk][ch] = __dmul_rn(pcc[2 * q], Fs[buf][kk][ch]);
                     Fs[buf][kk][ch + 1] = __dmul_rn(pcc[2 * q + 1], Fs[buf][kk][ch + 1]);
@@ -314,7 +318,7 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
             }
 #pragma unroll
             for (int j = 0; j < NCP; ++j) {
-                const double2 bv = *reinterpret_cast<const double2*>(&Fs[buf][kk][tx * 2 + 32 * j]);
+                const double2 bv = *reinterpret_cast<const double2*>(&Fs[buf][kk][tx * 2 + CS * j]);
                 b[2 * j] = bv.x; b[2 * j + 1] = bv.y;
             }
 #pragma unroll
@@ -337,26 +341,54 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
         // out[(col0 + c)*n + i]: store (i, i+1) pairs of one pencil; one unravel per pencil
 #pragma unroll
         for (int y = 0; y < 2 * NCP; ++y) {
-            if (GEN && tx * 2 + (y & 1) + 32 * (y >> 1) >= ncv) continue;
-            const i64 r = col0 + tx * 2 + (y & 1) + 32 * (y >> 1);
+            if (GEN && tx * 2 + (y & 1) + CS * (y >> 1) >= ncv) continue;
+            const i64 r = col0 + tx * 2 + (y & 1) + CS * (y >> 1);
             i64 po = 0, dv = 0, pa = 0, da = 0;             // offsets of (pencil r, i = 0), strides along i
             if (FUSED) {
                 const Idx4 ix0 = unravel4(r * (i64)n, F.shape);
                 if (F.post.ptr) { po = coef_off(F.post, ix0); pa = F.post.s[axis]; }
                 if (F.div.ptr) { dv = coef_off(F.div, ix0); da = F.div.s[axis]; }
             }
+            // the pairs (i, i+1), i = row0 + ty*2 + 32 j: the elementwise tail as straight-line passes with the
+            // (uniform) operand tests outside the loops -- same operations per element in the same order as fuse_tail
+            double2 v[4];
+            i64 lin[4];
+            bool live[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = row0 + ty * 2 + 32 * j;
-                if (GEN && i >= n) continue;                // n is even: the pair (i, i+1) is inside or outside
-                const i64 lin = r * (i64)n + i;
-                double2 v = make_double2(acc[2 * j][y], acc[2 * j + 1][y]);
-                if (FUSED) {
-                    v.x = fuse_tail_off(F, v.x, lin, po + i * pa, dv + i * da);
-                    v.y = fuse_tail_off(F, v.y, lin + 1, po + (i + 1) * pa, dv + (i + 1) * da);
-                }
-                *reinterpret_cast<double2*>(out + lin) = v;
+                live[j] = !(GEN && i >= n);                 // n is even: the pair (i, i+1) is inside or outside
+                lin[j] = r * (i64)n + (live[j] ? i : 0);
+                v[j] = make_double2(acc[2 * j][y], acc[2 * j + 1][y]);
             }
+            if (FUSED) {
+                if (F.minuend) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const double2 m = *reinterpret_cast<const double2*>(F.minuend + lin[j]); v[j].x = __dsub_rn(m.x, v[j].x); v[j].y = __dsub_rn(m.y, v[j].y); }
+                }
+                if (F.post.ptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const i64 i = lin[j] - r * (i64)n; v[j].x = __dmul_rn(F.post.ptr[po + i * pa], v[j].x); v[j].y = __dmul_rn(F.post.ptr[po + (i + 1) * pa], v[j].y); }
+                }
+                if (F.addend) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const double2 a = *reinterpret_cast<const double2*>(F.addend + lin[j]); v[j].x = __dadd_rn(a.x, v[j].x); v[j].y = __dadd_rn(a.y, v[j].y); }
+                } else if (F.add_zero) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { v[j].x = __dadd_rn(0.0, v[j].x); v[j].y = __dadd_rn(0.0, v[j].y); }
+                }
+                if (F.div.ptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const i64 i = lin[j] - r * (i64)n; v[j].x = __ddiv_rn(v[j].x, F.div.ptr[dv + i * da]); v[j].y = __ddiv_rn(v[j].y, F.div.ptr[dv + (i + 1) * da]); }
+                }
+                if (F.finite) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { v[j].x = isfinite(v[j].x) ? v[j].x : 0.0; v[j].y = isfinite(v[j].y) ? v[j].y : 0.0; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (live[j]) *reinterpret_cast<double2*>(out + lin[j]) = v[j];
         }
         return;
     }
@@ -364,32 +396,60 @@ dense_fast_kernel(const double* __restrict__ in, double* __restrict__ out,
     // pair (the row only changes the coordinate along `axis`).
 #pragma unroll
     for (int jc = 0; jc < NCP; ++jc) {
-        if (GEN && tx * 2 + 32 * jc >= ncv) continue;                   // inner is even: whole pairs
-        const i64 lin0 = (o * n) * inner + c0 + tx * 2 + 32 * jc;       // row 0 of this column pair
+        if (GEN && tx * 2 + CS * jc >= ncv) continue;                   // inner is even: whole pairs
+        const i64 lin0 = (o * n) * inner + c0 + tx * 2 + CS * jc;       // row 0 of this column pair
         i64 po = 0, dv = 0, pa = 0, da = 0, pv = 0, dvv = 0;   // offsets of row 0, strides along i / the pair
         if (FUSED) {
             const Idx4 ix0 = unravel4(lin0, F.shape);          // (row 0: the coordinate along `axis` is 0)
             if (F.post.ptr) { po = coef_off(F.post, ix0); pa = F.post.s[axis]; pv = F.post.s[F.vec_axis]; }
             if (F.div.ptr) { dv = coef_off(F.div, ix0); da = F.div.s[axis]; dvv = F.div.s[F.vec_axis]; }
         }
+        double2 v[8];
+        i64 lin[8];
+        int ri[8];
+        bool live[8];
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
             const int i = row0 + ty * 2 + (x & 1) + 32 * (x >> 1);
-            if (GEN && i >= n) continue;
-            const i64 lin = lin0 + (i64)i * inner;
-            double2 v = make_double2(acc[x][2 * jc], acc[x][2 * jc + 1]);
-            if (FUSED) {
-                v.x = fuse_tail_off(F, v.x, lin, po + i * pa, dv + i * da);
-                v.y = fuse_tail_off(F, v.y, lin + 1, po + i * pa + pv, dv + i * da + dvv);   // the pair stays inside the innermost row
-            }
-            *reinterpret_cast<double2*>(out + lin) = v;
+            live[x] = !(GEN && i >= n);
+            ri[x] = live[x] ? i : 0;
+            lin[x] = lin0 + (i64)ri[x] * inner;
+            v[x] = make_double2(acc[x][2 * jc], acc[x][2 * jc + 1]);
         }
+        if (FUSED) {      // straight-line passes, operand tests outside the loops (see the contiguous-axis epilogue above)
+            if (F.minuend) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { const double2 m = *reinterpret_cast<const double2*>(F.minuend + lin[x]); v[x].x = __dsub_rn(m.x, v[x].x); v[x].y = __dsub_rn(m.y, v[x].y); }
+            }
+            if (F.post.ptr) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { const i64 o_ = po + ri[x] * pa; v[x].x = __dmul_rn(F.post.ptr[o_], v[x].x); v[x].y = __dmul_rn(F.post.ptr[o_ + pv], v[x].y); }
+            }
+            if (F.addend) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { const double2 a = *reinterpret_cast<const double2*>(F.addend + lin[x]); v[x].x = __dadd_rn(a.x, v[x].x); v[x].y = __dadd_rn(a.y, v[x].y); }
+            } else if (F.add_zero) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { v[x].x = __dadd_rn(0.0, v[x].x); v[x].y = __dadd_rn(0.0, v[x].y); }
+            }
+            if (F.div.ptr) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { const i64 o_ = dv + ri[x] * da; v[x].x = __ddiv_rn(v[x].x, F.div.ptr[o_]); v[x].y = __ddiv_rn(v[x].y, F.div.ptr[o_ + dvv]); }   // the pair stays inside the innermost row
+            }
+            if (F.finite) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { v[x].x = isfinite(v[x].x) ? v[x].x : 0.0; v[x].y = isfinite(v[x].y) ? v[x].y : 0.0; }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+            if (live[x]) *reinterpret_cast<double2*>(out + lin[x]) = v[x];
     }
 }
 
-template <bool DESC, bool FMA, int NCP, bool LASTAX, bool GEN = false>
+template <bool DESC, bool FMA, int NCP, bool LASTAX, bool GEN = false, int THR = 256>
 int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
-    constexpr int TFN = 32 * NCP;
+    constexpr int TFN = (THR / 8) * NCP;
     const i64 ncols = p->outer * p->inner;
     dim3 grid((unsigned)(ncols / TFN), (unsigned)(p->n / FM));
     const int tiles_per_o = (int)((p->inner + TFN - 1) / TFN);
@@ -402,13 +462,14 @@ int launch_fast2(const ng_plan* p, const double* in, double* out, const FuseDev&
     const size_t smem = (size_t)2 * FK * (FM + TFN + (LASTAX ? 2 : 0)) * sizeof(double);
 #define NG_DENSE_FAST(FU)                                                                       \
     do {                                                                                        \
-        NG_FUNC_SMEM(smem, dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN>);                 \
-        dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN><<<grid, 256, smem, st>>>(                    \
+        NG_FUNC_SMEM(smem, dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN, THR>);            \
+        dense_fast_kernel<DESC, FMA, FU, NCP, LASTAX, GEN, THR><<<grid, THR, smem, st>>>(               \
             in, out, Mt, (int)p->n, p->inner, p->axis, F, npitch, p->outer, tiles_per_o);       \
     } while (0)
     if (F.any) NG_DENSE_FAST(true); else NG_DENSE_FAST(false);
 #undef NG_DENSE_FAST
-    NG_TRACE(GEN ? (LASTAX ? "dense_fast<gen,lastax>" : "dense_fast<gen>")
+    NG_TRACE(THR == 128 ? (LASTAX ? "dense_fast<8x4,lastax>" : "dense_fast<8x4>")
+             : GEN ? (LASTAX ? "dense_fast<gen,lastax>" : "dense_fast<gen>")
                  : NCP == 4 ? (LASTAX ? "dense_fast<ncp4,lastax>" : "dense_fast<ncp4>")
                  : NCP == 2 ? (LASTAX ? "dense_fast<ncp2,lastax>" : "dense_fast<ncp2>")
                             : (LASTAX ? "dense_fast<ncp1,lastax>" : "dense_fast<ncp1>"));
@@ -424,17 +485,20 @@ int launch_fast(const ng_plan* p, const double* in, double* out, const FuseDev& 
         const bool wide_l = force ? force == 4 : (big_tiles >= 4 * 148 && p->outer % FN == 0);
         if (wide_l && p->outer % FN == 0) return launch_fast2<DESC, FMA, 4, true>(p, in, out, F, st);
         if (force == 2 && p->outer % 64 == 0) return launch_fast2<DESC, FMA, 2, true>(p, in, out, F, st);
+        if (force != 1 && NG_ENV_INT("NG_DENSE_8X4", 1) != 0) return launch_fast2<DESC, FMA, 2, true, false, 128>(p, in, out, F, st);
         return launch_fast2<DESC, FMA, 1, true>(p, in, out, F, st);
     }
     const bool wide = force ? force == 4 : (big_tiles >= 4 * 148 && p->inner % FN == 0);
     if (wide && p->inner % FN == 0) return launch_fast2<DESC, FMA, 4, false>(p, in, out, F, st);
     if (force == 2 && p->inner % 64 == 0) return launch_fast2<DESC, FMA, 2, false>(p, in, out, F, st);
+    // small grids (cfg4): 128 x 32 tiles with 8 x 4 outputs per thread, three CTAs of 128 threads per SM
+    if (force != 1 && NG_ENV_INT("NG_DENSE_8X4", 1) != 0) return launch_fast2<DESC, FMA, 2, false, false, 128>(p, in, out, F, st);
     return launch_fast2<DESC, FMA, 1, false>(p, in, out, F, st);
 }
 
 // 0: fallback kernel; 1: exact shapes (n % 128 == 0, columns % 32 == 0); 2: general (GEN) kernel
 int fast_mode(const ng_plan* p, const double* in, const double* out, const FuseDev& F) {
-    if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return 0;
+    if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)F.addend | (uintptr_t)F.minuend) & 15) != 0) return 0;   // 128-bit accesses
     if (F.any && p->inner != 1 && F.shape[F.vec_axis] % 2 != 0) return 0;
     const int force = (int)NG_ENV_INT("NG_DENSE_FAST", 1);    // tuning / A-B: 0 = fallback only, 2 = general kernel even on exact shapes
     if (force == 0) return 0;
