@@ -2,7 +2,7 @@
 hardware paths a kernel uses (UTMALDG / UBLKCP = TMA and bulk copies, SYNCS = mbarrier, LDGSTS = cp.async, DMUL /
 DADD / DFMA = FP64 pipe; no HMMA / DMMA / UTCMMA anywhere: the parity contract forbids reordered sums).
 
-    python tools/sass_hist.py > profiles/r02_sass_opcodes.txt
+    python tools/sass_hist.py > profiles/r02b_sass_opcodes.txt
 """
 import collections
 import os
@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "numgrids_b200", "build")
 HOT = [("fdlap3d.o", r"fdlap3d_ring2_kernel"), ("curvlap3d.o", r"curvlap3d_kernel"), ("fd.o", r"fd_march_kernel"),
        ("fd_row.o", r"fd_row_kernel"), ("dense.o", r"dense_fast_kernel"), ("fft2.o", r"fft2pass_ring_kernel"),
-       ("fft2.o", r"fft2pass_kernel"), ("quad.o", r"quad_partial_kernel"), ("transpose.o", r"slab_block_copy_kernel")]
-KEY = ("UTMALDG", "UBLKCP", "SYNCS", "LDGSTS", "DMUL", "DADD", "DFMA", "HMMA", "DMMA", "UTCMMA", "LDS", "STS", "LDG",
+       ("fft2.o", r"fft2pass_kernel"), ("fft_tile.o", r"fft_tile_kernel"), ("slab.o", r"slab_"), ("quad.o", r"quad_partial_kernel"), ("transpose.o", r"slab_block_copy_kernel")]
+KEY = ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "DMUL", "DADD", "DFMA", "HMMA", "DMMA", "UTCMMA", "LDS", "STS", "LDG",
        "STG", "SHFL", "ATOMS", "BAR", "MUFU", "LDL", "STL")
 
 
