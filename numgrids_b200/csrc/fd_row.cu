@@ -1,55 +1,9 @@
 // fd_row.cu -- finite-difference stencil apply along the CONTIGUOUS axis (second translation unit of the
 // finite-difference path; fd.cu holds the gather and march kernels and the dispatch).  Same arithmetic
 // contract as fd.cu: acc = 0.0; acc = acc + w_k * x_k in stored tap order, DMUL + DADD, never FMA.
-#include "common.cuh"
+#include "fd_fuse.cuh"
 
 namespace {
-
-__device__ __forceinline__ double2 ldg128(const double* p) {
-    return __ldg(reinterpret_cast<const double2*>(p));
-}
-
-// Fused elementwise work (ng_fuse) as a template parameter MODE: 0 = none; -1 = every step tested at run time
-// (any combination); > 0 = the steps present, as a compile-time bit mask, for the combinations the curvilinear
-// composites of curv.cu issue -- no flag tests, no offset arithmetic for absent operands (the run-time form cost
-// 134 thread-instructions per point against 57 for the plain kernel, profiles/r01_fd_row_fused_ncu_summary.txt).
-enum : int { FM_PRE = 1, FM_MINUEND = 2, FM_POST = 4, FM_ADDEND = 8, FM_ADDZERO = 16, FM_DIV = 32, FM_FINITE = 64 };
-template <int MODE> __device__ __forceinline__ bool fm_pre(const FuseDev& F) { return MODE < 0 ? F.pre.ptr != nullptr : (MODE & FM_PRE) != 0; }
-template <int MODE> __device__ __forceinline__ bool fm_post(const FuseDev& F) { return MODE < 0 ? F.post.ptr != nullptr : (MODE & FM_POST) != 0; }
-template <int MODE> __device__ __forceinline__ bool fm_div(const FuseDev& F) { return MODE < 0 ? F.div.ptr != nullptr : (MODE & FM_DIV) != 0; }
-// correctly rounded divide, out of line: ~40 instructions that would otherwise be inlined 8 x 6 times per kernel
-__device__ __noinline__ double fd_row_div(double a, double b) { return __ddiv_rn(a, b); }
-// the tail of ng_fuse (same steps and order as fuse_tail_off in common.cuh)
-template <int MODE>
-__device__ __forceinline__ double fm_tail(const FuseDev& F, double d, i64 lin, i64 post_off, i64 div_off) {
-    if (MODE < 0) return fuse_tail_off(F, d, lin, post_off, div_off);
-    if (MODE & FM_MINUEND) d = __dsub_rn(F.minuend[lin], d);
-    if (MODE & FM_POST) d = __dmul_rn(F.post.ptr[post_off], d);
-    if (MODE & FM_ADDEND) d = __dadd_rn(F.addend[lin], d);
-    else if (MODE & FM_ADDZERO) d = __dadd_rn(0.0, d);
-    if (MODE & FM_DIV) d = fd_row_div(d, F.div.ptr[div_off]);
-    if (MODE & FM_FINITE) d = ng_nonfinite(d) ? 0.0 : d;
-    return d;
-}
-
-// the same with the operands of the pair already in registers (compile-time modes): coefficient pairs come from one
-// hoisted scalar when the table is constant along the row (spherical / cylindrical metrics along z), full-shape
-// operands (minuend / addend) from one aligned 128-bit load per pair
-template <int MODE>
-__device__ __forceinline__ double fm_tail_vals(double d, double mn, double pc, double ad, double dc) {
-    if (MODE & FM_MINUEND) d = __dsub_rn(mn, d);
-    if (MODE & FM_POST) d = __dmul_rn(pc, d);
-    if (MODE & FM_ADDEND) d = __dadd_rn(ad, d);
-    else if (MODE & FM_ADDZERO) d = __dadd_rn(0.0, d);
-    if (MODE & FM_DIV) d = fd_row_div(d, dc);
-    if (MODE & FM_FINITE) d = ng_nonfinite(d) ? 0.0 : d;
-    return d;
-}
-__device__ __forceinline__ double2 coef_pair(const double* base, i64 off0, int pos, i64 stride, double hoisted) {
-    if (stride == 0) return make_double2(hoisted, hoisted);          // (no offset arithmetic on this path)
-    const i64 off = off0 + pos * stride;
-    return make_double2(__ldg(base + off), __ldg(base + off + stride));
-}
 
 // (b) derivative axis IS the contiguous one: the [rows][n] view is cut into chunks of 64 doubles (lane l
 // holds the aligned pair 2l, 2l+1: one 512-byte load per chunk) and a warp takes a group of U consecutive
@@ -295,11 +249,6 @@ int launch_row(const ng_plan* p, const double* in, double* out, const FuseDev& F
 }
 
 // the compile-time fuse patterns of the curvilinear composites (curv.cu) for the acc = 4 stencils (P = 2), no halo
-int fuse_mask(const FuseDev& F) {
-    return (F.pre.ptr ? FM_PRE : 0) | (F.minuend ? FM_MINUEND : 0) | (F.post.ptr ? FM_POST : 0) | (F.addend ? FM_ADDEND : 0) |
-           (!F.addend && F.add_zero ? FM_ADDZERO : 0) | (F.div.ptr ? FM_DIV : 0) | (F.finite ? FM_FINITE : 0);
-}
-
 template <int MODE>
 int launch_row_mode(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st, int uu) {
     const int n = (int)p->n;
@@ -329,6 +278,8 @@ int ng_fd_row_launch_wide(int P, const ng_plan* p, const double* in, double* out
                           const double* lo, const double* hi, cudaStream_t st);
 int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
                            bool* handled);
+int ng_fd_tile_try_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
+                          bool* handled);
 #if NG_ROW_PSET == 2
 // third object: P = 2 with the fuse pattern known at compile time (12 patterns x 2 chunk depths)
 int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
@@ -341,18 +292,7 @@ int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, cons
     const int uu = ue ? ue : (!deep ? 1 : 4);
     switch (fuse_mask(F)) {
 #define NG_MODE(M) case (M): return launch_row_mode<(M)>(p, in, out, F, st, uu);
-        NG_MODE(FM_POST)                                                  // laplacian: work = (J/h^2) * D f
-        NG_MODE(FM_ADDZERO)                                               //            out = 0.0 + D work
-        NG_MODE(FM_ADDEND)                                                //            out = out + D work
-        NG_MODE(FM_ADDZERO | FM_DIV | FM_FINITE)                          //            ... / J, finite (1-D grids)
-        NG_MODE(FM_ADDEND | FM_DIV | FM_FINITE)
-        NG_MODE(FM_POST | FM_FINITE)                                      // gradient
-        NG_MODE(FM_PRE | FM_ADDZERO)                                      // divergence
-        NG_MODE(FM_PRE | FM_ADDEND)
-        NG_MODE(FM_PRE | FM_ADDZERO | FM_DIV | FM_FINITE)
-        NG_MODE(FM_PRE | FM_ADDEND | FM_DIV | FM_FINITE)
-        NG_MODE(FM_PRE)                                                   // curl: out = D(h v)
-        NG_MODE(FM_PRE | FM_MINUEND | FM_POST | FM_FINITE)                //       out = finite(c * (out - D(h v)))
+        NG_FD_FUSE_MODES(NG_MODE)
 #undef NG_MODE
         default: break;
     }
@@ -362,6 +302,11 @@ int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, cons
 #elif NG_ROW_PSET == 0
 int ng_fd_row_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
                      const double* lo, const double* hi, cudaStream_t st) {
+    if (!lo && !hi) {                                        // shared-memory row tiles (fd_tile.cu)
+        bool handled = false;
+        const int rc = ng_fd_tile_try_launch(P, p, in, out, F, st, &handled);
+        if (rc || handled) return rc;
+    }
     if (P == 2 && F.any && !lo && !hi && NG_ENV_INT("NG_FD_ROW_MODES", 1) != 0) {
         bool handled = false;
         const int rc = ng_fd_row_launch_modes(p, in, out, F, st, &handled);

@@ -16,6 +16,7 @@ lib = _lib.load()
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 ncase = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 bad = 0
+kernels = {}
 
 
 def coef(t, shape, vary):
@@ -84,6 +85,9 @@ for case in range(ncase):
     outs = []
     for stream_on in ("1", "0"):
         os.environ["NG_FD_STREAM"] = stream_on
+        # contiguous-axis cases: the shared-memory tile kernel (fd_tile.cu) on two cases of three, also for plain applies
+        # and at any size; the shuffle kernel (fd_row.cu) on the third
+        os.environ["NG_FD_TILE"], os.environ["NG_FD_TILE_MIN"] = ("2", "0") if case % 3 else ("0", "0")
         lib.ng_tuning_reload()
         o = torch.full(shape, float("nan"), dtype=torch.float64, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
@@ -96,6 +100,8 @@ for case in range(ncase):
         else:
             rc = lib.ng_apply(op.plan.handle, f.data_ptr(), o.data_ptr(), st)
         _lib.check(rc, "apply")
+        if stream_on == "1":
+            kernels[_lib.last_kernel()] = kernels.get(_lib.last_kernel(), 0) + 1
         outs.append(o)
     same = torch.equal(outs[0].view(torch.int64), outs[1].view(torch.int64))
     if not same:
@@ -104,5 +110,6 @@ for case in range(ncase):
         print(f"MISMATCH case {case}: shape {shape} axis {axis} order {order} acc {acc} kind {kind} fuse {fuse is not None} "
               f"halo {None if halo is None else [h is not None for h in halo]} nbad {int((outs[0].view(torch.int64) != outs[1].view(torch.int64)).sum())} "
               f"maxdiff {float(torch.nan_to_num(d).max()):.3e}")
+print("kernels:", kernels)
 print(f"{ncase} cases, {bad} mismatches")
 sys.exit(1 if bad else 0)
