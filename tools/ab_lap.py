@@ -21,8 +21,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from numgrids_b200 import _lib  # noqa: E402
 from numgrids_b200.slab import SlabLaplacian  # noqa: E402
 
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
+args = [a for i, a in enumerate(sys.argv[1:], 1) if not a.startswith("--") and sys.argv[i - 1] not in ("--rounds", "--only")]
 rounds = int(sys.argv[sys.argv.index("--rounds") + 1]) if "--rounds" in sys.argv else 6
+burst = "--burst" in sys.argv
+only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
 shape = tuple(int(s) for s in (args[:3] if len(args) >= 3 else (1024, 1024, 1024)))
 hs = [1.0 / (n - 1) for n in shape]
 lap = SlabLaplacian(shape, hs)
@@ -67,7 +69,7 @@ class Clock:
 
 
 def env(**kw):
-    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST", "NG_MBAR_HINT_NS"):
+    for k in ("NG_FDLAP_S", "NG_FDLAP_XCHUNK", "NG_FDLAP_RING", "NG_FDLAP_EDGE_TEST", "NG_MBAR_HINT_NS", "NG_FDLAP_TY"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -97,6 +99,9 @@ def parts_two_streams():
 
 variants = {
     "whole S=8 xc=64 (default)": whole(),
+    "whole S=10 xc=32": whole(NG_FDLAP_S=10, NG_FDLAP_XCHUNK=32),
+    "whole xc=32": whole(NG_FDLAP_XCHUNK=32),
+    "whole xc=256": whole(NG_FDLAP_XCHUNK=256),
     "whole S=6": whole(NG_FDLAP_S=6),
     "whole S=10": whole(NG_FDLAP_S=10),
     "whole, mbarrier hint 0 ns": whole(NG_MBAR_HINT_NS=0),
@@ -113,7 +118,7 @@ variants = {
     "experiment: tiles 1 and nt-2 alone": ({}, lambda: lap.apply_part(f, out, 3)),
     "experiment: boundary tiles as interior": ({"NG_FDLAP_EDGE_TEST": 1}, lambda: lap.apply_part(f, out, 2, lo, hi)),
 }
-names = list(variants)
+names = [n for n in variants if only is None or any(o in n for o in only)]
 res = {n: [] for n in names}
 clk = {n: [] for n in names}
 for r in range(rounds):
@@ -124,6 +129,8 @@ for r in range(rounds):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
+        if burst:
+            time.sleep(0.4)                         # let the part leave its power cap: the next 5 applies run at boost clocks
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with Clock() as c:
             a.record()
