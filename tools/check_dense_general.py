@@ -17,6 +17,7 @@ lib = _lib.load()
 ncase = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = 0
+kernels = {}
 
 
 def coef(t, shape, vary):
@@ -64,6 +65,7 @@ for case in range(ncase):
             t = torch.from_numpy(rng.standard_normal(shape)).cuda(); keep.append(t); fuse.minuend = t.data_ptr()
         fuse.finite = int(rng.random() < 0.5)
     outs = []
+    # modes: "2" = general panel kernel, "0" = fallback kernel, "1" = exact-shape panel kernel
     for mode in ("2", "0") + (("1",) if exact else ()):
         os.environ["NG_DENSE_FAST"] = mode
         lib.ng_tuning_reload()
@@ -72,6 +74,7 @@ for case in range(ncase):
         rc = (lib.ng_apply_fused(op.plan.handle, f.data_ptr(), o.data_ptr(), C.byref(fuse), st) if fuse is not None
               else lib.ng_apply(op.plan.handle, f.data_ptr(), o.data_ptr(), st))
         _lib.check(rc, "apply")
+        kernels[_lib.last_kernel()] = kernels.get(_lib.last_kernel(), 0) + 1
         outs.append(o)
     for k, o in enumerate(outs[1:]):
         if not torch.equal(outs[0].view(torch.int64), o.view(torch.int64)):
@@ -79,5 +82,6 @@ for case in range(ncase):
             d = torch.nan_to_num(outs[0] - o).abs().max().item()
             nb = int((outs[0].view(torch.int64) != o.view(torch.int64)).sum())
             print(f"MISMATCH case {case} vs mode {('0', '1')[k]}: shape {shape} axis {axis} order {order} fuse {fuse is not None} nbad {nb} maxdiff {d:.3e}")
+print("kernels:", kernels)
 print(f"{ncase} cases, {bad} mismatches")
 sys.exit(1 if bad else 0)
