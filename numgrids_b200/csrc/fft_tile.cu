@@ -41,15 +41,23 @@ __device__ __forceinline__ void ft_tma_store_3d(const CUtensorMap* tm, int c0, i
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                  ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
 }
+// out[box] += tile (IEEE double adds performed by the memory system): the `addend == out` accumulate of the composites
+__device__ __forceinline__ void ft_tma_reduce_add_3d(const CUtensorMap* tm, int c0, int c1, int c2, unsigned src) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
+}
 __device__ __forceinline__ void ft_group_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // C columns per tile (row = C*8 bytes: 64 -> SWIZZLE_64B, 128 -> SWIZZLE_128B), NSLOT slots, 8 warps
-template <int RT, int R2, int C, int NSLOT, int MINB>
+// FUSED: ng_fuse work on the register array (pre, the double apply `mid`, post, + 0.0, div, finite -- fft_net.cuh);
+// red_add: the apply accumulates into its own output (`addend == out`, no divide / select behind it): the tile is
+// stored with a TMA reduce-add instead of loading the addend (out + d and d + out are the same IEEE sum).
+template <int RT, int R2, int C, int NSLOT, int MINB, bool FUSED>
 __global__ void __launch_bounds__(256, MINB)
 fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ Wn,
-                const double2* __restrict__ tw, i64 ntiles, int tiles_per_outer, i64 inner, int axis,
+                const double2* __restrict__ tw, i64 ntiles, int tiles_per_outer, i64 inner, int axis, int red_add,
                 const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ FuseDev F) {
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T, NW = 8;
@@ -112,9 +120,25 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         const int sl = (int)(s % NSLOT);
         unsigned char* slot = slots + (size_t)sl * SLOT_B;
         pf_mbar_wait(full + 2 * sl + (int)((s / NSLOT) & 1), (unsigned)((s / (2 * NSLOT)) & 1));
+        const i64 id = s * gridDim.x + blockIdx.x;
+        const int o = (int)(id / tiles_per_outer);
+        const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
+        const bool vab = c0 + 2 * cp < inner;      // this lane's pencil pair exists (inner is even)
+        const i64 lin0 = vab ? (i64)o * N * inner + c0 + 2 * cp : 0;      // sample 0 of pencil a (b: + 1)
         double2 x[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) x[r] = *reinterpret_cast<const double2*>(slot + col(r * R2 + t));
+        if (FUSED && F.pre.ptr) {
+            const PencilCoef ca = pencil_coef(F, F.pre, lin0, axis, t, R2), cb = pencil_coef(F, F.pre, lin0 + (vab ? 1 : 0), axis, t, R2);
+            pencil_mul_all<RT>(x, ca, cb, vab, vab);
+        }
+        const int nrep = (FUSED && F.mid.ptr) ? 2 : 1;     // double apply (FuseDev::mid): a run-time loop around the one body
+#pragma unroll 1
+        for (int rep = 0; rep < nrep; ++rep) {
+        if (FUSED && rep == 1) {
+            const PencilCoef ma = pencil_coef(F, F.mid, lin0, axis, t, R2), mb = pencil_coef(F, F.mid, lin0 + (vab ? 1 : 0), axis, t, R2);
+            pencil_mul_all<RT>(x, ma, mb, vab, vab);
+        }
         __syncwarp();                              // the column becomes the exchange buffer
         dif_forward<RT>(x);
 #pragma unroll
@@ -157,18 +181,30 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
             x[q] = v;
         }
         dit_inverse<RT>(x);
-        __syncwarp();                              // every lane has its rows back: the column takes the result
-#pragma unroll
-        for (int r = 0; r < RT; ++r) *reinterpret_cast<double2*>(slot + col(r * R2 + t)) = x[r];
+        __syncwarp();                              // every lane has its rows back: the column is free again
+        }
         const bool bad = __any_sync(0xffffffffu, ng_nonfinite(x[0].x) || ng_nonfinite(x[0].y));
         if (bad && lane == 0) atomicOr(myflag, 1);
+        if (FUSED) {
+            PencilTail ta, tb;
+            ta.init(F, lin0, inner, axis, t, R2);
+            tb.init(F, lin0 + (vab ? 1 : 0), inner, axis, t, R2);
+            if (red_add) {
+                ta.addend = tb.addend = nullptr;   // the reduce-add store performs `out + d`
+                if (bad) {                         // poisoned pairs are redone below from `out` as it was: add -0.0 (the identity)
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) x[r] = make_double2(-0.0, -0.0);
+                }
+            }
+            if (!(red_add && bad)) pencil_tail_all<RT>(F, ta, tb, x);
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) *reinterpret_cast<double2*>(slot + col(r * R2 + t)) = x[r];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         ft_group_bar(1 + grp, 32 * WPT);
-        const i64 id = s * gridDim.x + blockIdx.x;
-        const int o = (int)(id / tiles_per_outer);
-        const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
         if (lane == 0) {                           // every warp stores (and below refills) its own rows of the tile
-            ft_tma_store_3d(&tm_out, c0, wg * BR, o, pf_smem_u32(slot + (size_t)wg * BOX_B));
+            if (FUSED && red_add) ft_tma_reduce_add_3d(&tm_out, c0, wg * BR, o, pf_smem_u32(slot + (size_t)wg * BOX_B));
+            else ft_tma_store_3d(&tm_out, c0, wg * BR, o, pf_smem_u32(slot + (size_t)wg * BOX_B));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (*reinterpret_cast<volatile int*>(myflag)) {
@@ -181,7 +217,7 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
                 for (int q = 0; q < 2 * TPW; ++q) {
                     const i64 cc = c0 + (i64)(wg * TPW) * 2 + q;
                     if (cc < inner)
-                        fft_slow_pencil<false>(in, out, (i64)o * N * inner + cc, inner, axis, N, LRT + LR2,
+                        fft_slow_pencil<FUSED>(in, out, (i64)o * N * inner + cc, inner, axis, N, LRT + LR2,
                                                reinterpret_cast<double2*>(slot + (size_t)(wg * TPW + (q >> 1)) * N * 16),
                                                Wn, tw, F, N);
                 }
@@ -244,7 +280,7 @@ int ft_make_tmap(CUtensorMap* tm, const double* base, i64 outer, i64 n, i64 inne
 }
 
 template <int RT, int R2, int C, int NSLOT, int MINB>
-int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
+int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& F, int red_add, cudaStream_t st) {
     constexpr int N = RT * R2, WPT = C / (2 * (32 / R2)), NG = 8 / WPT, BR = N / WPT;
     static_assert(BR <= 256, "TMA box extent");
     const i64 tpo = (p->inner + C - 1) / C;
@@ -254,13 +290,18 @@ int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& 
     if (!rc) rc = ft_make_tmap(&tmo, out, p->outer, N, p->inner, C, BR);
     if (rc) return rc;
     const size_t smem = (size_t)NSLOT * N * C * 8 + (size_t)2 * N * 16 + 2 * NSLOT * 8 + NG * 8 + 16;
-    NG_FUNC_SMEM(smem, fft_tile_kernel<RT, R2, C, NSLOT, MINB>);
     i64 g = (ntiles + NG - 1) / NG;                      // at least one tile per group
     if (g > (i64)148 * MINB) g = (i64)148 * MINB;
-    fft_tile_kernel<RT, R2, C, NSLOT, MINB><<<(unsigned)g, 256, smem, st>>>(
-        in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, ntiles, (int)tpo, p->inner, p->axis,
-        tmi, tmo, F);
-    NG_TRACE("fft_tile");
+#define NG_FFT_TILE(FU)                                                                                             \
+    do {                                                                                                            \
+        NG_FUNC_SMEM(smem, fft_tile_kernel<RT, R2, C, NSLOT, MINB, FU>);                                            \
+        fft_tile_kernel<RT, R2, C, NSLOT, MINB, FU><<<(unsigned)g, 256, smem, st>>>(                                \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, ntiles, (int)tpo, p->inner, p->axis, red_add, \
+            tmi, tmo, F);                                                                                           \
+    } while (0)
+    if (F.any) NG_FFT_TILE(true); else NG_FFT_TILE(false);
+#undef NG_FFT_TILE
+    NG_TRACE(F.any ? (red_add ? "fft_tile<fused,add>" : "fft_tile<fused>") : "fft_tile");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -272,17 +313,29 @@ int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& 
 int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
                            bool* handled) {
     *handled = false;
-    if (F.any || p->inner == 1 || p->fft_len != p->n || !p->d_Wn || !p->d_twn) return NG_OK;
+    if (p->inner == 1 || p->fft_len != p->n || !p->d_Wn || !p->d_twn) return NG_OK;
     if (NG_ENV_INT("NG_FFT_TILE", 1) == 0) return NG_OK;        // A/B: 0 = strided register kernel
     if ((p->inner & 1) || p->inner < 16 || ((((uintptr_t)in | (uintptr_t)out) & 15) != 0)) return NG_OK;
     if (p->outer > 0x7fffffff || p->inner > 0x7fffffff) return NG_OK;
+    // fused applies: everything but a minuend; an addend only as the in-place accumulate `out = out + D(...)` with no
+    // divide / select behind it (the periodic pass of a Laplacian or divergence that is not the last axis), which
+    // becomes a TMA reduce-add store.  The rest stays on the strided register kernel.
+    int red_add = 0;
+    if (F.any) {
+        if (NG_ENV_INT("NG_FFT_TILE", 1) == 2) return NG_OK;    // A/B: 2 = plain applies only
+        if (F.minuend) return NG_OK;
+        if (F.addend) {
+            if (F.addend != out || F.div.ptr || F.finite) return NG_OK;
+            red_add = 1;
+        }
+    }
     int rc = NG_OK;
     switch (p->n) {
-        case 1024: rc = launch_tile<32, 32, 8, 3, 1>(p, in, out, F, st); break;
-        case 512: rc = launch_tile<32, 16, 16, 3, 1>(p, in, out, F, st); break;
-        case 256: rc = launch_tile<16, 16, 16, 3, 2>(p, in, out, F, st); break;
-        case 128: rc = launch_tile<16, 8, 16, 6, 2>(p, in, out, F, st); break;
-        case 64: rc = launch_tile<8, 8, 16, 12, 2>(p, in, out, F, st); break;
+        case 1024: rc = launch_tile<32, 32, 8, 3, 1>(p, in, out, F, red_add, st); break;
+        case 512: rc = launch_tile<32, 16, 16, 3, 1>(p, in, out, F, red_add, st); break;
+        case 256: rc = launch_tile<16, 16, 16, 3, 2>(p, in, out, F, red_add, st); break;
+        case 128: rc = launch_tile<16, 8, 16, 6, 2>(p, in, out, F, red_add, st); break;
+        case 64: rc = launch_tile<8, 8, 16, 12, 2>(p, in, out, F, red_add, st); break;
         default: return NG_OK;
     }
     *handled = (rc == NG_OK);

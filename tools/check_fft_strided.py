@@ -17,6 +17,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 ncase = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 worst = 0.0
 bad = 0
+kernels = {}
 
 
 def coef(t, shape, vary):
@@ -48,6 +49,7 @@ for case in range(ncase):
     fh = rng.standard_normal(shape)
     f = torch.from_numpy(fh).cuda()
     fuse, keep = None, []
+    inplace = False
     if rng.random() < 0.6 and shape[-1] % 2 == 0:
         fuse = _lib.NgFuse()
         for name in ("pre", "post", "divisor"):
@@ -61,28 +63,40 @@ for case in range(ncase):
         if rng.random() < 0.3:
             t = torch.from_numpy(rng.standard_normal(shape)).cuda(); keep.append(t); fuse.minuend = t.data_ptr()
         fuse.finite = int(rng.random() < 0.5)
+        if rng.random() < 0.35:                              # the composites' in-place accumulate: out = out + D(pre * f)
+            fuse.addend, fuse.minuend, fuse.finite = 1, None, 0          # (addend is pointed at the output below)
+            fuse.divisor = _lib.NgCoef()
+            inplace = True
     if rng.random() < 0.3:                                   # a singular pencil: all-NaN out, neighbours clean
         idx = [int(rng.integers(0, s)) for s in shape]
         idx[axis] = int(rng.integers(0, n))
         f[tuple(idx)] = float("inf")
     outs = []
-    for mode in ("1", "0"):
-        os.environ["NG_FFT_STRIDED"] = mode
+    acc0 = torch.from_numpy(rng.standard_normal(shape)).cuda() if inplace else None
+    # tile kernel (fft_tile.cu: plain and fused applies where it takes them) / strided register kernel / radix-2 fallback
+    for mode, tile in (("1", "1"), ("1", "0"), ("0", "0")):
+        os.environ["NG_FFT_STRIDED"], os.environ["NG_FFT_TILE"] = mode, tile
         lib.ng_tuning_reload()
-        o = torch.full(shape, 7.0, dtype=torch.float64, device="cuda")
+        o = acc0.clone() if inplace else torch.full(shape, 7.0, dtype=torch.float64, device="cuda")
+        if inplace:
+            fuse.addend = o.data_ptr()
         st = torch.cuda.current_stream().cuda_stream
         rc = (lib.ng_apply_fused(op.plan.handle, f.data_ptr(), o.data_ptr(), C.byref(fuse), st) if fuse is not None
               else lib.ng_apply(op.plan.handle, f.data_ptr(), o.data_ptr(), st))
         _lib.check(rc, "apply")
+        if tile == "1":
+            kernels[_lib.last_kernel()] = kernels.get(_lib.last_kernel(), 0) + 1
         outs.append(o)
-    a, b = outs
-    nan_same = torch.equal(torch.isnan(a), torch.isnan(b))
-    fin = ~torch.isnan(b)
-    den = float(b[fin].abs().max()) if fin.any() else 1.0
-    err = float((a[fin] - b[fin]).abs().max() / max(den, 1e-300)) if fin.any() else 0.0
-    worst = max(worst, err)
-    if not nan_same or err > 5e-13:
-        bad += 1
-        print(f"MISMATCH case {case}: shape {shape} axis {axis} order {order} fuse {fuse is not None} nan_same {nan_same} err {err:.3e}")
+    b = outs[2]
+    for which, a in (("tile", outs[0]), ("strided", outs[1])):
+        nan_same = torch.equal(torch.isnan(a), torch.isnan(b))
+        fin = ~torch.isnan(b)
+        den = float(b[fin].abs().max()) if fin.any() else 1.0
+        err = float((a[fin] - b[fin]).abs().max() / max(den, 1e-300)) if fin.any() else 0.0
+        worst = max(worst, err)
+        if not nan_same or err > 5e-13:
+            bad += 1
+            print(f"MISMATCH case {case} ({which}): shape {shape} axis {axis} order {order} fuse {fuse is not None} inplace {inplace} nan_same {nan_same} err {err:.3e}")
+print("kernels:", kernels)
 print(f"{ncase} cases, {bad} mismatches, worst rel diff vs the radix-2 kernel {worst:.2e}")
 sys.exit(1 if bad else 0)
