@@ -535,10 +535,14 @@ int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStrea
     // tuning: tile rows / ring depth.  Two rows per warp recompute more of the y inner derivative ((R+4)/R rows per own
     // row) but put four warps on every scheduler instead of two, and the kernel is latency-bound (dependent FP64 chains):
     // 512^3 unit scale 1.45 ms against 1.64 ms (profiles/r02_tune_curvlap.txt)
-    switch ((int)NG_ENV_INT("NG_CURV_CFG", 2)) {
+    switch ((int)NG_ENV_INT("NG_CURV_CFG", 4)) {
         case 0: rc = cl_launch<4, 4, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, two CTAs of 4 warps per SM
         case 1: rc = cl_launch<4, 8, 9>(p, in, out, hp, gen, st); break;      // 32 x 64 tiles, one CTA of 8 warps per SM
-        default: rc = cl_launch<2, 8, 8>(p, in, out, hp, gen, st); break;     // 16 x 64 tiles, 2 rows per warp: two CTAs of 8 warps
+        case 2: rc = cl_launch<2, 8, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, 2 rows per warp: two CTAs of 8 warps
+        // the same with a ring of 6 planes (one ahead of the 5-plane window): 512^3 1.46 -> 1.36 ms -- the chunks are
+        // 16 planes long, so a deeper ring buys nothing, while 55 KB less shared memory per SM is 55 KB more L1 for the
+        // out-of-line boundary routine and the few spills (profiles/r02b_time_curvlap.txt)
+        default: rc = cl_launch<2, 8, 6>(p, in, out, hp, gen, st); break;
     }
     if (rc) return rc;
     *handled = true;
