@@ -208,12 +208,17 @@ struct ClRows {
 
 // The work of one consumer warp for output plane x (its R rows): y and z terms from the centre slot, the
 // x term from the gx window, combine, store.
-template <int R, bool GEN>
+// YS: the y inner derivatives are SHARED through shared memory instead of recomputed per warp: every warp forms gy on
+// its own R rows only (and warps 0..3 on one of the four rows just outside the tile), publishes them, the CTA meets at
+// one named barrier per plane, and the outer derivative reads the R + 4 rows it needs -- (R + 0.5) / R instead of
+// (R + 4) / R inner derivatives per own row.  gy_w: shared address of this plane's buffer ([TY + 4][32] pairs, row 0 =
+// tile row -2); warp / WY / yb place the warp in the tile.
+template <int R, bool GEN, bool YS, int WY>
 __device__ __forceinline__ void cl_output(int x, int y0, int z0, int lane, int nx, int ny, int nz, const ClTabs& T, const ClGen& G,
                                           const ClParams* P, const double* __restrict__ in, double* __restrict__ out,
                                           unsigned a_cen /*smem: (row y0, own pair) of plane x*/, unsigned a_tile /*smem: (row y0, column z0)*/,
                                           const ClRows<R>& G0, const ClRows<R>& G1, const ClRows<R>& G2,
-                                          const ClRows<R>& G3, const ClRows<R>& G4) {
+                                          const ClRows<R>& G3, const ClRows<R>& G4, unsigned gy_w, int warp, int yb) {
     constexpr unsigned PB = CL_PITCH * 8;
     const int z = z0 + 2 * lane;
     const i64 sx = (i64)ny * nz;
@@ -224,9 +229,50 @@ __device__ __forceinline__ void cl_output(int x, int y0, int z0, int lane, int n
 
     // ---------------- y: rows y0-4 .. y0+R+3 of the own column pair
     double2 F[R + 8];
+    double2 Y[R];
+    if (YS) {
+        constexpr int TYc = R * WY;
+#pragma unroll
+        for (int i = 2; i < R + 6; ++i) F[i] = cl_lds2(a_cen + (unsigned)((i - 4) * (int)PB));    // rows y0-2 .. y0+R+1
+        double2 GO[R];                                   // gy on the own rows (central scheme; rows within 2 of a y face
+#pragma unroll                                           // hold values nobody reads)
+        for (int r = 0; r < R; ++r) {
+            const int yr = y0 + r;
+            GO[r] = make_double2(0.0, 0.0);
+            if (yr >= 2 && yr < ny - 2)
+                GO[r] = cl_finish_xy<GEN>(cl_sum5(T.a[1].wc, F[r + 2], F[r + 3], F[r + 4], F[r + 5], F[r + 6]), T.a[1].ih, G, 1,
+                                          yr, true, x, yr, z);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(gy_w + (unsigned)((warp * R + r + 2) * 512 + lane * 16)),
+                         "d"(GO[r].x), "d"(GO[r].y) : "memory");
+        }
+        if (warp < 4) {                                  // one of the four rows just outside the tile: -2, -1, TY, TY+1
+            const int hr = warp < 2 ? warp - 2 : TYc + warp - 2;
+            const int yh = yb + hr;
+            if (yh >= 2 && yh < ny - 2) {
+                const unsigned a = a_tile + (unsigned)((hr - warp * R) * (int)PB) + 16u * lane;    // (row yh, own pair)
+                const double2 h = cl_finish_xy<GEN>(cl_sum5(T.a[1].wc, cl_lds2(a - 2 * PB), cl_lds2(a - PB), cl_lds2(a), cl_lds2(a + PB),
+                                                            cl_lds2(a + 2 * PB)), T.a[1].ih, G, 1, yh, true, x, yh, z);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(gy_w + (unsigned)((hr + 2) * 512 + lane * 16)),
+                             "d"(h.x), "d"(h.y) : "memory");
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * WY) : "memory");
+        if (!yfix) {
+            double2 GY[R + 4];
+#pragma unroll
+            for (int j = 0; j < R + 4; ++j)
+                GY[j] = (j >= 2 && j < R + 2) ? GO[j - 2] : cl_lds2(gy_w + (unsigned)((warp * R + j) * 512 + lane * 16));
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                Y[r] = cl_finish_xy<GEN>(cl_sum5(T.a[1].wc, GY[r], GY[r + 1], GY[r + 2], GY[r + 3], GY[r + 4]), T.a[1].ih, G, 1,
+                                         y0 + r, false, x, y0 + r, z);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) Y[r] = cl_term_global(P, GEN, in + goff + (i64)r * nz, nz, 1, y0 + r, ny, x, y0 + r, z);
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < R + 8; ++i) F[i] = cl_lds2(a_cen + (unsigned)((i - 4) * (int)PB));
-    double2 Y[R];
     if (!yfix) {
         double2 GY[R + 4];
 #pragma unroll
@@ -240,6 +286,7 @@ __device__ __forceinline__ void cl_output(int x, int y0, int z0, int lane, int n
     } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) Y[r] = cl_term_global(P, GEN, in + goff + (i64)r * nz, nz, 1, y0 + r, ny, x, y0 + r, z);
+    }
     }
 
     // ---------------- z: inner derivative of the own pairs, of the 2R pairs beyond the warp's columns
@@ -315,7 +362,7 @@ __device__ __forceinline__ void cl_output(int x, int y0, int z0, int lane, int n
 // exactly two CTAs x four warps each thread may use 255.  Slots are handed back through a shared counter:
 // the LAST warp to finish an iteration re-arms the slot's mbarrier and issues the TMA for the plane that
 // takes its place at once, so the ring stays S-5 planes ahead without anybody waiting for a producer.
-template <int R, int WY, int S, bool GEN>
+template <int R, int WY, int S, bool GEN, bool YS = false>
 __global__ void __launch_bounds__(32 * WY, (R * WY >= 32 ? 1 : 2))
 curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx, int ny, int nz, int xchunk,
                  const __grid_constant__ ClTabs T, const __grid_constant__ ClGen G, const ClParams* __restrict__ P,
@@ -327,6 +374,8 @@ curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx
     const unsigned ring = (cl_smem_u32(smem_raw) + 127u) & ~127u;        // TMA destinations: 128-byte aligned
     const unsigned full = ring + S * PLANE_B;
     int* const done = reinterpret_cast<int*>(smem_raw + (full - cl_smem_u32(smem_raw)) + 8 * S);   // warps finished with a slot
+    const unsigned gy_base = (full + 12 * S + 15u) & ~15u;     // YS: two buffers of [TY + 4][32] pairs, alternating per plane
+    constexpr unsigned GY_B = (TY + 4) * 512;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int z0 = blockIdx.x * CL_TZ;
@@ -371,6 +420,7 @@ curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx
     if (y0 >= ny) {                                    // warp outside the grid (ragged last y tile): keep pace, hand the slots back
         for (int it = 0; it < niter; ++it) {
             cl_wait(full + 8 * ((it + 4) % S), ((it + 4) / S) & 1);
+            if (YS && it >= 4) asm volatile("bar.sync 1, %0;" ::"n"(32 * WY) : "memory");   // (the CTA's barrier of cl_output)
             release(it);
         }
         return;
@@ -414,7 +464,8 @@ curvlap3d_kernel(double* __restrict__ out, const double* __restrict__ in, int nx
         }
         if (it >= 4) {                                  // the first four iterations only fill the window
             const unsigned slot = ring + (it % S) * PLANE_B;
-            cl_output<R, GEN>(q - 2, y0, z0, lane, nx, ny, nz, T, G, P, in, out, slot + my_off, slot + tile_off, g0, g1, g2, g3, g4);
+            cl_output<R, GEN, YS, WY>(q - 2, y0, z0, lane, nx, ny, nz, T, G, P, in, out, slot + my_off, slot + tile_off, g0, g1, g2,
+                                      g3, g4, gy_base + (it & 1) * GY_B, warp, yb);
         }
         release(it);
     }
@@ -459,7 +510,7 @@ int cl_make_tmap(CUtensorMap* tm, const double* in, i64 nx, i64 ny, i64 nz, int 
     return NG_OK;
 }
 
-template <int R, int WY, int S>
+template <int R, int WY, int S, bool YS = false>
 int cl_launch(ng_plan* p, const double* in, double* out, const ClParams& hp, bool gen, cudaStream_t st) {
     constexpr int TY = R * WY;
     const i64 nx = p->shape[0], ny = p->shape[1], nz = p->shape[2];
@@ -475,15 +526,15 @@ int cl_launch(ng_plan* p, const double* in, double* out, const ClParams& hp, boo
     if (xchunk < 1) xchunk = 16;
     if (xchunk > nx) xchunk = (int)nx;
     dim3 grid((unsigned)(nz / CL_TZ), (unsigned)((ny + TY - 1) / TY), (unsigned)((nx + xchunk - 1) / xchunk));
-    const size_t smem = (size_t)S * (TY + 2 * CL_H) * CL_PITCH * 8 + 8 * S + 4 * S + 128;
+    const size_t smem = (size_t)S * (TY + 2 * CL_H) * CL_PITCH * 8 + 8 * S + 4 * S + 128 + (YS ? 2 * (TY + 4) * 512 + 16 : 0);
     if (gen) {
-        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, S, true>);
-        curvlap3d_kernel<R, WY, S, true><<<grid, 32 * WY, smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
+        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, S, true, YS>);
+        curvlap3d_kernel<R, WY, S, true, YS><<<grid, 32 * WY, smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
                                                                             (const ClParams*)p->d_curvlap, tm);
         NG_TRACE("curvlap3d<gen>");
     } else {
-        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, S, false>);
-        curvlap3d_kernel<R, WY, S, false><<<grid, 32 * WY, smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
+        NG_FUNC_SMEM(smem, curvlap3d_kernel<R, WY, S, false, YS>);
+        curvlap3d_kernel<R, WY, S, false, YS><<<grid, 32 * WY, smem, st>>>(out, in, (int)nx, (int)ny, (int)nz, xchunk, hp.T, hp.G,
                                                                              (const ClParams*)p->d_curvlap, tm);
         NG_TRACE("curvlap3d<unit>");
     }
@@ -539,10 +590,16 @@ int ng_curvlap3d_try_launch(ng_plan* p, const double* in, double* out, cudaStrea
         case 0: rc = cl_launch<4, 4, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, two CTAs of 4 warps per SM
         case 1: rc = cl_launch<4, 8, 9>(p, in, out, hp, gen, st); break;      // 32 x 64 tiles, one CTA of 8 warps per SM
         case 2: rc = cl_launch<2, 8, 8>(p, in, out, hp, gen, st); break;      // 16 x 64 tiles, 2 rows per warp: two CTAs of 8 warps
+        case 8: rc = cl_launch<2, 8, 6, true>(p, in, out, hp, gen, st); break;   // ... with the y inner derivatives shared through smem
         // the same with a ring of 6 planes (one ahead of the 5-plane window): 512^3 1.46 -> 1.36 ms -- the chunks are
         // 16 planes long, so a deeper ring buys nothing, while 55 KB less shared memory per SM is 55 KB more L1 for the
         // out-of-line boundary routine and the few spills (profiles/r02b_time_curvlap.txt)
-        default: rc = cl_launch<2, 8, 6>(p, in, out, hp, gen, st); break;
+        default:
+            // general metrics (coefficient loads, divides in every inner derivative): the y inner derivatives shared through
+            // shared memory, one CTA barrier per plane (2.48 -> 2.35 ms at 512^3); unit scale: recomputed per warp -- there
+            // the barrier costs more than the 20 FP64 operations per row it saves (1.36 vs 1.70 ms)
+            rc = gen ? cl_launch<2, 8, 6, true>(p, in, out, hp, gen, st) : cl_launch<2, 8, 6>(p, in, out, hp, gen, st);
+            break;
     }
     if (rc) return rc;
     *handled = true;

@@ -44,7 +44,7 @@ for name, fns, shape in cases:
         g._jacobian = np.broadcast_to(1.0, shape)
     f = torch.rand(*shape, dtype=torch.float64, device="cuda")
     pts = f.numel()
-    for mode, cfg, xc in (("1", "4", "0"), ("1", "2", "0"), ("1", "0", "0"), ("0", "0", "0")):
+    for mode, cfg, xc in (("1", "4", "0"), ("1", "8", "0"), ("1", "2", "0"), ("1", "0", "0"), ("0", "0", "0")):
         os.environ["NG_CURV_FUSED"], os.environ["NG_CURV_CFG"], os.environ["NG_CURV_XCHUNK"] = mode, cfg, xc
         _lib.tuning_reload()
         med, mn = timed(lambda: g.laplacian(f))
