@@ -223,7 +223,13 @@ class LogDiff(_StencilMixin, GridDiff):
 class FFTDiff(GridDiff):
     """Spectral derivative on a periodic equidistant axis (reference numgrids/diff.py:109-171)."""
 
-    PADDED_MIN_POINTS = 65          # non-power-of-two axes from this length on: zero-padded transform (order 1)
+    PADDED_MIN_POINTS = 65          # non-power-of-two axes from this length on: zero-padded transform
+    # Derivative orders the zero-padded transform serves.  Order 2 amplifies ANY transform's rounding by (n/2)^2:
+    # measured against numpy.fft (tools/check_fft_order2_nonpow2.py, profiles/r02b_fft_order2_nonpow2.txt) the padded
+    # transform and the dense ordered contraction it replaces are equally close (n = 1000: 1.2e-11 / 9.7e-12,
+    # n = 1536: 3.1e-11 / 3.6e-11), both ten times closer to numpy.fft than numpy.fft is to a long-double DFT
+    # (9e-11 / 3e-10) -- so the O(n log n) path costs no accuracy.  Higher orders keep the dense contraction.
+    PADDED_ORDERS = (1, 2)
 
     def __init__(self, grid, order, axis_index, acc=6):
         super().__init__(grid, order, axis_index)
@@ -251,11 +257,10 @@ class FFTDiff(GridDiff):
         n = len(self.axis)
         out = C.c_void_p()
         pow2 = _tables.is_pow2(n) and n <= 8192
-        # Any other length: first derivatives run as a zero-padded power-of-two transform (O(n log n) like the
-        # reference's pocketfft, within a few 1e-14 of it); higher orders amplify the padded transform's rounding
-        # beyond the 1e-11 contract (order 2: 1e-11 at n = 1000), so they keep the dense O(n^2) contraction, as do
-        # short axes, where it is faster.
-        padded = None if pow2 or self.order != 1 or n < self.PADDED_MIN_POINTS else _tables.fft_padded_multiplier(self._W_1d)
+        # Any other length: first and second derivatives run as a zero-padded power-of-two transform (O(n log n) like
+        # the reference's pocketfft; see PADDED_ORDERS for the accuracy); orders >= 3 and short axes keep the dense
+        # O(n^2) contraction.
+        padded = None if pow2 or self.order not in self.PADDED_ORDERS or n < self.PADDED_MIN_POINTS else _tables.fft_padded_multiplier(self._W_1d)
         if padded is not None:
             m, Wm = padded
             Wmk, Wm_p = _lib.as_f64(np.ascontiguousarray(Wm, dtype=np.complex128).view(np.float64))
