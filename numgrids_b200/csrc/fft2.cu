@@ -404,6 +404,10 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
         // zero-padded plan (any axis length): plain applies on the two-pass kernel, fused ones on the radix-2 kernel
         if (F.any) return NG_OK;
         const bool str = p->inner != 1;
+        if (str) {                                          // strided pencils: TMA tiles (fft_tile.cu), rows past n zero-filled
+            rc = ng_fft_tile_try_launch(p, in, out, F, st, handled);
+            if (rc || *handled) return rc;
+        }
         switch (p->fft_len) {
             case 1024: rc = str ? launch_padded<32, 32, true>(p, in, out, F, st) : launch_padded<32, 32, false>(p, in, out, F, st); break;
             case 512: rc = str ? launch_padded<32, 16, true>(p, in, out, F, st) : launch_padded<32, 16, false>(p, in, out, F, st); break;

@@ -58,6 +58,7 @@ template <int RT, int R2, int C, int NSLOT, int MINB, bool FUSED>
 __global__ void __launch_bounds__(256, MINB)
 fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ Wn,
                 const double2* __restrict__ tw, i64 ntiles, int tiles_per_outer, i64 inner, int axis, int red_add,
+                int nv,      // samples per pencil in memory (< N: zero-padded plan -- the rows past nv are the TMA's zero fill)
                 const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ FuseDev F) {
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T, NW = 8;
@@ -124,7 +125,7 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
         const int o = (int)(id / tiles_per_outer);
         const int c0 = (int)(id - (i64)o * tiles_per_outer) * C;
         const bool vab = c0 + 2 * cp < inner;      // this lane's pencil pair exists (inner is even)
-        const i64 lin0 = vab ? (i64)o * N * inner + c0 + 2 * cp : 0;      // sample 0 of pencil a (b: + 1)
+        const i64 lin0 = vab ? (i64)o * nv * inner + c0 + 2 * cp : 0;     // sample 0 of pencil a (b: + 1)
         double2 x[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) x[r] = *reinterpret_cast<const double2*>(slot + col(r * R2 + t));
@@ -217,9 +218,9 @@ fft_tile_kernel(const double* __restrict__ in, double* __restrict__ out, const d
                 for (int q = 0; q < 2 * TPW; ++q) {
                     const i64 cc = c0 + (i64)(wg * TPW) * 2 + q;
                     if (cc < inner)
-                        fft_slow_pencil<FUSED>(in, out, (i64)o * N * inner + cc, inner, axis, N, LRT + LR2,
+                        fft_slow_pencil<FUSED>(in, out, (i64)o * nv * inner + cc, inner, axis, N, LRT + LR2,
                                                reinterpret_cast<double2*>(slot + (size_t)(wg * TPW + (q >> 1)) * N * 16),
-                                               Wn, tw, F, N);
+                                               Wn, tw, F, nv);
                 }
             }
             ft_group_bar(1 + grp, 32 * WPT);
@@ -286,8 +287,8 @@ int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& 
     const i64 tpo = (p->inner + C - 1) / C;
     const i64 ntiles = p->outer * tpo;
     CUtensorMap tmi, tmo;
-    int rc = ft_make_tmap(&tmi, in, p->outer, N, p->inner, C, BR);
-    if (!rc) rc = ft_make_tmap(&tmo, out, p->outer, N, p->inner, C, BR);
+    int rc = ft_make_tmap(&tmi, in, p->outer, p->n, p->inner, C, BR);      // p->n rows in memory (== N unless zero-padded)
+    if (!rc) rc = ft_make_tmap(&tmo, out, p->outer, p->n, p->inner, C, BR);
     if (rc) return rc;
     const size_t smem = (size_t)NSLOT * N * C * 8 + (size_t)2 * N * 16 + 2 * NSLOT * 8 + NG * 8 + 16;
     i64 g = (ntiles + NG - 1) / NG;                      // at least one tile per group
@@ -297,11 +298,11 @@ int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& 
         NG_FUNC_SMEM(smem, fft_tile_kernel<RT, R2, C, NSLOT, MINB, FU>);                                            \
         fft_tile_kernel<RT, R2, C, NSLOT, MINB, FU><<<(unsigned)g, 256, smem, st>>>(                                \
             in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, ntiles, (int)tpo, p->inner, p->axis, red_add, \
-            tmi, tmo, F);                                                                                           \
+            (int)p->n, tmi, tmo, F);                                                                                           \
     } while (0)
     if (F.any) NG_FFT_TILE(true); else NG_FFT_TILE(false);
 #undef NG_FFT_TILE
-    NG_TRACE(F.any ? (red_add ? "fft_tile<fused,add>" : "fft_tile<fused>") : "fft_tile");
+    NG_TRACE(F.any ? (red_add ? "fft_tile<fused,add>" : "fft_tile<fused>") : p->fft_len != p->n ? "fft_tile<padded>" : "fft_tile");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -313,7 +314,8 @@ int launch_tile(const ng_plan* p, const double* in, double* out, const FuseDev& 
 int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
                            bool* handled) {
     *handled = false;
-    if (p->inner == 1 || p->fft_len != p->n || !p->d_Wn || !p->d_twn) return NG_OK;
+    if (p->inner == 1 || !p->d_Wn || !p->d_twn) return NG_OK;
+    if (p->fft_len != p->n && (F.any || p->n > p->fft_len)) return NG_OK;      // zero-padded plans: plain applies
     if (NG_ENV_INT("NG_FFT_TILE", 1) == 0) return NG_OK;        // A/B: 0 = strided register kernel
     if ((p->inner & 1) || p->inner < 16 || ((((uintptr_t)in | (uintptr_t)out) & 15) != 0)) return NG_OK;
     if (p->outer > 0x7fffffff || p->inner > 0x7fffffff) return NG_OK;
@@ -330,7 +332,7 @@ int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, cons
         }
     }
     int rc = NG_OK;
-    switch (p->n) {
+    switch (p->fft_len) {
         case 1024: rc = launch_tile<32, 32, 8, 3, 1>(p, in, out, F, red_add, st); break;
         case 512: rc = launch_tile<32, 16, 16, 3, 1>(p, in, out, F, red_add, st); break;
         case 256: rc = launch_tile<16, 16, 16, 3, 2>(p, in, out, F, red_add, st); break;
