@@ -173,12 +173,16 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
 //     completing on the CONSUMER's own mbarrier so that a fast warp can never observe a stale phase.
 // Shared memory: 2 tables + NW exchange buffers + NSTAGE stages = (2 + 8 + 4) * 16 KB = 224 KB.
 // -------------------------------------------------------------------------------------------------
-template <int RT, int R2, bool FUSED, int NW, int NSTAGE>
+// PAD: zero-padded plan (ng_fft_plan_create_padded): a pencil has nv <= N samples in memory (nv even), the rest of the
+// N-point transform is zero; a unit's pencils are still ONE contiguous run (one bulk copy); plain applies only.
+template <int RT, int R2, bool FUSED, int NW, int NSTAGE, bool PAD = false>
 __global__ void __launch_bounds__(32 * NW, 1)
 fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
                      const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil,
-                     const __grid_constant__ FuseDev F) {   // (address taken for the rare slow path: no local copy)
+                     const __grid_constant__ FuseDev F, int nv) {   // (F: address taken for the rare slow path: no local copy)
+    static_assert(!(PAD && FUSED), "padded transforms are plain applies");
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
+    const int NV = PAD ? nv : N;                 // samples per pencil in memory
     constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
     constexpr int PPU = 2 * TPW;                 // pencils per warp unit
     constexpr int UNIT = PPU * N;                // doubles per unit (16 KB)
@@ -208,13 +212,13 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
     auto issue = [&](i64 jl) {                   // one lane: unit jl of this CTA -> stage jl % NSTAGE
         const i64 p0 = (jl * gridDim.x + blockIdx.x) * PPU;
         const i64 left = npencil - p0;
-        const unsigned bytes = (unsigned)((left < PPU ? left : PPU) * N * 8);
+        const unsigned bytes = (unsigned)((left < PPU ? left : PPU) * NV * 8);
         unsigned long long* bar = bars + (int)(jl % NW);
         pf_mbar_expect_tx(bar, bytes);
-        pf_bulk_g2s(rawall + (size_t)(jl % NSTAGE) * UNIT, in + p0 * N, bytes, bar);
+        pf_bulk_g2s(rawall + (size_t)(jl % NSTAGE) * UNIT, in + p0 * NV, bytes, bar);
     };
     if (warp < NSTAGE && lane == 0 && warp < njl) issue(warp);
-    const double* raw = rawall + (size_t)(warp % NSTAGE) * UNIT + (size_t)(2 * tr) * N;
+    const double* raw = rawall + (size_t)(warp % NSTAGE) * UNIT + (size_t)(2 * tr) * NV;
     unsigned long long* mybar = bars + warp;
     unsigned phase = 0;
     for (i64 jl = warp; jl < njl; jl += NW) {
@@ -229,7 +233,8 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
-            x[r] = make_double2(va ? raw[idx] : 0.0, vb ? raw[N + idx] : 0.0);
+            const bool in_mem = !PAD || idx < NV;
+            x[r] = make_double2(va && in_mem ? raw[idx] : 0.0, vb && in_mem ? raw[NV + idx] : 0.0);
         }
         if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb);
         __syncwarp();                              // the stage is drained
@@ -293,9 +298,9 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             const i64 p0 = (jl * gridDim.x + blockIdx.x) * PPU;
             for (int q = 0; q < PPU; ++q)
                 if (p0 + q < npencil)
-                    fft_slow_pencil<FUSED>(in, out, (p0 + q) * N, 1, F.vec_axis, N, LRT + LR2,
+                    fft_slow_pencil<FUSED>(in, out, (p0 + q) * NV, 1, F.vec_axis, N, LRT + LR2,
                                            reinterpret_cast<double2*>(Sall + (size_t)(warp * TPW + (q >> 1)) * N * 16),
-                                           Wn, tw, F, N);
+                                           Wn, tw, F, NV);
             continue;
         }
         if (FUSED) {
@@ -304,18 +309,19 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             tb.init(F, vb ? pb * N : 0, 1, F.vec_axis, t, R2);
             pencil_tail_all<RT>(F, ta, tb, x);
         }
-        double* const oa = out + pa * N;
-        double* const ob = oa + N;
+        double* const oa = out + pa * NV;
+        double* const ob = oa + NV;
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const int idx = r * R2 + t;
+            if (PAD && idx >= NV) continue;
             if (va) oa[idx] = x[r].x;
             if (vb) ob[idx] = x[r].y;
         }
     }
 }
 
-template <int RT, int R2, int NW, int NSTAGE>
+template <int RT, int R2, int NW, int NSTAGE, bool PAD = false>
 int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st) {
     constexpr int T = R2, TPW = 32 / T, N = RT * R2, PPU = 2 * TPW;
     const i64 npencil = p->outer;
@@ -325,20 +331,21 @@ int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& 
 #define NG_FFT2_RING(FU)                                                                          \
     do {                                                                                          \
         static int per_sm = 0;                           /* persistent: resident CTAs per SM */   \
-        NG_FUNC_SMEM(smem, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>);                         \
+        NG_FUNC_SMEM(smem, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE, PAD>);                    \
         if (!per_sm) {                                                                            \
             int occ = 0;                                                                          \
             NG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                             \
-                &occ, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE>, 32 * NW, smem));              \
+                &occ, fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE, PAD>, 32 * NW, smem));         \
             per_sm = occ > 0 ? occ : 1;                                                           \
         }                                                                                         \
         if (g > (i64)148 * per_sm) g = (i64)148 * per_sm;                                         \
-        fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE><<<(unsigned)g, 32 * NW, smem, st>>>(         \
-            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F);              \
+        fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE, PAD><<<(unsigned)g, 32 * NW, smem, st>>>(    \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F, (int)p->n);   \
     } while (0)
-    if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false);
+    if constexpr (PAD) { NG_FFT2_RING(false); }
+    else { if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false); }
 #undef NG_FFT2_RING
-    NG_TRACE("fft2pass_ring");
+    NG_TRACE(PAD ? "fft2pass_ring<padded>" : "fft2pass_ring");
     NG_LAUNCH_CHECK();
     return NG_OK;
 }
@@ -407,6 +414,15 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
         if (str) {                                          // strided pencils: TMA tiles (fft_tile.cu), rows past n zero-filled
             rc = ng_fft_tile_try_launch(p, in, out, F, st, handled);
             if (rc || *handled) return rc;
+        }
+        // contiguous pencils, enough of them, an even length: the persistent ring kernel (one bulk copy per unit)
+        if (!str && NG_ENV_INT("NG_FFT_PREFETCH", 1) != 0 && (((uintptr_t)in & 15) == 0) && p->outer >= 2 * 148 * 6 && p->n % 2 == 0) {
+            switch (p->fft_len) {
+                case 1024: rc = launch_ring<32, 32, 8, 4, true>(p, in, out, F, st); *handled = (rc == NG_OK); return rc;
+                case 512: rc = launch_ring<32, 16, 8, 4, true>(p, in, out, F, st); *handled = (rc == NG_OK); return rc;
+                case 256: rc = launch_ring<16, 16, 16, 8, true>(p, in, out, F, st); *handled = (rc == NG_OK); return rc;
+                default: break;
+            }
         }
         switch (p->fft_len) {
             case 1024: rc = str ? launch_padded<32, 32, true>(p, in, out, F, st) : launch_padded<32, 32, false>(p, in, out, F, st); break;
