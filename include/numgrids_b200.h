@@ -234,6 +234,12 @@ enum ng_coef_kind {
 int ng_curv_plan_create(int ndim, const int64_t* shape, ng_plan* const* axis_plans, ng_plan** out);
 int ng_curv_set_coef(ng_plan* plan, int kind, int index, const double* h_values, int64_t count,
                      const int64_t* stride);
+/* Optional: sq = a plan of the same shape and axis whose multiplier is the SQUARE of axis_plans[axis]'s (a periodic
+ * axis: D applied twice as one transform).  ng_curv_laplacian then evaluates D(c D f) as c * (D D f) on that axis
+ * whenever the registered J/h_axis**2 table does not vary along it (numgrids/curvilinear.py:235-244 applies D twice;
+ * for such c the two are the same operator, and the single transform carries less rounding).  The plan must outlive
+ * the curvilinear plan. */
+int ng_curv_set_axis_square(ng_plan* plan, int axis, const ng_plan* sq);
 int ng_curv_laplacian(ng_plan* plan, const double* d_f, double* d_out, void* stream);
 int ng_curv_gradient(ng_plan* plan, const double* d_f, double* const* d_out, void* stream);
 int ng_curv_divergence(ng_plan* plan, const double* const* d_v, double* d_out, void* stream);

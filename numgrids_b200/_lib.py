@@ -83,6 +83,7 @@ SIGNATURES = {
     "ng_slab_timed_out": (C.c_int, [_P]),
     "ng_curv_plan_create": (C.c_int, [C.c_int, _I64, _PP, _PP]),
     "ng_curv_set_coef": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int64, _I64]),
+    "ng_curv_set_axis_square": (C.c_int, [_P, C.c_int, _P]),
     "ng_curv_laplacian": (C.c_int, [_P, _P, _P, _P]),
     "ng_curv_gradient": (C.c_int, [_P, _P, _PP, _P]),
     "ng_curv_divergence": (C.c_int, [_P, _PP, _P, _P]),

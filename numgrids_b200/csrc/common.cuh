@@ -169,6 +169,7 @@ struct ng_plan {
         cCurl[NG_MAX_DIM];
     double* d_work = nullptr;
     void* d_curvlap = nullptr;   // parameter block of the single-pass Laplacian (curvlap3d.cu)
+    const ng_plan* axis_sq[NG_MAX_DIM] = {nullptr, nullptr, nullptr, nullptr};   // PK_CURV: D o D as one apply (periodic axes)
 
     // PK_SLAB
     void* slab = nullptr;        // SlabState (slab.cu): local Laplacian plan, peer pointers, side stream, events

@@ -129,6 +129,17 @@ int ng_curv_set_coef(ng_plan* p, int kind, int index, const double* h_values, in
     return NG_OK;
 }
 
+int ng_curv_set_axis_square(ng_plan* p, int axis, const ng_plan* sq) {
+    int rc = check_curv(p, "ng_curv_set_axis_square");
+    if (rc) return rc;
+    NG_REQUIRE(axis >= 0 && axis < p->ndim, "ng_curv_set_axis_square: bad axis %d", axis);
+    bool ok = sq && sq->kind == PK_FFT && sq->ndim == p->ndim && sq->axis == axis;
+    for (int b = 0; ok && b < p->ndim; ++b) ok = sq->shape[b] == p->shape[b];
+    NG_REQUIRE(ok, "ng_curv_set_axis_square: a periodic-axis plan of the same shape along axis %d is required", axis);
+    p->axis_sq[axis] = sq;
+    return NG_OK;
+}
+
 int ng_curv_laplacian(ng_plan* p, const double* d_f, double* d_out, void* stream) {
     int rc = check_curv(p, "ng_curv_laplacian");
     if (rc) return rc;
@@ -148,6 +159,14 @@ int ng_curv_laplacian(ng_plan* p, const double* d_f, double* d_out, void* stream
         FuseDev F2 = base_fuse(D);
         if (i == 0) F2.add_zero = 1; else F2.addend = d_out;
         if (i == p->ndim - 1) { F2.div = to_dev(p->cJ); F2.finite = 1; }
+        if (p->axis_sq[i] && p->cLap[i].stride[i] == 0 && NG_ENV_INT("NG_CURV_SQUARE", 1) != 0) {
+            // periodic axis, coefficient constant along it: D(c D f) = c (D D f) -- ONE transform with the squared
+            // multiplier, then the multiply as the apply's `post` (a non-finite c gives the same non-finite row)
+            F2.post = to_dev(p->cLap[i]);
+            rc = ng_apply_any(p->axis_sq[i], d_f, d_out, F2, st);
+            if (rc) return rc;
+            continue;
+        }
         if (ng_fft_twice_supported(D)) {
             // periodic axis: D_i, the multiply and D_i again in one launch -- the pencil pair stays in registers
             F2.mid = to_dev(p->cLap[i]);

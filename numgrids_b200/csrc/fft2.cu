@@ -31,7 +31,6 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
                 const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil, i64 inner, int axis,
                 int pair16,   // STR: the two pencils of a pair are one aligned 16-byte element of every row
                      const __grid_constant__ FuseDev F, int nv) {   // (address taken for the rare slow path: no local copy)
-    static_assert(!(PAD && FUSED), "padded transforms are plain applies");
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
     const int NV = PAD ? nv : N;                       // samples per pencil in memory
     constexpr int PITCH = R2 + 1, UNITS = RT * PITCH;
@@ -52,6 +51,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         return o * NV * inner + (p - o * inner);
     };
     const i64 ba = va ? pencil_base(pa) : 0, bb = vb ? pencil_base(pb) : 0;
+    const int rv = PAD ? (NV - t + R2 - 1) / R2 : RT;      // this lane's samples r*R2 + t < NV (zero-padded plans)
 
     // multi-index of sample 0 of each pencil (one unravel per pencil; the FFT axis is the innermost
     // non-unit axis, so sample idx only changes that coordinate)
@@ -75,7 +75,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
             }
             x[r] = make_double2(a, b);
         }
-        if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb);
+        if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb, rv);
     }
     // double apply (FuseDev::mid): the transform runs twice with the pointwise multiply between, the pair stays
     // in registers; a run-time loop, so the unrolled body exists once
@@ -84,7 +84,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
     for (int rep = 0; rep < nrep; ++rep) {
     if (FUSED && rep == 1) {
         const PencilCoef ma = pencil_coef(F, F.mid, ba, ax, t, R2), mb = pencil_coef(F, F.mid, bb, ax, t, R2);
-        pencil_mul_all<RT>(x, ma, mb, va, vb);
+        pencil_mul_all<RT>(x, ma, mb, va, vb, rv);            // (also zeroes the padding again: `work` has NV samples)
     }
     dif_forward<RT>(x);
 #pragma unroll
@@ -144,7 +144,7 @@ fft2pass_kernel(const double* __restrict__ in, double* __restrict__ out,
         PencilTail ta, tb;
         ta.init(F, ba, step, ax, t, R2);
         tb.init(F, bb, step, ax, t, R2);
-        pencil_tail_all<RT>(F, ta, tb, x);
+        pencil_tail_all<RT>(F, ta, tb, x, rv);
     }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(32 * NW, 1)
 fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
                      const double2* __restrict__ Wn, const double2* __restrict__ tw, i64 npencil,
                      const __grid_constant__ FuseDev F, int nv) {   // (F: address taken for the rare slow path: no local copy)
-    static_assert(!(PAD && FUSED), "padded transforms are plain applies");
     constexpr int N = RT * R2, T = R2, G = RT / R2, TPW = 32 / T;
     const int NV = PAD ? nv : N;                 // samples per pencil in memory
     constexpr int LRT = Log2<RT>::v, LR2 = Log2<R2>::v;
@@ -218,6 +217,7 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         pf_bulk_g2s(rawall + (size_t)(jl % NSTAGE) * UNIT, in + p0 * NV, bytes, bar);
     };
     if (warp < NSTAGE && lane == 0 && warp < njl) issue(warp);
+    const int rv = PAD ? (NV - t + R2 - 1) / R2 : RT;       // this lane's samples r*R2 + t < NV (zero-padded plans)
     const double* raw = rawall + (size_t)(warp % NSTAGE) * UNIT + (size_t)(2 * tr) * NV;
     unsigned long long* mybar = bars + warp;
     unsigned phase = 0;
@@ -226,7 +226,7 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         const bool va = pa < npencil, vb = pb < npencil;
         PencilCoef ca, cb;
         const bool pre = FUSED && F.pre.ptr;
-        if (pre) { ca = pencil_pre(F, va ? pa * N : 0, F.vec_axis, t, R2); cb = pencil_pre(F, vb ? pb * N : 0, F.vec_axis, t, R2); }
+        if (pre) { ca = pencil_pre(F, va ? pa * NV : 0, F.vec_axis, t, R2); cb = pencil_pre(F, vb ? pb * NV : 0, F.vec_axis, t, R2); }
         pf_mbar_wait(mybar, phase);
         phase ^= 1;
         double2 x[RT];
@@ -236,7 +236,7 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
             const bool in_mem = !PAD || idx < NV;
             x[r] = make_double2(va && in_mem ? raw[idx] : 0.0, vb && in_mem ? raw[NV + idx] : 0.0);
         }
-        if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb);
+        if (pre) pencil_mul_all<RT>(x, ca, cb, va, vb, rv);
         __syncwarp();                              // the stage is drained
         if (lane == 0 && jl + NSTAGE < njl) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -246,9 +246,9 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
 #pragma unroll 1
         for (int rep = 0; rep < nrep; ++rep) {
         if (FUSED && rep == 1) {
-            const PencilCoef ma = pencil_coef(F, F.mid, va ? pa * N : 0, F.vec_axis, t, R2),
-                             mb = pencil_coef(F, F.mid, vb ? pb * N : 0, F.vec_axis, t, R2);
-            pencil_mul_all<RT>(x, ma, mb, va, vb);
+            const PencilCoef ma = pencil_coef(F, F.mid, va ? pa * NV : 0, F.vec_axis, t, R2),
+                             mb = pencil_coef(F, F.mid, vb ? pb * NV : 0, F.vec_axis, t, R2);
+            pencil_mul_all<RT>(x, ma, mb, va, vb, rv);
         }
         dif_forward<RT>(x);
 #pragma unroll
@@ -305,9 +305,9 @@ fft2pass_ring_kernel(const double* __restrict__ in, double* __restrict__ out,
         }
         if (FUSED) {
             PencilTail ta, tb;
-            ta.init(F, va ? pa * N : 0, 1, F.vec_axis, t, R2);
-            tb.init(F, vb ? pb * N : 0, 1, F.vec_axis, t, R2);
-            pencil_tail_all<RT>(F, ta, tb, x);
+            ta.init(F, va ? pa * NV : 0, 1, F.vec_axis, t, R2);
+            tb.init(F, vb ? pb * NV : 0, 1, F.vec_axis, t, R2);
+            pencil_tail_all<RT>(F, ta, tb, x, rv);
         }
         double* const oa = out + pa * NV;
         double* const ob = oa + NV;
@@ -342,8 +342,7 @@ int launch_ring(const ng_plan* p, const double* in, double* out, const FuseDev& 
         fft2pass_ring_kernel<RT, R2, FU, NW, NSTAGE, PAD><<<(unsigned)g, 32 * NW, smem, st>>>(    \
             in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, F, (int)p->n);   \
     } while (0)
-    if constexpr (PAD) { NG_FFT2_RING(false); }
-    else { if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false); }
+    if (F.any) NG_FFT2_RING(true); else NG_FFT2_RING(false);
 #undef NG_FFT2_RING
     NG_TRACE(PAD ? "fft2pass_ring<padded>" : "fft2pass_ring");
     NG_LAUNCH_CHECK();
@@ -381,10 +380,15 @@ int launch_padded(const ng_plan* p, const double* in, double* out, const FuseDev
     const i64 per_block = (i64)WARPS * TPW;
     const unsigned grid = (unsigned)((pairs + per_block - 1) / per_block);
     const size_t smem = (size_t)WARPS * TPW * RT * (R2 + 1) * sizeof(double2);
-    NG_FUNC_SMEM(smem, fft2pass_kernel<RT, R2, false, 1, STR, true>);
-    fft2pass_kernel<RT, R2, false, 1, STR, true><<<grid, 32 * WARPS, smem, st>>>(
-        in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, p->inner, p->axis,
-        (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F, (int)p->n);
+#define NG_FFT2_PAD(FU)                                                                           \
+    do {                                                                                          \
+        NG_FUNC_SMEM(smem, fft2pass_kernel<RT, R2, FU, 1, STR, true>);                            \
+        fft2pass_kernel<RT, R2, FU, 1, STR, true><<<grid, 32 * WARPS, smem, st>>>(                \
+            in, out, (const double2*)p->d_Wn, (const double2*)p->d_twn, npencil, p->inner, p->axis,    \
+            (int)(STR && p->inner % 2 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0)), F, (int)p->n);   \
+    } while (0)
+    if (F.any) NG_FFT2_PAD(true); else NG_FFT2_PAD(false);
+#undef NG_FFT2_PAD
     NG_TRACE(STR ? "fft2pass<strided,padded>" : "fft2pass<padded>");
     NG_LAUNCH_CHECK();
     return NG_OK;
@@ -394,8 +398,10 @@ int launch_padded(const ng_plan* p, const double* in, double* out, const FuseDev
 
 // A fused apply with FuseDev::mid (double apply) is honoured exactly when ng_fft2_try_launch takes the plan.
 bool ng_fft_twice_supported(const ng_plan* p) {
-    if (p->kind != PK_FFT || !p->fft_pow2 || !p->d_Wn || !p->d_twn || p->fft_len != p->n) return false;
+    if (p->kind != PK_FFT || !p->fft_pow2 || !p->d_Wn || !p->d_twn) return false;
     if (NG_ENV_INT("NG_FFT_TWOPASS", 1) == 0 || NG_ENV_INT("NG_FFT_TWICE", 1) == 0) return false;
+    if (p->fft_len != p->n)                                  // zero-padded plans: the 256 / 512 / 1024-point kernels
+        return p->fft_len == 256 || p->fft_len == 512 || p->fft_len == 1024;
     if (p->inner != 1 && NG_ENV_INT("NG_FFT_STRIDED", 1) == 0) return false;
     return p->n == 64 || p->n == 128 || p->n == 256 || p->n == 512 || p->n == 1024;
 }
@@ -408,8 +414,7 @@ int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const Fu
     if (NG_ENV_INT("NG_FFT_TWOPASS", 1) == 0) return NG_OK;
     int rc = NG_OK;
     if (p->fft_len != p->n) {
-        // zero-padded plan (any axis length): plain applies on the two-pass kernel, fused ones on the radix-2 kernel
-        if (F.any) return NG_OK;
+        // zero-padded plan (any axis length): the two-pass kernels up to a 1024-point transform, the radix-2 kernel above
         const bool str = p->inner != 1;
         if (str) {                                          // strided pencils: TMA tiles (fft_tile.cu), rows past n zero-filled
             rc = ng_fft_tile_try_launch(p, in, out, F, st, handled);

@@ -115,7 +115,8 @@ __device__ __noinline__ void fft_slow_pencil(const double* __restrict__ in, doub
         if (rep == 1) {
             for (int k = lane; k < N; k += 32) {
                 ix.i[ax] = k;
-                double v = __dmul_rn(F.mid.ptr[coef_off(F.mid, ix)], S[k].x);
+                double v = 0.0;                              // (zero-padded plans: `work` has nv samples, the rest is padding)
+                if (k < nv) v = __dmul_rn(F.mid.ptr[coef_off(F.mid, ix)], S[k].x);
                 if (ng_nonfinite(v)) { bad = true; v = 0.0; }
                 S[k] = make_double2(v, 0.0);
             }
@@ -214,8 +215,10 @@ struct PencilTail {
 // branches OUTSIDE the unrolled loops: per element the same operations in the same order as fuse_tail, but ~10
 // branches per pair instead of ~10 per sample (ncu on the cfg4 gradient: 6.8 BRA + 7.6 BSSY/BSYNC + 15 ISETP per
 // point and 5.4 instruction-fetch stalls per issue with the per-sample form).
+// rv (zero-padded plans): only this lane's samples r < rv exist in memory -- operands are fetched for those only (the
+// rest of the register array is the transform's padding: forced to zero by pencil_mul_all, never stored).
 template <int RT>
-__device__ __forceinline__ void pencil_mul_all(double2* x, const PencilCoef& ca, const PencilCoef& cb, bool va, bool vb) {
+__device__ __forceinline__ void pencil_mul_all(double2* x, const PencilCoef& ca, const PencilCoef& cb, bool va, bool vb, int rv = RT) {
     // x[r] *= coefficient; an absent pencil stays exactly zero (its table entries are pencil 0's and may be non-finite)
     if (ca.step == 0) {
         const double a = ca.c, b = cb.c;
@@ -223,18 +226,20 @@ __device__ __forceinline__ void pencil_mul_all(double2* x, const PencilCoef& ca,
         for (int r = 0; r < RT; ++r) { x[r].x = __dmul_rn(a, x[r].x); x[r].y = __dmul_rn(b, x[r].y); }
     } else {
 #pragma unroll
-        for (int r = 0; r < RT; ++r) { x[r].x = __dmul_rn(ca.p[r * ca.step], x[r].x); x[r].y = __dmul_rn(cb.p[r * cb.step], x[r].y); }
+        for (int r = 0; r < RT; ++r)
+            if (r < rv) { x[r].x = __dmul_rn(ca.p[r * ca.step], x[r].x); x[r].y = __dmul_rn(cb.p[r * cb.step], x[r].y); }
     }
-    if (!va || !vb) {
+    if (!va || !vb || rv < RT) {
 #pragma unroll
-        for (int r = 0; r < RT; ++r) { if (!va) x[r].x = 0.0; if (!vb) x[r].y = 0.0; }
+        for (int r = 0; r < RT; ++r) { if (!va || r >= rv) x[r].x = 0.0; if (!vb || r >= rv) x[r].y = 0.0; }
     }
 }
 template <int RT>
-__device__ __forceinline__ void pencil_tail_all(const FuseDev& F, const PencilTail& ta, const PencilTail& tb, double2* x) {
+__device__ __forceinline__ void pencil_tail_all(const FuseDev& F, const PencilTail& ta, const PencilTail& tb, double2* x, int rv = RT) {
     if (ta.minuend) {
 #pragma unroll
-        for (int r = 0; r < RT; ++r) { x[r].x = __dsub_rn(ta.minuend[r * ta.mstep], x[r].x); x[r].y = __dsub_rn(tb.minuend[r * tb.mstep], x[r].y); }
+        for (int r = 0; r < RT; ++r)
+            if (r < rv) { x[r].x = __dsub_rn(ta.minuend[r * ta.mstep], x[r].x); x[r].y = __dsub_rn(tb.minuend[r * tb.mstep], x[r].y); }
     }
     if (ta.post.p) {
         if (ta.post.step == 0) {
@@ -243,12 +248,14 @@ __device__ __forceinline__ void pencil_tail_all(const FuseDev& F, const PencilTa
             for (int r = 0; r < RT; ++r) { x[r].x = __dmul_rn(a, x[r].x); x[r].y = __dmul_rn(b, x[r].y); }
         } else {
 #pragma unroll
-            for (int r = 0; r < RT; ++r) { x[r].x = __dmul_rn(ta.post.p[r * ta.post.step], x[r].x); x[r].y = __dmul_rn(tb.post.p[r * tb.post.step], x[r].y); }
+            for (int r = 0; r < RT; ++r)
+                if (r < rv) { x[r].x = __dmul_rn(ta.post.p[r * ta.post.step], x[r].x); x[r].y = __dmul_rn(tb.post.p[r * tb.post.step], x[r].y); }
         }
     }
     if (ta.addend) {
 #pragma unroll
-        for (int r = 0; r < RT; ++r) { x[r].x = __dadd_rn(ta.addend[r * ta.mstep], x[r].x); x[r].y = __dadd_rn(tb.addend[r * tb.mstep], x[r].y); }
+        for (int r = 0; r < RT; ++r)
+            if (r < rv) { x[r].x = __dadd_rn(ta.addend[r * ta.mstep], x[r].x); x[r].y = __dadd_rn(tb.addend[r * tb.mstep], x[r].y); }
     } else if (F.add_zero) {
 #pragma unroll
         for (int r = 0; r < RT; ++r) { x[r].x = __dadd_rn(0.0, x[r].x); x[r].y = __dadd_rn(0.0, x[r].y); }
@@ -260,7 +267,8 @@ __device__ __forceinline__ void pencil_tail_all(const FuseDev& F, const PencilTa
             for (int r = 0; r < RT; ++r) { x[r].x = __ddiv_rn(x[r].x, a); x[r].y = __ddiv_rn(x[r].y, b); }
         } else {
 #pragma unroll
-            for (int r = 0; r < RT; ++r) { x[r].x = __ddiv_rn(x[r].x, ta.div.p[r * ta.div.step]); x[r].y = __ddiv_rn(x[r].y, tb.div.p[r * tb.div.step]); }
+            for (int r = 0; r < RT; ++r)
+                if (r < rv) { x[r].x = __ddiv_rn(x[r].x, ta.div.p[r * ta.div.step]); x[r].y = __ddiv_rn(x[r].y, tb.div.p[r * tb.div.step]); }
         }
     }
     if (F.finite) {

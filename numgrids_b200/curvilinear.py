@@ -69,7 +69,15 @@ class CurvilinearGrid(Grid):
             out = C.c_void_p()
             _lib.check(lib.ng_curv_plan_create(self.ndims, shp_p, arr, C.byref(out)),
                        "ng_curv_plan_create")
-            self._curv_plan = _lib.Plan(out.value, keepalive=children)
+            keep = list(children)
+            from .diff import FFTDiff
+            for i in range(self.ndims):             # periodic axes: D applied twice as ONE transform (see make_square_plan)
+                op = self._diff_ops[i].operator
+                if isinstance(op, FFTDiff):
+                    sq = op.make_square_plan()
+                    _lib.check(lib.ng_curv_set_axis_square(out, i, sq.handle), "ng_curv_set_axis_square")
+                    keep.append(sq)
+            self._curv_plan = _lib.Plan(out.value, keepalive=keep)
         return self._curv_plan
 
     def _register(self, kind, index, make):

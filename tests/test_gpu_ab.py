@@ -59,15 +59,28 @@ def test_laplacian_double_apply_equals_two_launches(gpu_ready, kind):
     lib = _lib.load()
     outs = {}
     try:
+        os.environ["NG_CURV_SQUARE"] = "0"          # (the default evaluates c * (D D f) as ONE transform, see below)
         for mode in ("1", "0"):
             os.environ["NG_FFT_TWICE"] = mode
             lib.ng_tuning_reload()
             n0 = _lib.launch_count()
             outs[mode] = g.laplacian(fd).cpu().numpy()
             outs[mode + "n"] = _lib.launch_count() - n0
+        os.environ.pop("NG_CURV_SQUARE")
+        lib.ng_tuning_reload()
+        n0 = _lib.launch_count()
+        outs["sq"] = g.laplacian(fd).cpu().numpy()
+        outs["sqn"] = _lib.launch_count() - n0
     finally:
         os.environ.pop("NG_FFT_TWICE", None)
+        os.environ.pop("NG_CURV_SQUARE", None)
         lib.ng_tuning_reload()
+    # default path: the built-in metrics' J/h_phi**2 does not vary along phi, so D(c D f) = c (D D f) is ONE transform
+    # with the squared multiplier (ng_curv_set_axis_square): same operator, same launch count as the double apply,
+    # agreement to rounding
+    assert outs["sqn"] == outs["1n"], (outs["sqn"], outs["1n"])
+    assert np.all(np.isfinite(outs["sq"]))
+    assert float(np.max(np.abs(outs["sq"] - outs["1"]))) <= 1e-12 * float(np.max(np.abs(outs["1"])))
     assert outs["1n"] == outs["0n"] - 1, (outs["1n"], outs["0n"])
     assert np.all(np.isfinite(outs["1"])) and np.all(np.isfinite(outs["0"]))
     if kind.endswith("singular"):

@@ -511,3 +511,22 @@ def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
         D = [pencil.make_diff(pax, 1, i) for i in range(2)]
         ref = pencil.laplacian(f, (np.ones_like(R), R), D)
         assert rel_linf(pg.laplacian(f), ref) <= TOL_FFT
+        # enough pencils for the persistent ring kernel (>= 1776): spherical composites with n points in phi --
+        # fused prologue / double apply / tails on zero-padded transforms
+        sg = ng.SphericalGrid(ng.create_axis(A.CHEBYSHEV, 48, 0.5, 2.0), ng.create_axis(A.CHEBYSHEV, 40, 0.3, np.pi - 0.3), p)
+        R, T, P = sg.meshed_coords
+        f = R ** 2 * np.sin(T) ** 2 * np.cos(2 * P) + np.exp(-R) * np.cos(T)
+        pax = [pencil.make_axis("chebyshev", 48, 0.5, 2.0), pencil.make_axis("chebyshev", 40, 0.3, np.pi - 0.3),
+               pencil.make_axis("periodic", n, 0.0, 2 * np.pi)]
+        D = [pencil.make_diff(pax, 1, i) for i in range(3)]
+        h = (np.ones_like(R), R, R * np.sin(T))
+        # (this field is hard on a Laplacian: r^2 sin^2(theta) cos(2 phi) = x^2 - y^2 is harmonic, so its three terms cancel, and
+        # the phi term carries 1 / (r sin theta)^2 <= 46.  The zero-padded transform's rounding -- 3e-13 of D D f, a hundred
+        # times that of a native-length FFT, because the circular-convolution kernel of the derivative decays like 1/j --
+        # shows as 4e-11 of the result at n = 360; at n = 100 it is within the 1e-11 of the contract)
+        assert rel_linf(sg.laplacian(f), pencil.laplacian(f, h, D)) <= (TOL_FFT if n <= 128 else 1e-10)
+        assert _lib.last_kernel() == "fft2pass_ring<padded>", _lib.last_kernel()
+        for got, want in zip(sg.gradient(f), pencil.gradient(f, h, D)):
+            assert rel_linf(got, want) <= TOL_FFT
+        v = (R, np.sin(T), np.cos(P))
+        assert rel_linf(sg.divergence(*v), pencil.divergence(v, h, D)) <= TOL_FFT
