@@ -129,8 +129,10 @@ int ng_apply_fused(const ng_plan* plan, const double* d_in, double* d_out,
 /* `count` fields of the plan's shape stacked contiguously ([count][shape...], in and out): one launch for all of
  * them.  Small grids are launch-bound one field at a time; a stack streams at the large-array rate. */
 int ng_apply_batch(const ng_plan* plan, const double* d_in, double* d_out, int64_t count, void* stream);
-/* Same from host buffers (pinned or pageable): H2D, kernel, D2H, synchronous. */
+/* Same from host buffers (pinned or pageable): H2D, kernel, D2H, synchronous.  The device staging buffers (one input,
+ * one output array) stay with the plan for the next call; ng_plan_release_staging frees them. */
 int ng_apply_host(ng_plan* plan, const double* h_in, double* h_out);
+int ng_plan_release_staging(ng_plan* plan);
 /* Slab variant for a finite-difference plan whose `axis` is sharded across ranks: d_lo_halo /
  * d_hi_halo hold the nb neighbour planes [rows][nb] (rows = product of the other extents) or are
  * NULL on the global boundary, where the one-sided schemes are used. */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "ng_apply_fused": (C.c_int, [_P, _P, _P, C.POINTER(NgFuse), _P]),
     "ng_apply_batch": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "ng_apply_host": (C.c_int, [_P, _P, _P]),
+    "ng_plan_release_staging": (C.c_int, [_P]),
     "ng_fd_apply_slab": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ng_fd_pack_halo": (C.c_int, [_P, _P, _P, _P, _P]),
     "ng_plan_halo_width": (C.c_int, [_P]),

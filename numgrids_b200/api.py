@@ -176,6 +176,8 @@ class CartesianLaplacian:
         out = np.empty_like(a)
         _lib.check(_lib.load().ng_fdlap_apply_host(self.plan.handle, a.ctypes.data, out.ctypes.data),
                    "ng_fdlap_apply_host")
+        if a.nbytes >= (1 << 30):                       # big arrays: hand the two device staging arrays back at once
+            _lib.check(_lib.load().ng_plan_release_staging(self.plan.handle), "ng_plan_release_staging")
         return out
 
 

@@ -379,6 +379,20 @@ int ng_apply_fused(const ng_plan* plan, const double* d_in, double* d_out, const
 // `count` fields of the plan's shape stacked in one array [count][shape...]: along any axis the stack is the
 // same [outer][n][inner] view with `count` times the outer extent, so one launch covers all of them -- a
 // 512 x 512 field is launch-bound on its own (cfg1: 0.2 of the HBM peak), eighty of them stream.
+// The staging arrays of the *_host entry points (16 GiB at 1024^3) belong to the plan until released or destroyed.
+int ng_plan_release_staging(ng_plan* p) {
+    NG_REQUIRE(p != nullptr, "plan is NULL");
+    if (!p->d_stage_in && !p->d_stage_out) return NG_OK;
+    int rc = ng_check_plan_device(p, "ng_plan_release_staging");
+    if (rc) return rc;
+    if (p->d_stage_in) cudaFree(p->d_stage_in);
+    if (p->d_stage_out) cudaFree(p->d_stage_out);
+    p->device_bytes -= sizeof(double) * (p->stage_elems + p->size);
+    p->d_stage_in = p->d_stage_out = nullptr;
+    p->stage_elems = 0;
+    return NG_OK;
+}
+
 int ng_apply_batch(const ng_plan* plan, const double* d_in, double* d_out, int64_t count, void* stream) {
     NG_REQUIRE(plan && d_in && d_out && d_in != d_out, "ng_apply_batch: bad plan or buffers");
     NG_REQUIRE(plan->kind == PK_FD || plan->kind == PK_CHEB || plan->kind == PK_FFT,

@@ -24,6 +24,8 @@ from .axes import EquidistantAxis, LogAxis
 class DeviceOperator:
     """Callable ``f -> D f`` backed by an ``ng_plan`` (created on first use)."""
 
+    STAGING_KEEP_BYTES = 1 << 30     # host-array applies of at least this size free their device staging arrays afterwards
+
     def __init__(self, shape, plan_factory, flexible_shape=False, real_result_only=False):
         self.shape = tuple(int(s) for s in shape)
         self._factory = plan_factory
@@ -81,6 +83,8 @@ class DeviceOperator:
         out = np.empty_like(a)
         _lib.check(_lib.load().ng_apply_host(self.plan.handle, a.ctypes.data, out.ctypes.data),
                    "ng_apply_host")
+        if a.nbytes >= self.STAGING_KEEP_BYTES:         # big arrays: hand the two device staging arrays back at once
+            _lib.check(_lib.load().ng_plan_release_staging(self.plan.handle), "ng_plan_release_staging")
         if _device.is_torch_tensor(f):
             return _device.torch().from_numpy(out)
         return out

@@ -116,3 +116,19 @@ def test_cartesian_laplacian_golden(gpu_ready):
                 d = ng.Diff(g, 2, a, acc=acc)(f)
                 idiom = d if idiom is None else idiom + d
             assert np.array_equal(idiom, out)
+
+
+def test_host_apply_staging_can_be_released(gpu_ready):
+    """ng_apply_host keeps its two device staging arrays with the plan; ng_plan_release_staging hands them back and the
+    next host apply allocates them again (same result)."""
+    from numgrids_b200 import _lib
+    ax = ng.create_axis(ng.AxisType.EQUIDISTANT, 40, 0.0, 1.0)
+    g = ng.Grid(ax, ax)
+    f = np.sin(3 * g.meshed_coords[0]) * g.meshed_coords[1]
+    d = ng.Diff(g, 1, 0)
+    first = d(f)
+    op = d.operator.operator
+    lib = _lib.load()
+    assert lib.ng_plan_release_staging(op.plan.handle) == 0
+    assert lib.ng_plan_release_staging(op.plan.handle) == 0        # idempotent
+    assert np.array_equal(d(f), first)
