@@ -21,8 +21,7 @@ OBJDIR = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "fd.cu", "fd_row.cu", "fd_tile.cu", "dense.cu", "fft.cu", "fft2.cu", "fft_tile.cu", "fdlap.cu", "fdlap3d.cu", "curv.cu", "curvlap3d.cu", "slab.cu", "transpose.cu", "bc.cu", "quad.cu", "interp.cu"]
 # translation units compiled more than once with different macros (object name -> (source, defines)):
 # the contiguous-axis FD kernel is the slowest file to compile; its half widths 3-4 build as a second object
-EXTRA_OBJECTS = {"fd_row_wide.o": ("fd_row.cu", ["-DNG_ROW_PSET=1"]),
-                 "fd_row_modes.o": ("fd_row.cu", ["-DNG_ROW_PSET=2"])}   # P = 2 with compile-time fuse patterns
+EXTRA_OBJECTS = {"fd_row_wide.o": ("fd_row.cu", ["-DNG_ROW_PSET=1"])}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -248,68 +248,25 @@ int launch_row(const ng_plan* p, const double* in, double* out, const FuseDev& F
     return NG_OK;
 }
 
-// the compile-time fuse patterns of the curvilinear composites (curv.cu) for the acc = 4 stencils (P = 2), no halo
-template <int MODE>
-int launch_row_mode(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st, int uu) {
-    const int n = (int)p->n;
-    const i64 rows = p->outer;
-    const int nchunk = (n + 63) / 64;
-    if (uu >= 4) {
-        const int gpr = (nchunk + 3) / 4;
-        fd_row_kernel<2, MODE, false, 4><<<(unsigned)((rows * gpr + 7) / 8), 256, 0, st>>>(
-            in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, nullptr, nullptr, gpr);
-    } else {
-        fd_row_kernel<2, MODE, false, 1><<<(unsigned)((rows * nchunk + 7) / 8), 256, 0, st>>>(
-            in, out, rows, n, p->axis, p->fd, p->d_xdiv, F, nullptr, nullptr, nchunk);
-    }
-    NG_TRACE(uu >= 4 ? "fd_row<u4,mode>" : "fd_row<u1,mode>");
-    NG_LAUNCH_CHECK();
-    return NG_OK;
-}
-
 }  // namespace
 
 // This file is compiled twice (numgrids_b200/build.py) so that the two halves build in parallel:
 // NG_ROW_PSET = 0 instantiates the half widths 1 and 2 and the dispatcher, NG_ROW_PSET = 1 the half widths 3 and 4.
+// (Fused applies of 2^18 points and more run the shared-memory row tiles of fd_tile.cu with compile-time fuse patterns;
+// what reaches the MODE = -1 run-time form here is small, launch-bound arrays and slab halos.)
 #ifndef NG_ROW_PSET
 #define NG_ROW_PSET 0
 #endif
 int ng_fd_row_launch_wide(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
                           const double* lo, const double* hi, cudaStream_t st);
-int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
-                           bool* handled);
 int ng_fd_tile_try_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
                           bool* handled);
-#if NG_ROW_PSET == 2
-// third object: P = 2 with the fuse pattern known at compile time (12 patterns x 2 chunk depths)
-int ng_fd_row_launch_modes(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st,
-                           bool* handled) {
-    *handled = true;
-    const i64 rows = p->outer;
-    const int nchunk = ((int)p->n + 63) / 64;
-    const bool deep = rows * nchunk >= 148LL * 8 * 4 * 4 && nchunk >= 3;
-    const int ue = (int)NG_ENV_INT("NG_FD_ROW_U", 0);
-    const int uu = ue ? ue : (!deep ? 1 : 4);
-    switch (fuse_mask(F)) {
-#define NG_MODE(M) case (M): return launch_row_mode<(M)>(p, in, out, F, st, uu);
-        NG_FD_FUSE_MODES(NG_MODE)
-#undef NG_MODE
-        default: break;
-    }
-    *handled = false;
-    return NG_OK;
-}
-#elif NG_ROW_PSET == 0
+#if NG_ROW_PSET == 0
 int ng_fd_row_launch(int P, const ng_plan* p, const double* in, double* out, const FuseDev& F,
                      const double* lo, const double* hi, cudaStream_t st) {
     if (!lo && !hi) {                                        // shared-memory row tiles (fd_tile.cu)
         bool handled = false;
         const int rc = ng_fd_tile_try_launch(P, p, in, out, F, st, &handled);
-        if (rc || handled) return rc;
-    }
-    if (P == 2 && F.any && !lo && !hi && NG_ENV_INT("NG_FD_ROW_MODES", 1) != 0) {
-        bool handled = false;
-        const int rc = ng_fd_row_launch_modes(p, in, out, F, st, &handled);
         if (rc || handled) return rc;
     }
     switch (P) {
