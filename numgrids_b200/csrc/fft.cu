@@ -14,11 +14,59 @@
 //
 // Other n: the dense real matrix D = Re(F^-1 diag(W) F) (what diff.py:145-157 builds) is applied by
 // the ordered contraction kernel in dense.cu with FMA enabled.
-#include "common.cuh"
+#include "fft_net.cuh"
 
 namespace {
 
 constexpr int FFT_NT = 256;
+
+// shared-memory index with one double of padding per 16: the radix-16 passes below gather at strides of 1, 16, 256 ...
+// elements, and a stride of 16 doubles would put a warp's 32 accesses on one bank
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+
+// One radix-R pass (R = 2^LR) of the in-place transform over the stages s_lo .. s_lo+LR-1 (spans m_lo .. m_lo R/2): the R
+// elements base + q m_lo of a sub-network go through the register network of fft_net.cuh -- the same butterflies as LR
+// radix-2 stages in place, with one shared-memory round trip and one barrier instead of LR -- and the part of the
+// radix-2 twiddles that depends on the position j_lo inside the span collapses into ONE factor per element,
+// exp(-+2 pi i j_lo k / (R m_lo)), k = the element's (bit-reversed) output index.  FWD: DIF (network, then factors);
+// inverse: the conjugate transpose (conjugate factors, then the DIT network).
+template <int LR, bool FWD>
+__device__ __forceinline__ void fft_pass(double* sre, double* sim, const double2* __restrict__ tw, int n, int log2n, int P,
+                                         int s_lo) {
+    constexpr int R = 1 << LR;
+    const int m_lo = 1 << s_lo, per = n >> LR, items = P * per, half = n >> 1;
+    const int sh = log2n - LR - s_lo;                 // table index of angle a / (R m_lo) on the n-point circle: a << sh
+    for (int e = threadIdx.x; e < items; e += FFT_NT) {
+        const int p = e / per, b = e - p * per;
+        const int j_lo = b & (m_lo - 1);
+        const int base = ((b >> s_lo) << (s_lo + LR)) + j_lo + p * n;
+        double2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) { const int i = fpad(base + q * m_lo); x[q] = make_double2(sre[i], sim[i]); }
+        if (FWD) dif_forward<R>(x);
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            const int ti = (j_lo * bitrev(q, LR)) << sh;
+            if (ti != 0) {                            // (j_lo = 0: the whole sub-network has trivial factors)
+                double2 w = tw[ti < half ? ti : ti - half];
+                if (ti >= half) w = make_double2(-w.x, -w.y);
+                x[q] = cmul(x[q], w.x, FWD ? w.y : -w.y);
+            }
+        }
+        if (!FWD) dit_inverse<R>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) { const int i = fpad(base + q * m_lo); sre[i] = x[q].x; sim[i] = x[q].y; }
+    }
+}
+template <bool FWD>
+__device__ __forceinline__ void fft_pass_any(int lr, double* sre, double* sim, const double2* tw, int n, int log2n, int P, int s_lo) {
+    switch (lr) {
+        case 4: fft_pass<4, FWD>(sre, sim, tw, n, log2n, P, s_lo); break;
+        case 3: fft_pass<3, FWD>(sre, sim, tw, n, log2n, P, s_lo); break;
+        case 2: fft_pass<2, FWD>(sre, sim, tw, n, log2n, P, s_lo); break;
+        default: fft_pass<1, FWD>(sre, sim, tw, n, log2n, P, s_lo); break;
+    }
+}
 
 // W_br : [n][2] multipliers in bit-reversed order, pre-divided by n.  tw : [n/2][2] = exp(-2 pi i j/n).
 template <bool LAST, bool FUSED>
@@ -28,12 +76,13 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
                 int log2n, i64 inner, int P, int nv /* samples per pencil in memory (<= n; the rest is zero padding) */,
                 FuseDev F) {
     extern __shared__ double smem[];
-    double* sre = smem;                // [P][n]
-    double* sim = smem + (i64)P * n;   // [P][n]
+    const int plane = fpad(P * n) + 1;
+    double* sre = smem;                // [P][n], padded index fpad()
+    double* sim = smem + plane;
     // A pencil with a non-finite sample (the reference's inf/nan rows on coordinate singularities,
     // numgrids/curvilinear.py:236-244) must not leak into the pencil it shares a complex transform
     // with: it is transformed as zeros and its whole output is NaN, as numpy.fft would make it.
-    int* sbad = reinterpret_cast<int*>(smem + (i64)2 * P * n);   // [2P]
+    int* sbad = reinterpret_cast<int*>(smem + (i64)2 * plane);   // [2P]
     for (int e = threadIdx.x; e < 2 * P; e += FFT_NT) sbad[e] = 0;
     __syncthreads();
     const i64 npencil = outer * inner;
@@ -59,54 +108,35 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
             }
         }
         if (ng_nonfinite(v)) { sbad[pl] = 1; v = 0.0; }
-        ((pl & 1) ? sim : sre)[(pl >> 1) * n + k] = v;
+        ((pl & 1) ? sim : sre)[fpad((pl >> 1) * n + k)] = v;
     }
     __syncthreads();
 
-    const int half = n >> 1;
-    const int nbf = P * half;
-    // ---- forward DIF: spans n/2 .. 1
-    for (int s = log2n - 1; s >= 0; --s) {
-        const int m = 1 << s;
-        for (int e = tid; e < nbf; e += FFT_NT) {
-            const int p = e / half, b = e - p * half;
-            const int j = b & (m - 1);
-            const int i0 = ((b >> s) << (s + 1)) + j + p * n, i1 = i0 + m;
-            const double2 w = tw[j << (log2n - 1 - s)];
-            const double ur = sre[i0], ui = sim[i0], vr = sre[i1], vi = sim[i1];
-            sre[i0] = ur + vr;
-            sim[i0] = ui + vi;
-            const double dr = ur - vr, di = ui - vi;
-            sre[i1] = fma(dr, w.x, -(di * w.y));
-            sim[i1] = fma(dr, w.y, di * w.x);
-        }
+    // ---- forward DIF: radix-16 passes from the widest spans down (the last pass takes what is left: radix 8 / 4 / 2)
+    for (int s_hi = log2n; s_hi > 0;) {
+        const int lr = s_hi >= 4 ? 4 : s_hi;
+        fft_pass_any<true>(lr, sre, sim, tw, n, log2n, P, s_hi - lr);
+        s_hi -= lr;
         __syncthreads();
     }
     // ---- multiply by (ik)^order / n, bit-reversed order
     for (int e = tid; e < P * n; e += FFT_NT) {
         const double2 w = W_br[e & (n - 1)];
-        const double xr = sre[e], xi = sim[e];
-        sre[e] = fma(xr, w.x, -(xi * w.y));
-        sim[e] = fma(xr, w.y, xi * w.x);
+        const int i = fpad(e);
+        const double xr = sre[i], xi = sim[i];
+        sre[i] = fma(xr, w.x, -(xi * w.y));
+        sim[i] = fma(xr, w.y, xi * w.x);
     }
     __syncthreads();
-    // ---- inverse DIT: spans 1 .. n/2, conjugate twiddles
-    for (int s = 0; s < log2n; ++s) {
-        const int m = 1 << s;
-        for (int e = tid; e < nbf; e += FFT_NT) {
-            const int p = e / half, b = e - p * half;
-            const int j = b & (m - 1);
-            const int i0 = ((b >> s) << (s + 1)) + j + p * n, i1 = i0 + m;
-            const double2 w = tw[j << (log2n - 1 - s)];
-            const double ur = sre[i0], ui = sim[i0], xr = sre[i1], xi = sim[i1];
-            const double vr = fma(xr, w.x, xi * w.y);      // x * conj(w)
-            const double vi = fma(xi, w.x, -(xr * w.y));
-            sre[i0] = ur + vr;
-            sim[i0] = ui + vi;
-            sre[i1] = ur - vr;
-            sim[i1] = ui - vi;
+    // ---- inverse DIT: the same passes in reverse order, conjugated
+    {
+        const int lr0 = (log2n & 3) ? (log2n & 3) : 4;          // the forward transform's last pass
+        for (int s_lo = 0; s_lo < log2n;) {
+            const int lr = s_lo == 0 ? lr0 : 4;
+            fft_pass_any<false>(lr, sre, sim, tw, n, log2n, P, s_lo);
+            s_lo += lr;
+            __syncthreads();
         }
-        __syncthreads();
     }
     // ---- store real part -> pencil a, imaginary part -> pencil b
     for (int e = tid; e < total; e += FFT_NT) {
@@ -118,7 +148,7 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
         const i64 o = LAST ? q : q / inner;
         const i64 c = LAST ? 0 : q - o * inner;
         const i64 lin = (o * nv + k) * inner + c;
-        double d = ((pl & 1) ? sim : sre)[(pl >> 1) * n + k];
+        double d = ((pl & 1) ? sim : sre)[fpad((pl >> 1) * n + k)];
         if (sbad[pl]) d = ng_nan();
         if (FUSED) {
             const Idx4 ix = unravel4(lin, F.shape);
@@ -146,9 +176,10 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
     const int n = p->fft_len;                            // transform length (== p->n unless the plan is zero-padded)
     const i64 npencil = p->outer * p->inner;
     // pencil pairs per CTA: enough butterflies for 256 threads, bounded by shared memory
+    // (a radix-16 pass has P n / 16 work items: at least one per thread, within ~70 KB so that three CTAs share an SM)
     int P = 1;
-    while (P * n < 1024 && (i64)(2 * P) * 2 <= npencil) P *= 2;
-    const size_t smem = (size_t)P * n * 2 * sizeof(double) + (size_t)2 * P * sizeof(int);
+    while (P * n < 4096 && (i64)(2 * P) * 2 <= npencil) P *= 2;
+    const size_t smem = (size_t)((P * n + (P * n >> 4) + 1) * 2) * sizeof(double) + (size_t)2 * P * sizeof(int);   // fpad()
     const i64 nblk = (npencil + 2 * P - 1) / (2 * P);
     const bool last = p->inner == 1;
 #define NG_FFT_GO(LA, FU)                                                                        \
