@@ -106,9 +106,10 @@ int ng_cheb_plan_create(int ndim, const int64_t* shape, int axis,
 
 /* ---- periodic spectral derivative: FFTDiff --------------------------------------------------
  * Replaces real(ifft(W * fft(f, axis), axis)) (numgrids/diff.py:133-143).  h_W_re_im holds the n
- * complex multipliers of diff.py:117-125 interleaved (re, im).  Power-of-two n uses the in-shared-
- * memory FFT kernel; other n use h_D (n x n row-major real matrix F^-1 diag(W) F, the matrix of
- * diff.py:145-157) applied as a dense contraction (NULL h_D with non-power-of-two n -> NG_EINVAL). */
+ * complex multipliers of diff.py:117-125 interleaved (re, im).  Power-of-two n (<= 8192): in-shared-memory / register
+ * FFT kernels.  Other n with h_D == NULL: the native n-point mixed-radix transform (n = 2^a 3^b 5^c 7^d 11^e 13^f <= 8192,
+ * any derivative order, numpy.fft's O(n log n) and rounding class; another prime factor -> NG_EINVAL).  Other n with
+ * h_D given (n x n row-major real matrix F^-1 diag(W) F, the matrix of diff.py:145-157): dense ordered contraction. */
 int ng_fft_plan_create(int ndim, const int64_t* shape, int axis,
                        const double* h_W_re_im, const double* h_D, ng_plan** out);
 

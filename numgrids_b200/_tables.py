@@ -147,6 +147,21 @@ def is_pow2(n: int) -> bool:
     return n >= 2 and (n & (n - 1)) == 0
 
 
+MIXED_RADIX_PRIMES = (2, 3, 5, 7, 11, 13)
+MIXED_RADIX_MAX = 8192
+
+
+def fft_mixed_supported(n: int) -> bool:
+    """True if the library has a native n-point mixed-radix transform for this non-power-of-two length
+    (csrc/fft_mixed.cu: prime factors up to 13, n <= 8192) -- mirrors ng_fft_mixed_supported()."""
+    if n < 3 or n > MIXED_RADIX_MAX or is_pow2(n):
+        return False
+    for p in MIXED_RADIX_PRIMES:
+        while n % p == 0:
+            n //= p
+    return n == 1
+
+
 # ------------------------------------------------------------------ broadcast-compact coefficients
 
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libnumgrids_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "fd.cu", "fd_row.cu", "fd_tile.cu", "dense.cu", "fft.cu", "fft2.cu", "fft_tile.cu", "fdlap.cu", "fdlap3d.cu", "curv.cu", "curvlap3d.cu", "slab.cu", "transpose.cu", "bc.cu", "quad.cu", "interp.cu"]
+SOURCES = ["api.cu", "fd.cu", "fd_row.cu", "fd_tile.cu", "dense.cu", "fft.cu", "fft2.cu", "fft_tile.cu", "fft_mixed.cu", "fdlap.cu", "fdlap3d.cu", "curv.cu", "curvlap3d.cu", "slab.cu", "transpose.cu", "bc.cu", "quad.cu", "interp.cu"]
 # translation units compiled more than once with different macros (object name -> (source, defines)):
 # the contiguous-axis FD kernel is the slowest file to compile; its half widths 3-4 build as a second object
 EXTRA_OBJECTS = {"fd_row_wide.o": ("fd_row.cu", ["-DNG_ROW_PSET=1"])}

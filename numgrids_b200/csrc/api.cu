@@ -341,11 +341,17 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis, const double* h
     const i64 n = p->n;
     const bool pow2 = n >= 2 && (n & (n - 1)) == 0 && n <= 8192;
     const bool force_dense = NG_ENV_INT("NG_FFT_DENSE", 0) != 0;
+    const bool mixed = !pow2 && !h_D && ng_fft_mixed_supported(n);     // (a caller that passes the dense matrix asks for it)
     if (pow2 && !(force_dense && h_D)) {
         rc = build_fft_tables(p, n, h_W_re_im);
+    } else if (mixed) {
+        std::vector<double> Wdr, tw;
+        rc = ng_fft_mixed_tables(p, h_W_re_im, Wdr, tw);
+        if (!rc) rc = upload(p, &p->d_W, Wdr.data(), 2 * n);
+        if (!rc) rc = upload(p, &p->d_twn, tw.data(), 2 * n);
     } else {
         if (!h_D) {
-            ng_set_error("n = %lld is not a power of two <= 8192: the dense spectral matrix is required",
+            ng_set_error("n = %lld is neither a power of two nor a product of 2, 3, 5, 7, 11, 13 (<= 8192): the dense spectral matrix is required",
                          (long long)n);
             delete p;
             return NG_EINVAL;

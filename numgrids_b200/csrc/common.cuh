@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/numgrids_b200.h"
 
@@ -159,6 +160,9 @@ struct ng_plan {
     double* d_tw = nullptr;   // [n/2][2] forward twiddles exp(-2 pi i k / n) (radix-2 kernel)
     double* d_Wn = nullptr;   // [n][2] multipliers / n in natural order (two-pass kernel, fft2.cu)
     double* d_twn = nullptr;  // [n][2] exp(-2 pi i k / n), k < n (two-pass kernel)
+    int fft_mixed = 0;        // native mixed-radix plan of a non-power-of-two n (fft_mixed.cu): d_W digit-reversed, d_twn
+    int mix_nst = 0;
+    int mix_radix[12] = {0};
 
     // PK_FDLAP
     FdTables lap[NG_MAX_DIM];
@@ -193,6 +197,11 @@ int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev
 int ng_fft2_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                        cudaStream_t st, bool* handled);
 bool ng_fft_twice_supported(const ng_plan* p);
+// native mixed-radix transform of a non-power-of-two length with prime factors <= 13 (fft_mixed.cu)
+#define NG_FFT_MIXED_MAX 8192
+bool ng_fft_mixed_supported(i64 n);
+int ng_fft_mixed_tables(ng_plan* p, const double* h_W_re_im, std::vector<double>& Wdr, std::vector<double>& tw);
+int ng_fft_mixed_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F, cudaStream_t st);
 int ng_fft_tile_try_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                            cudaStream_t st, bool* handled);
 int ng_fdlap_launch(const ng_plan* p, const double* in, double* out, const double* lo,

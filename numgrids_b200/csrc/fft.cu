@@ -68,6 +68,29 @@ __device__ __forceinline__ void fft_pass_any(int lr, double* sre, double* sim, c
     }
 }
 
+// The last forward pass (stages 0 .. LR-1: trivial factors), the multiplication by the bit-reversed multiplier table and the
+// first inverse pass work on the same R contiguous elements: one shared-memory round trip and one barrier instead of three.
+template <int LR>
+__device__ __forceinline__ void fft_mid(double* sre, double* sim, const double2* __restrict__ W_br, int n, int P) {
+    constexpr int R = 1 << LR;
+    const int items = (P * n) >> LR;
+    for (int e = threadIdx.x; e < items; e += FFT_NT) {
+        const int base = e << LR;
+        double2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) { const int i = fpad(base + q); x[q] = make_double2(sre[i], sim[i]); }
+        dif_forward<R>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const double2 w = W_br[(base + q) & (n - 1)];
+            x[q] = cmul(x[q], w.x, w.y);
+        }
+        dit_inverse<R>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) { const int i = fpad(base + q); sre[i] = x[q].x; sim[i] = x[q].y; }
+    }
+}
+
 // W_br : [n][2] multipliers in bit-reversed order, pre-divided by n.  tw : [n/2][2] = exp(-2 pi i j/n).
 template <bool LAST, bool FUSED>
 __global__ void __launch_bounds__(FFT_NT)
@@ -136,31 +159,24 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
     }
     __syncthreads();
 
-    // ---- forward DIF: radix-16 passes from the widest spans down (the last pass takes what is left: radix 8 / 4 / 2)
-    for (int s_hi = log2n; s_hi > 0;) {
-        const int lr = s_hi >= 4 ? 4 : s_hi;
-        fft_pass_any<true>(lr, sre, sim, tw, n, log2n, P, s_hi - lr);
-        s_hi -= lr;
+    // ---- forward DIF: radix-16 passes from the widest spans down to the last one (radix lr0 = 16 / 8 / 4 / 2), which
+    // runs fused with the multiplication by (ik)^order / n (bit-reversed order) and the first inverse pass
+    const int lr0 = (log2n & 3) ? (log2n & 3) : 4;
+    for (int s_hi = log2n; s_hi > lr0; s_hi -= 4) {
+        fft_pass_any<true>(4, sre, sim, tw, n, log2n, P, s_hi - 4);
         __syncthreads();
     }
-    // ---- multiply by (ik)^order / n, bit-reversed order
-    for (int e = tid; e < P * n; e += FFT_NT) {
-        const double2 w = W_br[e & (n - 1)];
-        const int i = fpad(e);
-        const double xr = sre[i], xi = sim[i];
-        sre[i] = fma(xr, w.x, -(xi * w.y));
-        sim[i] = fma(xr, w.y, xi * w.x);
+    switch (lr0) {
+        case 4: fft_mid<4>(sre, sim, W_br, n, P); break;
+        case 3: fft_mid<3>(sre, sim, W_br, n, P); break;
+        case 2: fft_mid<2>(sre, sim, W_br, n, P); break;
+        default: fft_mid<1>(sre, sim, W_br, n, P); break;
     }
     __syncthreads();
-    // ---- inverse DIT: the same passes in reverse order, conjugated
-    {
-        const int lr0 = (log2n & 3) ? (log2n & 3) : 4;          // the forward transform's last pass
-        for (int s_lo = 0; s_lo < log2n;) {
-            const int lr = s_lo == 0 ? lr0 : 4;
-            fft_pass_any<false>(lr, sre, sim, tw, n, log2n, P, s_lo);
-            s_lo += lr;
-            __syncthreads();
-        }
+    // ---- inverse DIT: the remaining passes in reverse order, conjugated
+    for (int s_lo = lr0; s_lo < log2n; s_lo += 4) {
+        fft_pass_any<false>(4, sre, sim, tw, n, log2n, P, s_lo);
+        __syncthreads();
     }
     // ---- store real part -> pencil a, imaginary part -> pencil b
     for (int e = tid; e < total; e += FFT_NT) {
@@ -184,6 +200,7 @@ fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
 int ng_fft_launch(const ng_plan* p, const double* in, double* out, const FuseDev& F,
                   cudaStream_t st) {
     if (p->size == 0) return NG_OK;
+    if (p->fft_mixed) return ng_fft_mixed_launch(p, in, out, F, st);
     if (!p->fft_pow2) {
         NG_REQUIRE(!F.mid.ptr, "double apply requested from a kernel that does not implement it (ng_fft_twice_supported)");
         return ng_dense_launch(p, in, out, F, st);

@@ -63,14 +63,16 @@ class CurvilinearGrid(Grid):
             self._ensure_diff_ops()
             lib = _lib.load()
             _lib.require_gpu()
-            children = [self._diff_ops[i].operator.operator.plan for i in range(self.ndims)]
+            from .diff import FFTDiff
+            ops = [self._diff_ops[i].operator for i in range(self.ndims)]
+            # (periodic axes: the composites' own plan -- native-length transform where the plain Diff would zero-pad)
+            children = [op.make_composite_plan() if isinstance(op, FFTDiff) else op.operator.plan for op in ops]
             arr = _lib.ptr_array([p.handle.value for p in children])
             shp, shp_p = _lib.as_i64(list(self.shape))
             out = C.c_void_p()
             _lib.check(lib.ng_curv_plan_create(self.ndims, shp_p, arr, C.byref(out)),
                        "ng_curv_plan_create")
             keep = list(children)
-            from .diff import FFTDiff
             for i in range(self.ndims):             # periodic axes: D applied twice as ONE transform (see make_square_plan)
                 op = self._diff_ops[i].operator
                 if isinstance(op, FFTDiff):

@@ -13,6 +13,7 @@ There is no CPU fallback: calling an operator without a CUDA device raises Numgr
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse
@@ -234,6 +235,9 @@ class FFTDiff(GridDiff):
     # n = 1536: 3.1e-11 / 3.6e-11), both ten times closer to numpy.fft than numpy.fft is to a long-double DFT
     # (9e-11 / 3e-10) -- so the O(n log n) path costs no accuracy.  Higher orders keep the dense contraction.
     PADDED_ORDERS = (1, 2)
+    PADDED_FAST_MAX = 512           # padded transforms up to 1024 points run on the register kernels (fft2.cu, fft_tile.cu)
+    MIXED_MIN_POINTS = 96           # shorter axes: the dense contraction is as fast or faster (n = 24..60: 74-96 vs 46-70 Gpts/s)
+    NONPOW2 = os.environ.get("NUMGRIDS_B200_FFT_NONPOW2", "auto")       # auto | native | padded
 
     def __init__(self, grid, order, axis_index, acc=6):
         super().__init__(grid, order, axis_index)
@@ -256,6 +260,14 @@ class FFTDiff(GridDiff):
     def _make_plan(self, shape=None) -> _lib.Plan:
         return self._plan_for(self._W_1d, self.order, shape, self._dense_matrix)
 
+    def make_composite_plan(self, shape=None) -> _lib.Plan:
+        """Plan of this operator as a building block of ``CurvilinearGrid.laplacian / gradient / divergence / curl``.
+        On a non-power-of-two length those prefer the native mixed-radix transform to the (2-3 x faster) zero-padded one:
+        the composites amplify rounding -- 1/h^2 factors, terms that cancel -- and against the reference the native
+        transform is 3-5 x closer (spherical Laplacian of a harmonic field, n_phi = 500: 2.4e-11 vs 1.1e-10,
+        gradient 5e-14 vs 1.3e-13; profiles/r02b_fft_mixed.txt)."""
+        return self._plan_for(self._W_1d, self.order, shape, self._dense_matrix, prefer_native=True)
+
     def make_square_plan(self, shape=None) -> _lib.Plan:
         """Plan of this operator applied TWICE in one transform: multiplier W**2 (for a first derivative: -(k s)**2 with
         the Nyquist bin zeroed, exactly what two applications do).  ``CurvilinearGrid.laplacian`` uses it for
@@ -263,9 +275,9 @@ class FFTDiff(GridDiff):
         of two, and none of the first transform's rounding noise amplified by the second (on zero-padded lengths the
         chained form reaches 6e-11 at n = 360, the single transform 1.4e-12)."""
         W2 = self._W_1d * self._W_1d
-        return self._plan_for(W2, 2 * self.order, shape, lambda: _tables.fft_dense_matrix(W2))
+        return self._plan_for(W2, 2 * self.order, shape, lambda: _tables.fft_dense_matrix(W2), prefer_native=True)
 
-    def _plan_for(self, W1d, order, shape, dense) -> _lib.Plan:
+    def _plan_for(self, W1d, order, shape, dense, prefer_native=False) -> _lib.Plan:
         lib = _lib.load()
         shp, shp_p = _shape_arg(self.grid) if shape is None else _lib.as_i64(list(shape))
         W = np.ascontiguousarray(W1d, dtype=np.complex128).view(np.float64)
@@ -273,10 +285,25 @@ class FFTDiff(GridDiff):
         n = len(self.axis)
         out = C.c_void_p()
         pow2 = _tables.is_pow2(n) and n <= 8192
-        # Any other length: first and second derivatives run as a zero-padded power-of-two transform (O(n log n) like
-        # the reference's pocketfft; see PADDED_ORDERS for the accuracy); orders >= 3 and short axes keep the dense
-        # O(n^2) contraction.
-        padded = None if pow2 or order not in self.PADDED_ORDERS or n < self.PADDED_MIN_POINTS else _tables.fft_padded_multiplier(W1d)
+        # Any other length (NONPOW2 = "auto"):
+        #   * first and second derivatives with 65 <= n <= 512: zero-padded power-of-two transform on the two-pass
+        #     register kernels (O(n log n) like the reference's pocketfft, 100-160 Gpts/s; as close to numpy.fft as the
+        #     native transform: see PADDED_ORDERS);
+        #   * otherwise, n = 2^a 3^b 5^c 7^d 11^e 13^f from MIXED_MIN_POINTS on: the library's native n-point mixed-radix
+        #     transform (any order; 30-58 Gpts/s, faster than the padded transform beyond n = 1024);
+        #   * what is left (other prime factors): padded for orders 1-2, else the dense O(n^2) contraction.
+        # "native" prefers the mixed-radix transform wherever it exists (as the curvilinear composites do:
+        # make_composite_plan), "padded" never uses it.
+        mixed_ok = (not pow2 and self.NONPOW2 != "padded" and _tables.fft_mixed_supported(n)
+                    and n >= (self.PADDED_MIN_POINTS if prefer_native else self.MIXED_MIN_POINTS))
+        pad_ok = not pow2 and order in self.PADDED_ORDERS and n >= self.PADDED_MIN_POINTS
+        if mixed_ok and pad_ok and self.NONPOW2 == "auto" and not prefer_native:
+            mixed_ok = n > self.PADDED_FAST_MAX
+        if mixed_ok:
+            _lib.check(lib.ng_fft_plan_create(len(shp), shp_p, self.axis_index, W_p, None, C.byref(out)),
+                       "ng_fft_plan_create")
+            return _lib.Plan(out.value)
+        padded = _tables.fft_padded_multiplier(W1d) if pad_ok else None
         if padded is not None:
             m, Wm = padded
             Wmk, Wm_p = _lib.as_f64(np.ascontiguousarray(Wm, dtype=np.complex128).view(np.float64))

@@ -461,48 +461,70 @@ def test_matrix_free_linear_operator(gpu_ready):
         assert rel_linf(L.rmatvec(v), d.as_matrix().T @ v) <= 1e-12
 
 
-@pytest.mark.parametrize("n", [65, 96, 100, 200, 360, 500, 1000, 1536, 3000])
+def _smooth(n):
+    for q in (2, 3, 5, 7, 11, 13):
+        while n % q == 0:
+            n //= q
+    return n == 1
+
+
+def _exact_pencil(f1d, W):
+    """real(ifft(W fft(f))) of one pencil through a long-double DFT: the exact answer to ~1e-19."""
+    n = len(f1d)
+    k = np.arange(n, dtype=np.longdouble)
+    E = np.exp(-2j * np.pi * np.outer(k, k).astype(np.longdouble) / n)
+    return np.real((np.conj(E) @ (W.astype(np.clongdouble) * (E @ f1d.astype(np.longdouble)))) / n).astype(np.float64)
+
+
+@pytest.mark.parametrize("n", [65, 96, 100, 118, 200, 360, 500, 1000, 1536, 3000])
 def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
-    """Periodic axes whose length is not a power of two: first and second derivatives run as a zero-padded power-of-two
-    transform (two-pass register kernel up to n = 512, radix-2 kernel above), not the O(n^2) dense contraction;
-    <= 1e-11 against numpy.fft (oracle) on the last axis and on a strided one, plain and fused (polar Laplacian)."""
+    """Periodic axes whose length is not a power of two never take the O(n^2) dense contraction for first and second
+    derivatives: up to n = 512 a zero-padded power-of-two transform on the two-pass register kernels, beyond that the
+    native mixed-radix transform (n = 2^a 3^b 5^c 7^d 11^e 13^f; csrc/fft_mixed.cu), which also serves every higher order;
+    <= 1e-11 against numpy.fft (oracle) on the last axis and on a strided one, plain and fused (polar / spherical
+    composites, which use the native transform wherever it exists)."""
     import torch
     from numgrids_b200 import _lib
     p = ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi)
     e = ng.create_axis(A.EQUIDISTANT, 10, 0.0, 1.0)
     rng = np.random.default_rng(n)
+
+    def check_kernel(order):
+        kernel = _lib.last_kernel()
+        if n > 512 and _smooth(n) or order > 2 and _smooth(n) and n >= 96:
+            assert kernel == "fft_mixed", (n, order, kernel)
+        elif order <= 2:
+            assert "padded" in kernel, (n, order, kernel)
+            assert ("fft2pass" in kernel) == (n <= 512), (n, kernel)
+        else:
+            assert "dense" in kernel, (n, order, kernel)
+
     for axes, axis in (((e, p), 1), ((p, e), 0)):
         g = ng.Grid(*axes)
         X = g.meshed_coords[axis]
         f = np.exp(np.sin(X)) * np.cos(2 * X) + 0.05 * rng.standard_normal(g.shape)
         out = ng.Diff(g, 1, axis)(torch.from_numpy(f).cuda())
-        kernel = _lib.last_kernel()
-        assert "padded" in kernel, kernel
-        assert ("fft2pass" in kernel) == (n <= 512), (n, kernel)
+        check_kernel(1)
         ref = pencil.fft_apply(f, axis, pencil.fft_multiplier(n, p.spacing, 1))
         err = rel_linf(out.cpu().numpy(), ref)
         assert err <= TOL_FFT, (n, axis, err)
-    # order 2: the same zero-padded transform.  Order 2 amplifies the rounding of ANY transform by (n/2)^2 -- numpy.fft
-    # itself is 9e-11 from a long-double DFT at n = 1000 -- so beyond n = 500 the bound is half of numpy.fft's own
-    # distance from the exact answer (the dense contraction this replaced measures the same: 9.7e-12 vs 1.2e-11 at
-    # n = 1000, tools/check_fft_order2_nonpow2.py); up to n = 500 it is the 1e-11 of the contract.
+    # orders 2 and 3.  Order k amplifies the rounding of ANY transform by (n/2)^k -- numpy.fft itself is 9e-11 from a
+    # long-double DFT at n = 1000, order 2 -- so the bound is the 1e-11 of the contract or half of numpy.fft's own
+    # distance from the exact answer, whichever is larger (the dense contraction measures the same: 9.7e-12 vs 1.2e-11
+    # at n = 1000, tools/check_fft_order2_nonpow2.py).
     g = ng.Grid(e, p)
     P = g.meshed_coords[1]
     f = np.exp(np.sin(P)) * np.cos(2 * P) * (1.0 + g.meshed_coords[0])
-    out = ng.Diff(g, 2, 1)(torch.from_numpy(f).cuda()).cpu().numpy()
-    assert "padded" in _lib.last_kernel(), _lib.last_kernel()
-    W2 = pencil.fft_multiplier(n, p.spacing, 2)
-    ref = pencil.fft_apply(f, 1, W2)
-    bound = TOL_FFT
-    if n > 500:
-        k = np.arange(n, dtype=np.longdouble)
-        E = np.exp(-2j * np.pi * np.outer(k, k).astype(np.longdouble) / n)
-        exact = np.real((np.conj(E) @ (W2.astype(np.clongdouble) * (E @ f[3].astype(np.longdouble)))) / n).astype(np.float64)
-        bound = max(TOL_FFT, 0.5 * rel_linf(ref[3], exact))
-    err = rel_linf(out, ref)
-    assert err <= bound, (n, err, bound)
-    # fused: polar Laplacian with n points in phi (Chebyshev r), through the radix-2 kernel's fused path
-    if n in (100, 360):
+    for order in (2, 3):
+        out = ng.Diff(g, order, 1)(torch.from_numpy(f).cuda()).cpu().numpy()
+        check_kernel(order)
+        Wk = pencil.fft_multiplier(n, p.spacing, order)
+        ref = pencil.fft_apply(f, 1, Wk)
+        bound = max(TOL_FFT, 0.5 * rel_linf(ref[3], _exact_pencil(f[3], Wk)))
+        err = rel_linf(out, ref)
+        assert err <= bound, (n, order, err, bound)
+    # fused: polar Laplacian with n points in phi (Chebyshev r)
+    if n in (100, 118, 360):
         r = ng.create_axis(A.CHEBYSHEV, 12, 0.5, 2.0)
         pg = ng.PolarGrid(r, p)
         R, P = pg.meshed_coords
@@ -521,12 +543,70 @@ def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
         D = [pencil.make_diff(pax, 1, i) for i in range(3)]
         h = (np.ones_like(R), R, R * np.sin(T))
         # (this field is hard on a Laplacian: r^2 sin^2(theta) cos(2 phi) = x^2 - y^2 is harmonic, so its three terms cancel, and
-        # the phi term carries 1 / (r sin theta)^2 <= 46.  The zero-padded transform's rounding -- 3e-13 of D D f, a hundred
-        # times that of a native-length FFT, because the circular-convolution kernel of the derivative decays like 1/j --
-        # shows as 4e-11 of the result at n = 360; at n = 100 it is within the 1e-11 of the contract)
-        assert rel_linf(sg.laplacian(f), pencil.laplacian(f, h, D)) <= (TOL_FFT if n <= 128 else 1e-10)
-        assert _lib.last_kernel() == "fft2pass_ring<padded>", _lib.last_kernel()
+        # the phi term carries 1 / (r sin theta)^2 <= 46: two correct n-point transforms differ by more than 1e-11 of the
+        # result from n ~ 300 on.  Measured against the oracle at n = 360: native mixed-radix 2.3e-11, zero-padded 3.7e-11;
+        # n = 500: 2.4e-11 / 1.1e-10; up to n = 128 both are within the 1e-11 of the contract)
+        assert rel_linf(sg.laplacian(f), pencil.laplacian(f, h, D)) <= (TOL_FFT if n <= 128 else 5e-11)
+        assert _lib.last_kernel() == ("fft_mixed" if _smooth(n) else "fft2pass_ring<padded>"), _lib.last_kernel()
         for got, want in zip(sg.gradient(f), pencil.gradient(f, h, D)):
             assert rel_linf(got, want) <= TOL_FFT
         v = (R, np.sin(T), np.cos(P))
         assert rel_linf(sg.divergence(*v), pencil.divergence(v, h, D)) <= TOL_FFT
+
+
+@pytest.mark.parametrize("n", [6, 12, 45, 77, 143, 182, 210, 364, 1155, 2187, 6000])
+def test_mixed_radix_transform_vs_oracle(gpu_ready, n, monkeypatch):
+    """The native mixed-radix kernel on its own (every radix: 2 4 8 16 3 5 7 9 11 13; one to seven passes), forced for
+    every length and order: <= 1e-11 against numpy.fft on the contiguous axis and on strided ones (odd extents, a ragged
+    last CTA), with a fused prologue / tail, and with non-finite pencils, which must come out all-NaN without touching
+    the pencil they share a complex transform with (numgrids/diff.py:133-143; curvilinear.py:236-244 relies on it)."""
+    import torch
+    from numgrids_b200 import _lib
+    from numgrids_b200.diff import FFTDiff
+    monkeypatch.setattr(FFTDiff, "NONPOW2", "native")
+    monkeypatch.setattr(FFTDiff, "MIXED_MIN_POINTS", 3)
+    monkeypatch.setattr(FFTDiff, "PADDED_MIN_POINTS", 3)       # (the composites' threshold for the native transform)
+    p = ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi)
+    rng = np.random.default_rng(n)
+    small = n <= 400
+    for shape, axis in (((7, 9, n), 2), ((5, n, 11), 1), ((n, 3, 7), 0)) if small else (((3, 5, n), 2), ((n, 9), 0)):
+        axes = [p if a == axis else ng.create_axis(A.EQUIDISTANT, m, 0.0, 1.0) for a, m in enumerate(shape)]
+        g = ng.Grid(*axes)
+        X = g.meshed_coords[axis]
+        f = np.exp(np.sin(X)) * np.cos(2 * X) + 0.05 * rng.standard_normal(g.shape)
+        for order in (1, 2, 3) if small else (1,):
+            out = ng.Diff(g, order, axis)(torch.from_numpy(f).cuda()).cpu().numpy()
+            assert _lib.last_kernel() == "fft_mixed", _lib.last_kernel()
+            Wk = pencil.fft_multiplier(n, p.spacing, order)
+            ref = pencil.fft_apply(f, axis, Wk)
+            line = tuple(0 if a != axis else slice(None) for a in range(len(shape)))
+            bound = max(TOL_FFT, 0.5 * rel_linf(ref[line], _exact_pencil(f[line], Wk))) if order > 1 and n <= 1200 else TOL_FFT
+            assert rel_linf(out, ref) <= bound, (n, shape, axis, order)
+        # non-finite samples
+        fb = f.copy()
+        idx = [tuple(int(rng.integers(0, m)) for m in shape) for _ in range(3)]
+        for k, ix in enumerate(idx):
+            fb[ix] = (np.inf, -np.inf, np.nan)[k]
+        out = ng.Diff(g, 1, axis)(torch.from_numpy(fb).cuda()).cpu().numpy()
+        ref = pencil.fft_apply(f, axis, pencil.fft_multiplier(n, p.spacing, 1))
+        bad = np.zeros(shape, dtype=bool)
+        for ix in idx:
+            sl = list(ix); sl[axis] = slice(None)
+            bad[tuple(sl)] = True
+        assert np.isnan(out[bad]).all()
+        assert np.max(np.abs(out[~bad] - ref[~bad])) <= TOL_FFT * np.max(np.abs(ref))
+    # fused prologue / tails: polar composites with n points in phi against the oracle
+    if n in (45, 182, 364):
+        r = ng.create_axis(A.CHEBYSHEV, 14, 0.5, 2.0)
+        pg = ng.PolarGrid(r, p)
+        R, P = pg.meshed_coords
+        f = R ** 2 * np.cos(2 * P) + np.exp(-R) * np.sin(P)
+        pax = [pencil.make_axis("chebyshev", 14, 0.5, 2.0), pencil.make_axis("periodic", n, 0.0, 2 * np.pi)]
+        D = [pencil.make_diff(pax, 1, i) for i in range(2)]
+        h = (np.ones_like(R), R)
+        assert rel_linf(pg.laplacian(f), pencil.laplacian(f, h, D)) <= TOL_FFT
+        assert _lib.last_kernel() == "fft_mixed", _lib.last_kernel()
+        for got, want in zip(pg.gradient(f), pencil.gradient(f, h, D)):
+            assert rel_linf(got, want) <= TOL_FFT
+        v = (R * np.cos(P), np.sin(2 * P) / R)
+        assert rel_linf(pg.divergence(*v), pencil.divergence(v, h, D)) <= TOL_FFT
