@@ -34,7 +34,7 @@ template <int LR, bool FWD>
 __device__ __forceinline__ void fft_pass(double* sre, double* sim, const double2* __restrict__ tw, int n, int log2n, int P,
                                          int s_lo) {
     constexpr int R = 1 << LR;
-    const int m_lo = 1 << s_lo, per = n >> LR, items = P * per, half = n >> 1;
+    const int m_lo = 1 << s_lo, per = n >> LR, items = P * per;
     const int sh = log2n - LR - s_lo;                 // table index of angle a / (R m_lo) on the n-point circle: a << sh
     for (int e = threadIdx.x; e < items; e += FFT_NT) {
         const int p = e / per, b = e - p * per;
@@ -44,14 +44,12 @@ __device__ __forceinline__ void fft_pass(double* sre, double* sim, const double2
 #pragma unroll
         for (int q = 0; q < R; ++q) { const int i = fpad(base + q * m_lo); x[q] = make_double2(sre[i], sim[i]); }
         if (FWD) dif_forward<R>(x);
+        if (j_lo != 0) {                              // (j_lo = 0: the whole sub-network has trivial factors)
+            const double2 w = tw[j_lo << sh];         // j_lo < m_lo: the index is below n / R
+            double2 pw[R];
+            twiddle_powers<R>(make_double2(w.x, FWD ? w.y : -w.y), pw);
 #pragma unroll
-        for (int q = 1; q < R; ++q) {
-            const int ti = (j_lo * bitrev(q, LR)) << sh;
-            if (ti != 0) {                            // (j_lo = 0: the whole sub-network has trivial factors)
-                double2 w = tw[ti < half ? ti : ti - half];
-                if (ti >= half) w = make_double2(-w.x, -w.y);
-                x[q] = cmul(x[q], w.x, FWD ? w.y : -w.y);
-            }
+            for (int q = 1; q < R; ++q) { const double2 t = pw[bitrev(q, LR)]; x[q] = cmul(x[q], t.x, t.y); }
         }
         if (!FWD) dit_inverse<R>(x);
 #pragma unroll
@@ -93,7 +91,7 @@ __device__ __forceinline__ void fft_mid(double* sre, double* sim, const double2*
 
 // W_br : [n][2] multipliers in bit-reversed order, pre-divided by n.  tw : [n/2][2] = exp(-2 pi i j/n).
 template <bool LAST, bool FUSED>
-__global__ void __launch_bounds__(FFT_NT)
+__global__ void __launch_bounds__(FFT_NT, 2)
 fft_diff_kernel(const double* __restrict__ in, double* __restrict__ out,
                 const double2* __restrict__ W_br, const double2* __restrict__ tw, i64 outer, int n,
                 int log2n, i64 inner, int P, int nv /* samples per pencil in memory (<= n; the rest is zero padding) */,

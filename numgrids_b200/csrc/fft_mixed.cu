@@ -251,12 +251,11 @@ __device__ __noinline__ void mix_pass(double* sre, double* sim, const double2* _
         for (int q = 0; q < R; ++q) { const int i = mpad(base + q * m); x[q] = make_double2(sre[i], sim[i]); }
         if (FWD) small_dft<R, true>(x);
         if (j != 0) {                               // (j = 0: trivial factors)
-            const int tj = j * step;                // < n / R
+            const double2 w = tw[j * step];         // exp(-2 pi i j / L); the other outputs' factors are its powers
+            double2 pw[R];
+            twiddle_powers<R>(make_double2(w.x, FWD ? w.y : -w.y), pw);
 #pragma unroll
-            for (int q = 1; q < R; ++q) {
-                const double2 w = tw[tj * freq_digit<R>(q)];          // j f step < m R step = n
-                x[q] = cmul(x[q], w.x, FWD ? w.y : -w.y);
-            }
+            for (int q = 1; q < R; ++q) { const double2 t = pw[freq_digit<R>(q)]; x[q] = cmul(x[q], t.x, t.y); }
         }
         if (!FWD) small_dft<R, false>(x);
 #pragma unroll
@@ -320,7 +319,7 @@ __device__ __forceinline__ void mix_pass_any(int r, double* sre, double* sim, co
 
 // W_dr : [n] multipliers / n in the digit-reversed order of the forward passes.  tw : [n] = exp(-2 pi i t / n).
 template <bool LAST, bool FUSED>
-__global__ void __launch_bounds__(MX_NT)
+__global__ void __launch_bounds__(MX_NT, 2)
 fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ W_dr,
                  const double2* __restrict__ tw, i64 outer, int n, i64 inner, int P, MixStages S, FuseDev F) {
     extern __shared__ double smem[];

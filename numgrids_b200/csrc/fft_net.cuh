@@ -47,6 +47,21 @@ __host__ __device__ __forceinline__ constexpr int bitrev(int v, int bits) {
     for (int b = 0; b < bits; ++b) if (v & (1 << b)) r |= 1 << (bits - 1 - b);
     return r;
 }
+// p[f] = w^f, f = 1 .. R-1, from ONE table value: p[f] = p[floor(f/2)] p[ceil(f/2)], at most ceil(log2 f) products deep
+// (a few 1e-16; the periodic path's tolerance is 1e-11).  The shared-memory FFT passes need w^(j f) for every output f
+// of a radix-R butterfly: R-1 scattered 16-byte table loads per work item were 3-4 x the load/store pipe traffic of the
+// butterfly's own shared-memory accesses (ncu: l1tex 74 % busy, FP64 pipe 18 %).
+template <int R>
+__device__ __forceinline__ void twiddle_powers(double2 w, double2* p) {
+    p[0] = make_double2(1.0, 0.0);
+    p[1] = w;
+#pragma unroll
+    for (int f = 2; f < R; ++f) {
+        const double2 a = p[f / 2], b = p[f - f / 2];
+        p[f] = make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+    }
+}
+
 template <int R> struct Log2 { static constexpr int v = 1 + Log2<R / 2>::v; };
 template <> struct Log2<1> { static constexpr int v = 0; };
 

