@@ -226,3 +226,13 @@ def test_as_matrix_equals_oracle_operator(specs, axis, order):
     ref = pencil.make_diff([pencil.make_axis(*s) for s in specs], order, axis, 4)(f)
     np.testing.assert_allclose((M @ f.reshape(-1)).reshape(g.shape), ref, rtol=0,
                                atol=1e-10 * np.max(np.abs(ref)))
+
+
+def test_mixed_radix_lengths():
+    """Which periodic-axis lengths the library's native mixed-radix transform serves (mirrors ng_fft_mixed_supported,
+    csrc/fft_mixed.cu): not a power of two, prime factors up to 13, at most 8192 points."""
+    from numgrids_b200 import _tables
+    yes = [3, 6, 9, 12, 45, 96, 100, 360, 1000, 1536, 2310, 3000, 6000, 2 * 3 * 5 * 7 * 11 * 3, 13 ** 3]
+    no = [1, 2, 4, 64, 1024, 8192, 17, 34, 118, 2 * 59, 19 * 5, 8193, 9000, 10 ** 4]
+    assert all(_tables.fft_mixed_supported(n) for n in yes)
+    assert not any(_tables.fft_mixed_supported(n) for n in no)
