@@ -524,6 +524,28 @@ def per_config_extras(torch, ng, peak_gbs, quick):
         out["fft_strided_axis"] = {"error": repr(e)}
 
     try:
+        # periodic axes whose length is not a power of two: zero-padded transform on the register kernels (plain first
+        # derivative, n <= 512), native mixed-radix transform (csrc/fft_mixed.cu) beyond that and for higher orders
+        b = 128 if quick else 512
+        res = {}
+        for n, order in ((360, 1), (360, 3), (1000, 1), (1536, 1)):
+            shape = (b, b if n < 1200 else b // 2, n)
+            axes = [ng.create_axis(A.EQUIDISTANT_PERIODIC if a == 2 else A.EQUIDISTANT, m, 0.0,
+                                   2 * np.pi if a == 2 else 1.0) for a, m in enumerate(shape)]
+            g = ng.Grid(*axes)
+            f = torch.randn(*shape, dtype=torch.float64, device=dev)
+            o = torch.empty_like(f)
+            op = ng.Diff(g, order, 2).operator.operator
+            ms = timed(lambda: op.apply_ptr(f.data_ptr(), o.data_ptr()), 10, 3, b < 512)
+            pts = int(np.prod(shape))
+            res["x".join(map(str, shape)) + f"_order{order}"] = {"gpts": pts / ms / 1e6, "ms": ms, "kernel": _lib_last_kernel(),
+                                                                  "hbm_frac": 16 * pts / ms / 1e6 / peak_gbs}
+            del f, o
+        out["fft_any_length_axis2"] = res
+    except Exception as e:  # pragma: no cover
+        out["fft_any_length"] = {"error": repr(e)}
+
+    try:
         # cfg4: SphericalGrid(Cheb 128, Cheb 128, periodic 256): laplacian / gradient / divergence
         r = ng.create_axis(A.CHEBYSHEV, 128, 0.5, 2.0)
         th = ng.create_axis(A.CHEBYSHEV, 128, 0.3, np.pi - 0.3)

@@ -17,6 +17,7 @@
 // FMA is allowed here (tolerance 1e-11, BASELINE.json); HBM traffic 16 B per point.
 #include "fft_net.cuh"
 
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -228,13 +229,72 @@ __device__ __forceinline__ void odd_dft(double2* x) {
 }
 
 template <int R> struct IsPow2 { static constexpr bool v = (R & (R - 1)) == 0; };
-// frequency digit held by register q after the forward r-point transform (the power-of-two networks leave bit-reversed order)
-template <int R> __host__ __device__ constexpr int freq_digit(int q) { return IsPow2<R>::v ? bitrev(q, Log2<R>::v) : q; }
+
+// Composite radices 6 10 12 14 15 = A * B with coprime factors: a prime-factor (Good-Thomas) butterfly in registers -- input
+// index (B n1 + A n2) mod R, output index the CRT combination of (k1, k2) -- needs NO factors between its two stages, so
+// a length like 1000 = 10 * 10 * 10 takes three shared-memory passes instead of the four of 8 * 5 * 5 * 5.
+__host__ __device__ constexpr int mx_split_a(int r) { return r == 6 || r == 10 || r == 14 ? 2 : r == 12 ? 4 : r == 15 ? 3 : 0; }
+__host__ __device__ constexpr int mx_modinv(int a, int m) {
+    for (int x = 1; x <= m; ++x)
+        if ((a % m) * x % m == 1 % m) return x;
+    return 1;
+}
+__host__ __device__ constexpr int mx_slot(int ra, int rb, int n1, int n2) { return (rb * n1 + ra * n2) % (ra * rb); }
+// frequency digit held by register q after the forward r-point butterfly (power-of-two networks leave bit-reversed order)
+__host__ __device__ constexpr int mx_base_freq(int r, int q) {
+    if ((r & (r - 1)) != 0) return q;
+    int l = 0;
+    while ((1 << l) < r) ++l;
+    return bitrev(q, l);
+}
+__host__ __device__ constexpr int mx_freq(int r, int q) {
+    const int ra = mx_split_a(r);
+    if (!ra) return mx_base_freq(r, q);
+    const int rb = r / ra;
+    for (int n1 = 0; n1 < ra; ++n1)
+        for (int n2 = 0; n2 < rb; ++n2)
+            if (mx_slot(ra, rb, n1, n2) == q)
+                return (mx_base_freq(ra, n1) * rb * mx_modinv(rb, ra) + mx_base_freq(rb, n2) * ra * mx_modinv(ra, rb)) % r;
+    return 0;
+}
+
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
 
 template <int R, bool FWD>
 __device__ __forceinline__ void small_dft(double2* x) {
-    if constexpr (IsPow2<R>::v) { if (FWD) dif_forward<R>(x); else dit_inverse<R>(x); }
-    else odd_dft<R, FWD>(x);
+    constexpr int RA = mx_split_a(R);
+    if constexpr (RA != 0) {
+        constexpr int RB = R / RA;
+        auto stage_a = [&]() {
+            static_for<0, RB>([&](auto n2c) {
+                constexpr int n2 = decltype(n2c)::value;
+                double2 t[RA];
+                static_for<0, RA>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; t[n1] = x[mx_slot(RA, RB, n1, n2)]; });
+                small_dft<RA, FWD>(t);
+                static_for<0, RA>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; x[mx_slot(RA, RB, n1, n2)] = t[n1]; });
+            });
+        };
+        auto stage_b = [&]() {
+            static_for<0, RA>([&](auto n1c) {
+                constexpr int n1 = decltype(n1c)::value;
+                double2 t[RB];
+                static_for<0, RB>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; t[n2] = x[mx_slot(RA, RB, n1, n2)]; });
+                small_dft<RB, FWD>(t);
+                static_for<0, RB>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; x[mx_slot(RA, RB, n1, n2)] = t[n2]; });
+            });
+        };
+        if (FWD) { stage_a(); stage_b(); } else { stage_b(); stage_a(); }
+    } else if constexpr (IsPow2<R>::v) {
+        if (FWD) dif_forward<R>(x); else dit_inverse<R>(x);
+    } else {
+        odd_dft<R, FWD>(x);
+    }
 }
 
 // One pass over the blocks of length L (L = R m): see the header.  tw = exp(-2 pi i t / n), t < n.
@@ -254,8 +314,11 @@ __device__ __noinline__ void mix_pass(double* sre, double* sim, const double2* _
             const double2 w = tw[j * step];         // exp(-2 pi i j / L); the other outputs' factors are its powers
             double2 pw[R];
             twiddle_powers<R>(make_double2(w.x, FWD ? w.y : -w.y), pw);
-#pragma unroll
-            for (int q = 1; q < R; ++q) { const double2 t = pw[freq_digit<R>(q)]; x[q] = cmul(x[q], t.x, t.y); }
+            static_for<1, R>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                constexpr int f = mx_freq(R, q);
+                x[q] = cmul(x[q], pw[f].x, pw[f].y);
+            });
         }
         if (!FWD) small_dft<R, false>(x);
 #pragma unroll
@@ -294,6 +357,11 @@ __device__ __forceinline__ void mix_mid_any(int r, double* sre, double* sim, con
         case 16: mix_mid<16>(sre, sim, W_dr, n, P); break;
         case 3: mix_mid<3>(sre, sim, W_dr, n, P); break;
         case 5: mix_mid<5>(sre, sim, W_dr, n, P); break;
+        case 6: mix_mid<6>(sre, sim, W_dr, n, P); break;
+        case 10: mix_mid<10>(sre, sim, W_dr, n, P); break;
+        case 12: mix_mid<12>(sre, sim, W_dr, n, P); break;
+        case 14: mix_mid<14>(sre, sim, W_dr, n, P); break;
+        case 15: mix_mid<15>(sre, sim, W_dr, n, P); break;
         case 7: mix_mid<7>(sre, sim, W_dr, n, P); break;
         case 9: mix_mid<9>(sre, sim, W_dr, n, P); break;
         case 11: mix_mid<11>(sre, sim, W_dr, n, P); break;
@@ -310,6 +378,11 @@ __device__ __forceinline__ void mix_pass_any(int r, double* sre, double* sim, co
         case 16: mix_pass<16, FWD>(sre, sim, tw, n, P, L); break;
         case 3: mix_pass<3, FWD>(sre, sim, tw, n, P, L); break;
         case 5: mix_pass<5, FWD>(sre, sim, tw, n, P, L); break;
+        case 6: mix_pass<6, FWD>(sre, sim, tw, n, P, L); break;
+        case 10: mix_pass<10, FWD>(sre, sim, tw, n, P, L); break;
+        case 12: mix_pass<12, FWD>(sre, sim, tw, n, P, L); break;
+        case 14: mix_pass<14, FWD>(sre, sim, tw, n, P, L); break;
+        case 15: mix_pass<15, FWD>(sre, sim, tw, n, P, L); break;
         case 7: mix_pass<7, FWD>(sre, sim, tw, n, P, L); break;
         case 9: mix_pass<9, FWD>(sre, sim, tw, n, P, L); break;
         case 11: mix_pass<11, FWD>(sre, sim, tw, n, P, L); break;
@@ -321,7 +394,7 @@ __device__ __forceinline__ void mix_pass_any(int r, double* sre, double* sim, co
 template <bool LAST, bool FUSED>
 __global__ void __launch_bounds__(MX_NT, 2)
 fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ W_dr,
-                 const double2* __restrict__ tw, i64 outer, int n, i64 inner, int P, MixStages S, FuseDev F) {
+                 const double2* __restrict__ tw, i64 outer, int n, i64 inner, int P, const __grid_constant__ MixStages S, FuseDev F) {
     extern __shared__ double smem[];
     const int plane = mpad(P * n) + 1;
     double* sre = smem;                // [P][n], padded index mpad()
@@ -425,39 +498,50 @@ fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const 
     }
 }
 
-// n = product of the returned radices, powers of two first (bits spread evenly over ceil(a/4) passes), then 3 (pairs as
-// 9), 5, 7, 11, 13 ascending; false if n has another prime factor
+// n as a product of radices from {16 15 14 13 12 11 10 9 8 7 6 5 4 3 2} with the fewest passes (ties: the smallest largest
+// radix, then the largest smallest one), powers of two first, the others ascending; false if n has a prime factor > 13
+struct MixBest { int cnt, mx, mn; int r[MX_MAX_STAGES]; };
+bool mix_search(i64 n, int depth, MixBest& cur, MixBest& best) {
+    if (n == 1) {
+        if (best.cnt < 0 || cur.cnt < best.cnt || (cur.cnt == best.cnt && (cur.mx < best.mx || (cur.mx == best.mx && cur.mn > best.mn)))) best = cur;
+        return true;
+    }
+    if (depth >= MX_MAX_STAGES || (best.cnt >= 0 && depth + 1 > best.cnt)) return false;
+    bool any = false;
+    const int last = depth ? cur.r[depth - 1] : 16;
+    for (int r = last; r >= 2; --r) {                       // non-increasing radices: every multiset once
+        if (n % r) continue;
+        MixBest nxt = cur;
+        nxt.r[depth] = r;
+        nxt.cnt = depth + 1;
+        nxt.mx = depth ? cur.mx : r;
+        nxt.mn = r;
+        any |= mix_search(n / r, depth + 1, nxt, best);
+    }
+    return any;
+}
 bool mix_factor(i64 n, MixStages* S) {
     S->nst = 0;
     if (n < 2) return false;
-    int a = 0;
-    while (n % 2 == 0) { n /= 2; ++a; }
-    const int np2 = (a + 3) / 4;
-    for (int i = 0; i < np2; ++i) S->radix[S->nst++] = 1 << ((a + np2 - 1 - i) / np2);
-    int odd[32], no = 0;
-    const int primes[5] = {3, 5, 7, 11, 13};
-    for (int pi = 0; pi < 5; ++pi)
-        while (n % primes[pi] == 0) {
-            n /= primes[pi];
-            if (primes[pi] == 3 && no > 0 && odd[no - 1] == 3) odd[no - 1] = 9;
-            else if (no < 32) odd[no++] = primes[pi];
-        }
-    if (n != 1) return false;
-    // ascending: the 9s formed above sit before a trailing single 3
-    for (int i = 0; i < no; ++i)
-        for (int j = i + 1; j < no; ++j)
-            if (odd[j] < odd[i]) { const int t = odd[i]; odd[i] = odd[j]; odd[j] = t; }
-    if (S->nst + no > MX_MAX_STAGES) return false;
-    for (int i = 0; i < no; ++i) S->radix[S->nst++] = odd[i];
+    i64 m = n;
+    const int primes[6] = {2, 3, 5, 7, 11, 13};
+    for (int pi = 0; pi < 6; ++pi)
+        while (m % primes[pi] == 0) m /= primes[pi];
+    if (m != 1) return false;
+    MixBest cur{}, best{};
+    best.cnt = -1;
+    if (!mix_search(n, 0, cur, best) || best.cnt < 1) return false;
+    int rest[MX_MAX_STAGES], nr = 0;
+    for (int i = 0; i < best.cnt; ++i) {                    // (found in non-increasing order)
+        const int r = best.r[i];
+        if ((r & (r - 1)) == 0) S->radix[S->nst++] = r;
+        else rest[nr++] = r;
+    }
+    for (int i = nr - 1; i >= 0; --i) S->radix[S->nst++] = rest[i];
     return true;
 }
 
-int host_freq_digit(int r, int q) {
-    if ((r & (r - 1)) != 0) return q;
-    int l = 0;
-    while ((1 << l) < r) ++l;
-    return bitrev(q, l);
-}
+int host_freq_digit(int r, int q) { return mx_freq(r, q); }
 
 }  // namespace
 
