@@ -3,17 +3,18 @@
 // Replaces the closure of reference numgrids/diff.py:133-143 (numpy.fft / pocketfft c2c).
 // Tolerance for this path is rel. L-inf <= 1e-11 (BASELINE.json), so FMA is allowed here.
 //
-// Power-of-two n: one CTA keeps P pencil PAIRS in shared memory.  Two real pencils a, b are packed
-// as z = a + i b; because W is Hermitian ((ik)^order with the Nyquist bin zeroed for odd order,
-// diff.py:117-125) the operator F^-1 diag(W) F is real, so Re/Im of the result are D a and D b:
-// one complex transform pair serves two pencils.  Forward = decimation-in-frequency (natural in,
-// bit-reversed out), the multiplier table is pre-permuted to bit-reversed order and pre-scaled by
-// 1/n on upload (exact: n is a power of two), inverse = decimation-in-time (bit-reversed in,
-// natural out): no reordering pass.  Twiddles come from a host-computed fp64 table.
-// HBM traffic 16 B/point (read f, write the real part).
+// Power-of-two n outside the register kernels' range (n < 64, n > 1024; fft2.cu / fft_tile.cu serve 64 ... 1024) and long
+// zero-padded plans: one CTA keeps P pencil PAIRS in shared memory.  Two real pencils a, b are packed as z = a + i b;
+// because W is Hermitian ((ik)^order with the Nyquist bin zeroed for odd order, diff.py:117-125) the operator
+// F^-1 diag(W) F is real, so Re/Im of the result are D a and D b: one complex transform pair serves two pencils.
+// Forward = decimation-in-frequency (natural in, bit-reversed out) in radix-16 register passes, the multiplier table is
+// pre-permuted to bit-reversed order and pre-scaled by 1/n on upload (exact: n is a power of two), inverse =
+// decimation-in-time (bit-reversed in, natural out): no reordering pass.  The last forward pass, the multiplication and
+// the first inverse pass are ONE shared-memory round trip; the factors of a pass are powers of one value of the
+// host-computed fp64 table.  HBM traffic 16 B/point (read f, write the real part).
 //
-// Other n: the dense real matrix D = Re(F^-1 diag(W) F) (what diff.py:145-157 builds) is applied by
-// the ordered contraction kernel in dense.cu with FMA enabled.
+// Other n: the native mixed-radix kernel (fft_mixed.cu), or -- plans created with the dense real matrix
+// D = Re(F^-1 diag(W) F) (what diff.py:145-157 builds) -- the ordered contraction kernel in dense.cu with FMA enabled.
 #include "fft_net.cuh"
 
 namespace {

@@ -8,12 +8,15 @@
 //     the result are D a and D b -- fft.cu's packing);
 //   * forward = in-place decimation in frequency, one pass per factor r of n: the r elements base + q m of a block of
 //     length L = r m go through an r-point DFT held in registers (radix 2/4/8/16: the networks of fft_net.cuh; radix
-//     3/5/7/9/11/13: the symmetric direct form below), output p is multiplied by exp(-2 pi i j p / L) and stored back in
-//     place, so the spectrum ends up in digit-reversed order;
+//     3/5/7/9/11/13: the symmetric direct form below; radix 6/10/12/14/15: prime-factor butterflies of the two), output
+//     p is multiplied by exp(-2 pi i j p / L) -- a power of ONE table value -- and stored back in place, so the spectrum
+//     ends up in digit-reversed order; the host picks the factorisation with the fewest passes;
 //   * the multiplier table is uploaded in that order, pre-divided by n;
 //   * inverse = the conjugate transpose of the forward passes in reverse order: digit-reversed in, natural out -- no
-//     reordering pass anywhere.
-// Power-of-two radices run first (their strides are multiples of the odd part: conflict-free), odd radices last.
+//     reordering pass anywhere; the last forward pass, the multiplication and the first inverse pass share one
+//     shared-memory round trip.
+// Power-of-two radices run first (their strides are multiples of the odd part: conflict-free), the others after them.
+// Measured: profiles/r02b_fft_mixed.txt (54-147 Gpts/s for n = 6 ... 3000).
 // FMA is allowed here (tolerance 1e-11, BASELINE.json); HBM traffic 16 B per point.
 #include "fft_net.cuh"
 
@@ -541,8 +544,6 @@ bool mix_factor(i64 n, MixStages* S) {
     return true;
 }
 
-int host_freq_digit(int r, int q) { return mx_freq(r, q); }
-
 }  // namespace
 
 bool ng_fft_mixed_supported(i64 n) {
@@ -572,7 +573,7 @@ int ng_fft_mixed_tables(ng_plan* p, const double* h_W_re_im, std::vector<double>
             const i64 m = L / S.radix[s];
             const i64 q = rem / m;
             rem -= q * m;
-            k += (i64)host_freq_digit(S.radix[s], (int)q) * mult;
+            k += (i64)mx_freq(S.radix[s], (int)q) * mult;
             mult *= S.radix[s];
             L = m;
         }
