@@ -163,6 +163,8 @@ struct ng_plan {
     int fft_mixed = 0;        // native mixed-radix plan of a non-power-of-two n (fft_mixed.cu): d_W digit-reversed, d_twn
     int mix_nst = 0;
     int mix_radix[12] = {0};
+    int mix_pairs = 1;        // pencil pairs per CTA
+    int mix_pad_shift = 4;    // shared-memory index padding i + (i >> shift), chosen by the plan's bank-conflict model (31: none)
 
     // PK_FDLAP
     FdTables lap[NG_MAX_DIM];

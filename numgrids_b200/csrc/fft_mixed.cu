@@ -29,7 +29,7 @@ constexpr int MX_NT = 256;
 constexpr int MX_MAX_STAGES = 12;
 struct MixStages { int nst; int radix[MX_MAX_STAGES]; };
 
-__device__ __forceinline__ int mpad(int i) { return i + (i >> 4); }   // (see fft.cu: strides of 16 doubles would share a bank)
+__device__ __forceinline__ int mpad(int i, int psh) { return i + (i >> psh); }   // psh = 4: fft.cu's padding (strides of 16 doubles would share a bank); 31: none
 
 // a / d for 0 <= a < 2^22 through a float reciprocal, corrected: the passes below divide by run-time block lengths once
 // per work item, and a 32-bit integer division is ~20 instructions next to a radix-3 butterfly's 30
@@ -302,7 +302,7 @@ __device__ __forceinline__ void small_dft(double2* x) {
 
 // One pass over the blocks of length L (L = R m): see the header.  tw = exp(-2 pi i t / n), t < n.
 template <int R, bool FWD>
-__device__ __noinline__ void mix_pass(double* sre, double* sim, const double2* __restrict__ tw, int n, int P, int L) {
+__device__ __noinline__ void mix_pass(double* sre, double* sim, const double2* __restrict__ tw, int n, int P, int L, int psh) {
     const int m = L / R, per = n / R, items = P * per, step = n / L;
     const float rper = 1.0f / (float)per, rm = 1.0f / (float)m;
     for (int e = threadIdx.x; e < items; e += MX_NT) {
@@ -311,7 +311,7 @@ __device__ __noinline__ void mix_pass(double* sre, double* sim, const double2* _
         const int base = p * n + blk * L + j;
         double2 x[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) { const int i = mpad(base + q * m); x[q] = make_double2(sre[i], sim[i]); }
+        for (int q = 0; q < R; ++q) { const int i = mpad(base + q * m, psh); x[q] = make_double2(sre[i], sim[i]); }
         if (FWD) small_dft<R, true>(x);
         if (j != 0) {                               // (j = 0: trivial factors)
             const double2 w = tw[j * step];         // exp(-2 pi i j / L); the other outputs' factors are its powers
@@ -325,14 +325,14 @@ __device__ __noinline__ void mix_pass(double* sre, double* sim, const double2* _
         }
         if (!FWD) small_dft<R, false>(x);
 #pragma unroll
-        for (int q = 0; q < R; ++q) { const int i = mpad(base + q * m); sre[i] = x[q].x; sim[i] = x[q].y; }
+        for (int q = 0; q < R; ++q) { const int i = mpad(base + q * m, psh); sre[i] = x[q].x; sim[i] = x[q].y; }
     }
 }
 
 // The last forward pass (blocks of R contiguous elements: trivial factors), the multiplication by the digit-reversed
 // multiplier table and the first inverse pass touch the same R elements: one shared-memory round trip instead of three.
 template <int R>
-__device__ __noinline__ void mix_mid(double* sre, double* sim, const double2* __restrict__ W_dr, int n, int P) {
+__device__ __noinline__ void mix_mid(double* sre, double* sim, const double2* __restrict__ W_dr, int n, int P, int psh) {
     const int per = n / R, items = P * per;
     const float rper = 1.0f / (float)per;
     for (int e = threadIdx.x; e < items; e += MX_NT) {
@@ -340,7 +340,7 @@ __device__ __noinline__ void mix_mid(double* sre, double* sim, const double2* __
         const int base = e * R, k0 = base - p * n;
         double2 x[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) { const int i = mpad(base + q); x[q] = make_double2(sre[i], sim[i]); }
+        for (int q = 0; q < R; ++q) { const int i = mpad(base + q, psh); x[q] = make_double2(sre[i], sim[i]); }
         small_dft<R, true>(x);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
@@ -349,47 +349,47 @@ __device__ __noinline__ void mix_mid(double* sre, double* sim, const double2* __
         }
         small_dft<R, false>(x);
 #pragma unroll
-        for (int q = 0; q < R; ++q) { const int i = mpad(base + q); sre[i] = x[q].x; sim[i] = x[q].y; }
+        for (int q = 0; q < R; ++q) { const int i = mpad(base + q, psh); sre[i] = x[q].x; sim[i] = x[q].y; }
     }
 }
-__device__ __forceinline__ void mix_mid_any(int r, double* sre, double* sim, const double2* W_dr, int n, int P) {
+__device__ __forceinline__ void mix_mid_any(int r, double* sre, double* sim, const double2* W_dr, int n, int P, int psh) {
     switch (r) {
-        case 2: mix_mid<2>(sre, sim, W_dr, n, P); break;
-        case 4: mix_mid<4>(sre, sim, W_dr, n, P); break;
-        case 8: mix_mid<8>(sre, sim, W_dr, n, P); break;
-        case 16: mix_mid<16>(sre, sim, W_dr, n, P); break;
-        case 3: mix_mid<3>(sre, sim, W_dr, n, P); break;
-        case 5: mix_mid<5>(sre, sim, W_dr, n, P); break;
-        case 6: mix_mid<6>(sre, sim, W_dr, n, P); break;
-        case 10: mix_mid<10>(sre, sim, W_dr, n, P); break;
-        case 12: mix_mid<12>(sre, sim, W_dr, n, P); break;
-        case 14: mix_mid<14>(sre, sim, W_dr, n, P); break;
-        case 15: mix_mid<15>(sre, sim, W_dr, n, P); break;
-        case 7: mix_mid<7>(sre, sim, W_dr, n, P); break;
-        case 9: mix_mid<9>(sre, sim, W_dr, n, P); break;
-        case 11: mix_mid<11>(sre, sim, W_dr, n, P); break;
-        default: mix_mid<13>(sre, sim, W_dr, n, P); break;
+        case 2: mix_mid<2>(sre, sim, W_dr, n, P, psh); break;
+        case 4: mix_mid<4>(sre, sim, W_dr, n, P, psh); break;
+        case 8: mix_mid<8>(sre, sim, W_dr, n, P, psh); break;
+        case 16: mix_mid<16>(sre, sim, W_dr, n, P, psh); break;
+        case 3: mix_mid<3>(sre, sim, W_dr, n, P, psh); break;
+        case 5: mix_mid<5>(sre, sim, W_dr, n, P, psh); break;
+        case 6: mix_mid<6>(sre, sim, W_dr, n, P, psh); break;
+        case 10: mix_mid<10>(sre, sim, W_dr, n, P, psh); break;
+        case 12: mix_mid<12>(sre, sim, W_dr, n, P, psh); break;
+        case 14: mix_mid<14>(sre, sim, W_dr, n, P, psh); break;
+        case 15: mix_mid<15>(sre, sim, W_dr, n, P, psh); break;
+        case 7: mix_mid<7>(sre, sim, W_dr, n, P, psh); break;
+        case 9: mix_mid<9>(sre, sim, W_dr, n, P, psh); break;
+        case 11: mix_mid<11>(sre, sim, W_dr, n, P, psh); break;
+        default: mix_mid<13>(sre, sim, W_dr, n, P, psh); break;
     }
 }
 
 template <bool FWD>
-__device__ __forceinline__ void mix_pass_any(int r, double* sre, double* sim, const double2* tw, int n, int P, int L) {
+__device__ __forceinline__ void mix_pass_any(int r, double* sre, double* sim, const double2* tw, int n, int P, int L, int psh) {
     switch (r) {
-        case 2: mix_pass<2, FWD>(sre, sim, tw, n, P, L); break;
-        case 4: mix_pass<4, FWD>(sre, sim, tw, n, P, L); break;
-        case 8: mix_pass<8, FWD>(sre, sim, tw, n, P, L); break;
-        case 16: mix_pass<16, FWD>(sre, sim, tw, n, P, L); break;
-        case 3: mix_pass<3, FWD>(sre, sim, tw, n, P, L); break;
-        case 5: mix_pass<5, FWD>(sre, sim, tw, n, P, L); break;
-        case 6: mix_pass<6, FWD>(sre, sim, tw, n, P, L); break;
-        case 10: mix_pass<10, FWD>(sre, sim, tw, n, P, L); break;
-        case 12: mix_pass<12, FWD>(sre, sim, tw, n, P, L); break;
-        case 14: mix_pass<14, FWD>(sre, sim, tw, n, P, L); break;
-        case 15: mix_pass<15, FWD>(sre, sim, tw, n, P, L); break;
-        case 7: mix_pass<7, FWD>(sre, sim, tw, n, P, L); break;
-        case 9: mix_pass<9, FWD>(sre, sim, tw, n, P, L); break;
-        case 11: mix_pass<11, FWD>(sre, sim, tw, n, P, L); break;
-        default: mix_pass<13, FWD>(sre, sim, tw, n, P, L); break;
+        case 2: mix_pass<2, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 4: mix_pass<4, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 8: mix_pass<8, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 16: mix_pass<16, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 3: mix_pass<3, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 5: mix_pass<5, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 6: mix_pass<6, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 10: mix_pass<10, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 12: mix_pass<12, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 14: mix_pass<14, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 15: mix_pass<15, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 7: mix_pass<7, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 9: mix_pass<9, FWD>(sre, sim, tw, n, P, L, psh); break;
+        case 11: mix_pass<11, FWD>(sre, sim, tw, n, P, L, psh); break;
+        default: mix_pass<13, FWD>(sre, sim, tw, n, P, L, psh); break;
     }
 }
 
@@ -397,9 +397,9 @@ __device__ __forceinline__ void mix_pass_any(int r, double* sre, double* sim, co
 template <bool LAST, bool FUSED>
 __global__ void __launch_bounds__(MX_NT, 2)
 fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const double2* __restrict__ W_dr,
-                 const double2* __restrict__ tw, i64 outer, int n, i64 inner, int P, const __grid_constant__ MixStages S, FuseDev F) {
+                 const double2* __restrict__ tw, i64 outer, int n, i64 inner, int P, int psh, const __grid_constant__ MixStages S, FuseDev F) {
     extern __shared__ double smem[];
-    const int plane = mpad(P * n) + 1;
+    const int plane = mpad(P * n, psh) + 1;
     double* sre = smem;                // [P][n], padded index mpad()
     double* sim = smem + plane;
     // a pencil with a non-finite sample is transformed as zeros and comes out all-NaN, as numpy.fft makes it, without
@@ -453,7 +453,7 @@ fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const 
             else      { k = e >> lp; pl = e & (2 * P - 1); }
             double x = v[u];
             if (ng_nonfinite(x)) { sbad[pl] = 1; x = 0.0; }
-            ((pl & 1) ? sim : sre)[mpad((pl >> 1) * n + k)] = x;
+            ((pl & 1) ? sim : sre)[mpad((pl >> 1) * n + k, psh)] = x;
         }
     }
     __syncthreads();
@@ -462,11 +462,11 @@ fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const 
     {
         int L = n;
         for (int s = 0; s + 1 < S.nst; ++s) {
-            mix_pass_any<true>(S.radix[s], sre, sim, tw, n, P, L);
+            mix_pass_any<true>(S.radix[s], sre, sim, tw, n, P, L, psh);
             L /= S.radix[s];
             __syncthreads();
         }
-        mix_mid_any(S.radix[S.nst - 1], sre, sim, W_dr, n, P);
+        mix_mid_any(S.radix[S.nst - 1], sre, sim, W_dr, n, P, psh);
         __syncthreads();
     }
     // ---- inverse: the adjoint passes in reverse order
@@ -474,7 +474,7 @@ fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const 
         int L = S.radix[S.nst - 1];
         for (int s = S.nst - 2; s >= 0; --s) {
             L *= S.radix[s];
-            mix_pass_any<false>(S.radix[s], sre, sim, tw, n, P, L);
+            mix_pass_any<false>(S.radix[s], sre, sim, tw, n, P, L, psh);
             __syncthreads();
         }
     }
@@ -491,7 +491,7 @@ fft_mixed_kernel(const double* __restrict__ in, double* __restrict__ out, const 
             if (!pvalid) break;
             lin = pbase + (i64)k * inner;
         }
-        double d = ((pl & 1) ? sim : sre)[mpad((pl >> 1) * n + k)];
+        double d = ((pl & 1) ? sim : sre)[mpad((pl >> 1) * n + k, psh)];
         if (sbad[pl]) d = ng_nan();
         if (FUSED) {
             const Idx4 ix = unravel4(lin, F.shape);
@@ -544,6 +544,91 @@ bool mix_factor(i64 n, MixStages* S) {
     return true;
 }
 
+// ---- plan-time choices: pencil pairs per CTA and the shared-memory padding -------------------------------------------
+
+// Pencil pairs per CTA: a power of two (off the contiguous axis 2P divides the block size) within 64 KB of shared memory
+// (three CTAs per SM), chosen for the fewest block-wide iterations per pencil: a pass of radix r has P n / r work items
+// for 256 threads, and e.g. n = 360 = 8 * 5 * 9 leaves 40 % of the last iteration idle at P = 4.
+int mix_choose_pairs(int n, const MixStages& S, i64 npencil, bool last) {
+    int P = 1;
+    double best = 1e300;
+    for (int c = 1; c <= 1024; c *= 2) {
+        if (c > 1 && ((i64)(2 * c) * 2 > npencil || (size_t)c * n * 18 > 64 * 1024 || (!last && c > MX_NT / 2))) break;
+        double cost = 6.0;                                  // per-CTA fixed part (launch, table init, barriers)
+        for (int s = 0; s < S.nst; ++s) {
+            const int r = S.radix[s];
+            const int it = (int)(((i64)c * n / r + MX_NT - 1) / MX_NT);
+            cost += (double)it * r * (s + 1 == S.nst ? 1.5 : 2.0);   // (the fused middle pass runs once, the others twice)
+        }
+        cost += 2.0 * (((i64)2 * c * n + MX_NT - 1) / MX_NT);              // load + store
+        cost /= c;
+        if (cost < best * 0.97) { best = cost; P = c; }
+    }
+    return P;
+}
+
+// Shared-memory wavefronts of one 64-bit access of a warp: the two half-warps are served separately, each in as many
+// passes as its most contended 8-byte bank has distinct words.
+int mix_wavefronts(const int* word, int lanes) {
+    int total = 0;
+    for (int h = 0; h < lanes; h += 16) {
+        int worst = 0;
+        for (int b = 0; b < 16; ++b) {
+            int distinct = 0, seen[16];
+            for (int l = h; l < h + 16 && l < lanes; ++l) {
+                if ((word[l] & 15) != b) continue;
+                bool dup = false;
+                for (int k = 0; k < distinct; ++k) dup |= seen[k] == word[l];
+                if (!dup) seen[distinct++] = word[l];
+            }
+            if (distinct > worst) worst = distinct;
+        }
+        total += worst;
+    }
+    return total;
+}
+
+// Bank-conflict model of one CTA (the kernel's own index maps) for the padding i + (i >> psh).  Lengths that are not
+// powers of two put the passes' bases anywhere, and fft.cu's i + (i >> 4) -- made for strides of 16 -- then costs every
+// unaligned unit-stride access one conflict per half-warp (ncu at n = 1000: 231 M conflicts, 1.6 x the wavefronts of a
+// conflict-free kernel); which shift is best depends on n, its factors and P, so the plan asks this model.
+double mix_conflict_score(int n, const MixStages& S, int P, bool last, int psh) {
+    auto pad = [&](int i) { return i + (i >> psh); };
+    const int plane = pad(P * n) + 1;
+    double score = 0.0;
+    int word[32];
+    // load / store phases: lane -> (pencil, sample)
+    const int total = 2 * P * n;
+    int lp = 0;
+    while ((1 << lp) < 2 * P) ++lp;
+    for (int e0 = 0; e0 < total; e0 += 32) {
+        int lanes = 0;
+        for (int e = e0; e < e0 + 32 && e < total; ++e) {
+            const int pl = last ? e / n : (e & (2 * P - 1)), k = last ? e - pl * n : (e >> lp);
+            word[lanes++] = ((pl & 1) ? plane : 0) + pad((pl >> 1) * n + k);
+        }
+        score += 2.0 * mix_wavefronts(word, lanes);
+    }
+    // passes: 2 arrays x (load + store) = 4 accesses of the same pattern per element; every pass but the last runs twice
+    int L = n;
+    for (int s = 0; s < S.nst; ++s) {
+        const int r = S.radix[s], m = L / r, per = n / r, items = P * per;
+        const double weight = s + 1 == S.nst ? 4.0 : 8.0;
+        // (work items are spread over the block's 8 warps in rounds of 256; every warp sees 32 consecutive items)
+        for (int e0 = 0; e0 < items; e0 += 32)
+            for (int q = 0; q < r; ++q) {
+                int lanes = 0;
+                for (int e = e0; e < e0 + 32 && e < items; ++e) {
+                    const int pp = e / per, b = e - pp * per, blk = b / m, j = b - blk * m;
+                    word[lanes++] = pad(pp * n + blk * L + j + q * m);
+                }
+                score += weight * mix_wavefronts(word, lanes);
+            }
+        L = m;
+    }
+    return score;
+}
+
 }  // namespace
 
 bool ng_fft_mixed_supported(i64 n) {
@@ -564,6 +649,16 @@ int ng_fft_mixed_tables(ng_plan* p, const double* h_W_re_im, std::vector<double>
     p->fft_len = (int)n;
     p->mix_nst = S.nst;
     for (int s = 0; s < S.nst; ++s) p->mix_radix[s] = S.radix[s];
+    {
+        const bool last = p->inner == 1;
+        p->mix_pairs = mix_choose_pairs((int)n, S, p->outer * p->inner, last);
+        double best = 1e300;
+        const int shifts[5] = {31, 3, 4, 5, 6};              // 31: no padding
+        for (int k = 0; k < 5; ++k) {
+            const double sc = mix_conflict_score((int)n, S, p->mix_pairs, last, shifts[k]);
+            if (sc < best * 0.98) { best = sc; p->mix_pad_shift = shifts[k]; }
+        }
+    }
     Wdr.assign((size_t)(2 * n), 0.0);
     tw.assign((size_t)(2 * n), 0.0);
     for (i64 i = 0; i < n; ++i) {
@@ -594,26 +689,10 @@ int ng_fft_mixed_launch(const ng_plan* p, const double* in, double* out, const F
     const int n = (int)p->n;
     const i64 npencil = p->outer * p->inner;
     const bool last = p->inner == 1;
-    // pencil pairs per CTA: a power of two (off the contiguous axis 2P divides the block size) within 64 KB of shared
-    // memory (three CTAs per SM), chosen for the fewest block-wide iterations per pencil: a pass of radix r has P n / r
-    // work items for 256 threads, and e.g. n = 360 = 8 * 5 * 9 leaves 40 % of the last iteration idle at P = 4
-    int P = 1;
-    {
-        double best = 1e300;
-        for (int c = 1; c <= 1024; c *= 2) {
-            if (c > 1 && ((i64)(2 * c) * 2 > npencil || (size_t)c * n * 17 > 64 * 1024 || (!last && c > MX_NT / 2))) break;
-            double cost = 6.0;                                  // per-CTA fixed part (launch, table init, barriers)
-            for (int s = 0; s < p->mix_nst; ++s) {
-                const int r = p->mix_radix[s];
-                const int it = (int)(((i64)c * n / r + MX_NT - 1) / MX_NT);
-                cost += (double)it * r * (s + 1 == p->mix_nst ? 1.5 : 2.0);   // (the fused middle pass runs once, the others twice)
-            }
-            cost += 2.0 * (((i64)2 * c * n + MX_NT - 1) / MX_NT);              // load + store
-            cost /= c;
-            if (cost < best * 0.97) { best = cost; P = c; }
-        }
-    }
-    const size_t smem = (size_t)((P * n + (P * n >> 4) + 1) * 2) * sizeof(double) + (size_t)2 * P * sizeof(int);
+    const int P = p->mix_pairs;                              // pencil pairs per CTA and padding: chosen with the plan
+    const int psh_env = (int)NG_ENV_INT("NG_FFT_MIXED_PAD", 0);
+    const int psh = psh_env >= 3 ? psh_env : p->mix_pad_shift;
+    const size_t smem = (size_t)((P * n + (P * n >> 3) + 1) * 2) * sizeof(double) + (size_t)2 * P * sizeof(int);   // (room for any shift >= 3)
     const i64 nblk = (npencil + 2 * P - 1) / (2 * P);
     MixStages S;
     S.nst = p->mix_nst;
@@ -622,7 +701,7 @@ int ng_fft_mixed_launch(const ng_plan* p, const double* in, double* out, const F
     do {                                                                                                    \
         NG_FUNC_SMEM(200 * 1024, fft_mixed_kernel<LA, FU>);                                                 \
         fft_mixed_kernel<LA, FU><<<(unsigned)nblk, MX_NT, smem, st>>>(                                      \
-            in, out, (const double2*)p->d_W, (const double2*)p->d_twn, p->outer, n, p->inner, P, S, F);     \
+            in, out, (const double2*)p->d_W, (const double2*)p->d_twn, p->outer, n, p->inner, P, psh, S, F);     \
     } while (0)
     if (last) { if (F.any) NG_MIX_GO(true, true); else NG_MIX_GO(true, false); }
     else      { if (F.any) NG_MIX_GO(false, true); else NG_MIX_GO(false, false); }
