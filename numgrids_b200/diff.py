@@ -257,6 +257,15 @@ class FFTDiff(GridDiff):
             self._dense = _tables.fft_dense_matrix(self._W_1d)
         return self._dense
 
+    @staticmethod
+    def _padded_is_faster(n: int) -> bool:
+        """Measured on a B200 (profiles/r02b_fft_mixed.txt): the zero-padded transform runs at about 1.55 n / 0.55 n /
+        0.33 n Gpts/s on its 256 / 512 / 1024-point register kernels (n = 65..128 / ..256 / ..512) when n is even -- an odd n
+        misses the persistent ring kernel and halves that -- against 85-105 Gpts/s for the native mixed-radix transform."""
+        if n % 2:
+            return False
+        return not 128 < n < 182
+
     def _make_plan(self, shape=None) -> _lib.Plan:
         return self._plan_for(self._W_1d, self.order, shape, self._dense_matrix)
 
@@ -286,9 +295,9 @@ class FFTDiff(GridDiff):
         out = C.c_void_p()
         pow2 = _tables.is_pow2(n) and n <= 8192
         # Any other length (NONPOW2 = "auto"):
-        #   * first and second derivatives with 65 <= n <= 512: zero-padded power-of-two transform on the two-pass
-        #     register kernels (O(n log n) like the reference's pocketfft, 100-160 Gpts/s; as close to numpy.fft as the
-        #     native transform: see PADDED_ORDERS);
+        #   * first and second derivatives with 65 <= n <= 512 (n even, and not just above 128: _padded_is_faster):
+        #     zero-padded power-of-two transform on the two-pass register kernels (O(n log n) like the reference's
+        #     pocketfft, 100-160 Gpts/s; as close to numpy.fft as the native transform: see PADDED_ORDERS);
         #   * otherwise, n = 2^a 3^b 5^c 7^d 11^e 13^f from MIXED_MIN_POINTS on: the library's native n-point mixed-radix
         #     transform (any order; 55-110 Gpts/s, faster than the padded transform beyond n = 512 and than the dense
         #     contraction everywhere);
@@ -299,7 +308,7 @@ class FFTDiff(GridDiff):
                     and n >= (self.PADDED_MIN_POINTS if prefer_native else self.MIXED_MIN_POINTS))
         pad_ok = not pow2 and order in self.PADDED_ORDERS and n >= self.PADDED_MIN_POINTS
         if mixed_ok and pad_ok and self.NONPOW2 == "auto" and not prefer_native:
-            mixed_ok = n > self.PADDED_FAST_MAX
+            mixed_ok = n > self.PADDED_FAST_MAX or not self._padded_is_faster(n)
         if mixed_ok:
             _lib.check(lib.ng_fft_plan_create(len(shp), shp_p, self.axis_index, W_p, None, C.byref(out)),
                        "ng_fft_plan_create")
