@@ -257,6 +257,28 @@ class FFTDiff(GridDiff):
             self._dense = _tables.fft_dense_matrix(self._W_1d)
         return self._dense
 
+    @classmethod
+    def route(cls, n: int, order: int, prefer_native: bool = False) -> str:
+        """Which transform serves a periodic axis of n points: "pow2", "mixed", "padded" or "dense".
+
+        Powers of two (<= 8192): the register / shared-memory FFT kernels.  Any other length (NONPOW2 = "auto"):
+          * first and second derivatives with 65 <= n <= 512 (n even, and not just above 128: _padded_is_faster):
+            zero-padded power-of-two transform on the two-pass register kernels (O(n log n) like the reference's
+            pocketfft, 100-160 Gpts/s; as close to numpy.fft as the native transform: see PADDED_ORDERS);
+          * otherwise, n = 2^a 3^b 5^c 7^d 11^e 13^f: the library's native n-point mixed-radix transform (any order;
+            60-155 Gpts/s, faster than the padded transform beyond n = 512 and than the dense contraction everywhere);
+          * what is left (other prime factors): padded for orders 1-2, else the dense O(n^2) contraction.
+        "native" -- and prefer_native, which the curvilinear composites pass (make_composite_plan) -- takes the
+        mixed-radix transform wherever it exists, "padded" never does."""
+        if _tables.is_pow2(n) and n <= 8192:
+            return "pow2"
+        mixed = cls.NONPOW2 != "padded" and _tables.fft_mixed_supported(n) and n >= cls.MIXED_MIN_POINTS
+        padded = order in cls.PADDED_ORDERS and n >= cls.PADDED_MIN_POINTS
+        if (mixed and padded and cls.NONPOW2 == "auto" and not prefer_native
+                and n <= cls.PADDED_FAST_MAX and cls._padded_is_faster(n)):
+            mixed = False
+        return "mixed" if mixed else "padded" if padded else "dense"
+
     @staticmethod
     def _padded_is_faster(n: int) -> bool:
         """Measured on a B200 (profiles/r02b_fft_mixed.txt): the zero-padded transform runs at about 1.55 n / 0.55 n /
@@ -293,22 +315,8 @@ class FFTDiff(GridDiff):
         Wk, W_p = _lib.as_f64(W)
         n = len(self.axis)
         out = C.c_void_p()
-        pow2 = _tables.is_pow2(n) and n <= 8192
-        # Any other length (NONPOW2 = "auto"):
-        #   * first and second derivatives with 65 <= n <= 512 (n even, and not just above 128: _padded_is_faster):
-        #     zero-padded power-of-two transform on the two-pass register kernels (O(n log n) like the reference's
-        #     pocketfft, 100-160 Gpts/s; as close to numpy.fft as the native transform: see PADDED_ORDERS);
-        #   * otherwise, n = 2^a 3^b 5^c 7^d 11^e 13^f from MIXED_MIN_POINTS on: the library's native n-point mixed-radix
-        #     transform (any order; 55-110 Gpts/s, faster than the padded transform beyond n = 512 and than the dense
-        #     contraction everywhere);
-        #   * what is left (other prime factors): padded for orders 1-2, else the dense O(n^2) contraction.
-        # "native" prefers the mixed-radix transform wherever it exists (as the curvilinear composites do:
-        # make_composite_plan), "padded" never uses it.
-        mixed_ok = (not pow2 and self.NONPOW2 != "padded" and _tables.fft_mixed_supported(n)
-                    and n >= (self.PADDED_MIN_POINTS if prefer_native else self.MIXED_MIN_POINTS))
-        pad_ok = not pow2 and order in self.PADDED_ORDERS and n >= self.PADDED_MIN_POINTS
-        if mixed_ok and pad_ok and self.NONPOW2 == "auto" and not prefer_native:
-            mixed_ok = n > self.PADDED_FAST_MAX or not self._padded_is_faster(n)
+        route = self.route(n, order, prefer_native)
+        pow2, mixed_ok, pad_ok = route == "pow2", route == "mixed", route == "padded"
         if mixed_ok:
             _lib.check(lib.ng_fft_plan_create(len(shp), shp_p, self.axis_index, W_p, None, C.byref(out)),
                        "ng_fft_plan_create")

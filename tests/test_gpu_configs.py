@@ -569,7 +569,6 @@ def test_mixed_radix_transform_vs_oracle(gpu_ready, n, monkeypatch):
     from numgrids_b200.diff import FFTDiff
     monkeypatch.setattr(FFTDiff, "NONPOW2", "native")
     monkeypatch.setattr(FFTDiff, "MIXED_MIN_POINTS", 3)
-    monkeypatch.setattr(FFTDiff, "PADDED_MIN_POINTS", 3)       # (the composites' threshold for the native transform)
     p = ng.create_axis(A.EQUIDISTANT_PERIODIC, n, 0.0, 2 * np.pi)
     rng = np.random.default_rng(n)
     small = n <= 400

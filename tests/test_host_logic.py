@@ -236,3 +236,23 @@ def test_mixed_radix_lengths():
     no = [1, 2, 4, 64, 1024, 8192, 17, 34, 118, 2 * 59, 19 * 5, 8193, 9000, 10 ** 4]
     assert all(_tables.fft_mixed_supported(n) for n in yes)
     assert not any(_tables.fft_mixed_supported(n) for n in no)
+
+
+def test_periodic_axis_routing():
+    """FFTDiff.route: which transform serves a periodic axis (numgrids/diff.py:133-143 is one numpy.fft call for all of them)."""
+    from numgrids_b200.diff import FFTDiff
+    r = FFTDiff.route
+    assert FFTDiff.NONPOW2 == "auto"
+    assert [r(n, 1) for n in (2, 64, 1024, 8192)] == ["pow2"] * 4
+    # plain first / second derivatives: zero-padded where measured faster (even n, 65..512, not just above 128)
+    assert [r(n, 1) for n in (96, 100, 200, 360, 500)] == ["padded"] * 5
+    assert [r(n, 2) for n in (96, 500)] == ["padded"] * 2
+    assert [r(n, 1) for n in (6, 45, 60, 65, 81, 150, 180, 1000, 1536, 3000, 6000)] == ["mixed"] * 11
+    # higher orders and the composites: native wherever the length factors into 2 3 5 7 11 13
+    assert [r(n, 3) for n in (12, 96, 360, 1000)] == ["mixed"] * 4
+    assert [r(n, 1, prefer_native=True) for n in (24, 100, 360, 500)] == ["mixed"] * 4
+    # a prime factor above 13: padded for orders 1-2 from 65 points on, else the dense contraction
+    assert [r(n, 1) for n in (118, 177, 1018)] == ["padded"] * 3
+    assert [r(n, 1, prefer_native=True) for n in (118,)] == ["padded"]
+    assert [r(n, 3) for n in (118, 34)] == ["dense"] * 2
+    assert r(34, 1) == "dense"
