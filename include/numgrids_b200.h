@@ -122,6 +122,12 @@ int ng_fft_plan_create(int ndim, const int64_t* shape, int axis,
 int ng_fft_plan_create_padded(int ndim, const int64_t* shape, int axis, int64_t m, const double* h_Wm_re_im,
                               ng_plan** out);
 
+/* The radices of the native mixed-radix transform of a non-power-of-two length n (at most 12, each from
+ * {2..16} \ {primes above 13}, product n, fewest passes; powers of two first): what ng_fft_plan_create(..., h_D = NULL)
+ * runs for this n.  NG_EINVAL if n has no such plan (a power of two, a prime factor above 13, n > 8192).  Host only:
+ * needs no device. */
+int ng_fft_mixed_radices(int64_t n, int* radices12, int* count);
+
 /* ---- apply ------------------------------------------------------------------------------------
  * GridDiff.__call__ (numgrids/diff.py:48-61).  d_out must not alias d_in. */
 int ng_apply(const ng_plan* plan, const double* d_in, double* d_out, void* stream);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ng_cheb_plan_create": (C.c_int, [C.c_int, _I64, C.c_int, _D, C.c_int, _PP]),
     "ng_fft_plan_create": (C.c_int, [C.c_int, _I64, C.c_int, _D, _D, _PP]),
     "ng_fft_plan_create_padded": (C.c_int, [C.c_int, _I64, C.c_int, C.c_int64, _D, _PP]),
+    "ng_fft_mixed_radices": (C.c_int, [C.c_int64, _I32, _I32]),
     "ng_apply": (C.c_int, [_P, _P, _P, _P]),
     "ng_apply_fused": (C.c_int, [_P, _P, _P, C.POINTER(NgFuse), _P]),
     "ng_apply_batch": (C.c_int, [_P, _P, _P, C.c_int64, _P]),

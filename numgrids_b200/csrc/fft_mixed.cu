@@ -636,6 +636,20 @@ bool ng_fft_mixed_supported(i64 n) {
     return n >= 3 && n <= NG_FFT_MIXED_MAX && (n & (n - 1)) != 0 && mix_factor(n, &S);
 }
 
+extern "C" int ng_fft_mixed_radices(int64_t n, int* radices12, int* count) {
+    NG_REQUIRE(radices12 != nullptr && count != nullptr, "output pointers are NULL");
+    *count = 0;
+    MixStages S;
+    if (!ng_fft_mixed_supported(n) || !mix_factor(n, &S)) {
+        ng_set_error("n = %lld has no mixed-radix plan (a power of two, a prime factor above 13, or n > %d)", (long long)n,
+                     NG_FFT_MIXED_MAX);
+        return NG_EINVAL;
+    }
+    for (int s = 0; s < S.nst; ++s) radices12[s] = S.radix[s];
+    *count = S.nst;
+    return NG_OK;
+}
+
 // Host tables of the native n-point plan (api.cu uploads them): multipliers / n in digit-reversed order, the full twiddle
 // circle; the stage list goes into the plan.
 int ng_fft_mixed_tables(ng_plan* p, const double* h_W_re_im, std::vector<double>& Wdr, std::vector<double>& tw) {

@@ -256,3 +256,33 @@ def test_periodic_axis_routing():
     assert [r(n, 1, prefer_native=True) for n in (118,)] == ["padded"]
     assert [r(n, 3) for n in (118, 34)] == ["dense"] * 2
     assert r(34, 1) == "dense"
+
+
+def test_mixed_radix_factorisation():
+    """ng_fft_mixed_radices (host only): the passes of the native transform -- product n, allowed radices, powers of two
+    first, as few passes as any factorisation into radices <= 16 allows -- and the lengths it refuses."""
+    import ctypes as C
+    from numgrids_b200 import _lib, _tables
+    lib = _lib.load()
+    allowed = set(range(2, 17))
+
+    def radices(n):
+        buf, cnt = (C.c_int32 * 12)(), C.c_int32(0)
+        rc = lib.ng_fft_mixed_radices(n, buf, C.byref(cnt))
+        return rc, list(buf[:cnt.value])
+
+    def fewest(n, memo={1: 0}):
+        if n not in memo:
+            memo[n] = 1 + min(fewest(n // r) for r in range(2, 17) if n % r == 0)
+        return memo[n]
+
+    for n in (6, 12, 24, 45, 48, 60, 96, 100, 182, 200, 360, 500, 1000, 1536, 2187, 2310, 3000, 6000, 8190):
+        rc, rs = radices(n)
+        assert rc == 0 and int(np.prod(rs)) == n and set(rs) <= allowed, (n, rs)
+        assert len(rs) == fewest(n), (n, rs)
+        pow2 = [r for r in rs if r & (r - 1) == 0]
+        assert rs[:len(pow2)] == pow2, (n, rs)
+    assert radices(1000)[1] == [10, 10, 10] and radices(1536)[1] == [16, 8, 12] and radices(360)[1] == [8, 5, 9]
+    for n in (1, 2, 64, 1024, 17, 34, 118, 8193, 9000):
+        assert not _tables.fft_mixed_supported(n)
+        assert radices(n)[0] != 0
