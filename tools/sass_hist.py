@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "numgrids_b200", "build")
 HOT = [("fdlap3d.o", r"fdlap3d_ring2_kernel"), ("curvlap3d.o", r"curvlap3d_kernel"), ("fd.o", r"fd_march_kernel"),
        ("fd_row.o", r"fd_row_kernel"), ("dense.o", r"dense_fast_kernel"), ("fft2.o", r"fft2pass_ring_kernel"),
-       ("fft2.o", r"fft2pass_kernel"), ("fft_tile.o", r"fft_tile_kernel"), ("slab.o", r"slab_"), ("quad.o", r"quad_partial_kernel"), ("transpose.o", r"slab_block_copy_kernel")]
+       ("fft2.o", r"fft2pass_kernel"), ("fft_tile.o", r"fft_tile_kernel"), ("fft.o", r"fft_diff_kernel"), ("fft_mixed.o", r"fft_mixed_kernel"), ("fd_tile.o", r"fd_tile_kernel"), ("slab.o", r"slab_"), ("quad.o", r"quad_partial_kernel"), ("transpose.o", r"slab_block_copy_kernel")]
 KEY = ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "DMUL", "DADD", "DFMA", "HMMA", "DMMA", "UTCMMA", "LDS", "STS", "LDG",
        "STG", "SHFL", "ATOMS", "BAR", "MUFU", "LDL", "STL")
 
