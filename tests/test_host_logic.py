@@ -286,3 +286,9 @@ def test_mixed_radix_factorisation():
     for n in (1, 2, 64, 1024, 17, 34, 118, 8193, 9000):
         assert not _tables.fft_mixed_supported(n)
         assert radices(n)[0] != 0
+    # the host layer's rule and the library's agree on every length
+    for n in range(1, 8300):
+        rc, rs = radices(n)
+        assert (rc == 0) == _tables.fft_mixed_supported(n), n
+        if rc == 0:
+            assert int(np.prod(rs)) == n and len(rs) == fewest(n), (n, rs)
